@@ -1,0 +1,161 @@
+"""blingfire_b200 -- Python binding of the B200-native drop-in for BlingFire's TextToIds path.
+
+Mirrors the reference's own ctypes wrapper for this path (dist-pypi/blingfire/__init__.py:
+229-253: load_model / free_model / text_to_ids, :85-122: text_to_words[_with_model]) with the
+same names, argument meaning and return conventions, over the C ABI declared in
+include/blingfiretokdll_b200.h.  Additive: the batch calls (text_to_ids_batch*), which the
+reference does not have.
+
+The CUDA library is mandatory: importing works anywhere, but the first call that needs it
+raises if lib/libblingfiretokdll.so is missing -- there is no CPU path to fall back to.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_int, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libblingfiretokdll.so")
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library (ctypes.CDLL).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "blingfire_b200 has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.GetBlingFireTokVersion.restype = c_int
+        L.LoadModel.restype = c_void_p
+        L.LoadModel.argtypes = [c_char_p]
+        L.SetModel.restype = c_void_p
+        L.SetModel.argtypes = [c_char_p, c_int]
+        L.FreeModel.restype = c_int
+        L.FreeModel.argtypes = [c_void_p]
+        for name in ("TextToIds", "TextToIds_wp", "TextToIds_sp"):
+            f = getattr(L, name)
+            f.restype = c_int
+            f.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_int, c_int]
+        L.TextToWords.restype = c_int
+        L.TextToWords.argtypes = [c_char_p, c_int, c_void_p, c_int]
+        L.TextToWordsWithModel.restype = c_int
+        L.TextToWordsWithModel.argtypes = [c_char_p, c_int, c_void_p, c_int, c_void_p]
+        L.TextToIdsBatch.restype = c_int64
+        L.TextToIdsBatch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int]
+        L.TextToIdsBatchCsr.restype = c_int64
+        L.TextToIdsBatchCsr.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int]
+        L.TextToIdsBatchDevice.restype = c_int
+        L.TextToIdsBatchDevice.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]
+        L.BlingFireB200LastError.restype = c_char_p
+        L.BlingFireB200KernelLaunches.restype = c_int64
+        L.BlingFireB200ModelEngine.restype = c_int
+        L.BlingFireB200ModelEngine.argtypes = [c_void_p]
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().BlingFireB200LastError().decode("utf-8", "replace")
+
+
+def kernel_launches():
+    return int(lib().BlingFireB200KernelLaunches())
+
+
+def get_blingfiretok_version():
+    return lib().GetBlingFireTokVersion()
+
+
+def load_model(file_name):
+    """dist-pypi/blingfire/__init__.py:229-234.  Returns a handle; raises on failure
+    (the reference aborts the process on a missing file; a None handle would only defer the error)."""
+    h = lib().LoadModel(file_name.encode("utf-8"))
+    if not h:
+        raise RuntimeError(f"LoadModel({file_name!r}) failed: {last_error()}")
+    return h
+
+
+def free_model(h):
+    lib().FreeModel(c_void_p(h))
+
+
+def text_to_ids(h, s, max_len, unk=0, no_padding=False):
+    """dist-pypi/blingfire/__init__.py:243-253: zero-padded uint32 array of max_len ids
+    (or just the produced ids with no_padding=True)."""
+    s_bytes = s.encode("utf-8") if isinstance(s, str) else bytes(s)
+    o = np.zeros(max_len, dtype=np.int32)
+    t_count = lib().TextToIds(c_void_p(h), s_bytes, len(s_bytes), o.ctypes.data, max_len, unk)
+    out_count = min(max_len, t_count) if no_padding else max_len
+    return o.view(np.uint32)[:out_count]
+
+
+def text_to_words_with_model(h, s):
+    """dist-pypi/blingfire/__init__.py:105-122."""
+    s_bytes = s.encode("utf-8")
+    o_cap = len(s_bytes) * 3 + 1
+    o = ctypes.create_string_buffer(o_cap)
+    n = lib().TextToWordsWithModel(s_bytes, len(s_bytes), o, o_cap, c_void_p(h) if h else None)
+    if n < 0 or n > o_cap:
+        return ""
+    return o.value.decode("utf-8")
+
+
+def text_to_words(s):
+    """dist-pypi/blingfire/__init__.py:85-102 (default word-breaking model)."""
+    return text_to_words_with_model(None, s)
+
+
+# ---- additive batch API --------------------------------------------------------------------
+
+def make_csr(docs):
+    """Concatenates an iterable of bytes/str documents into (uint8 buffer, int64 offsets)."""
+    bs = [d.encode("utf-8") if isinstance(d, str) else bytes(d) for d in docs]
+    offsets = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        np.cumsum([len(b) for b in bs], out=offsets[1:])
+    buf = np.frombuffer(b"".join(bs), dtype=np.uint8) if bs else np.zeros(0, np.uint8)
+    return buf, offsets
+
+
+def text_to_ids_batch(h, docs, max_len, unk=0):
+    """Row-major batch: returns (ids[n_docs, max_len] int32 zero-padded, counts[n_docs] int32).
+    Row i / counts[i] equal the reference's TextToIds on document i."""
+    buf, offsets = docs if isinstance(docs, tuple) else make_csr(docs)
+    n = len(offsets) - 1
+    ids = np.zeros((n, max_len), dtype=np.int32)
+    counts = np.zeros(n, dtype=np.int32)
+    buf = np.ascontiguousarray(buf)
+    r = lib().TextToIdsBatch(c_void_p(h), buf.ctypes.data, offsets.ctypes.data, n, ids.ctypes.data,
+                             counts.ctypes.data, max_len, unk)
+    if r < 0:
+        raise RuntimeError(f"TextToIdsBatch failed: {last_error()}")
+    return ids, counts
+
+
+def text_to_ids_batch_csr(h, docs, max_len, unk=0, capacity=None):
+    """Compact batch: returns (ids int32[total], id_offsets int64[n_docs+1])."""
+    buf, offsets = docs if isinstance(docs, tuple) else make_csr(docs)
+    n = len(offsets) - 1
+    if capacity is None:
+        capacity = int(np.minimum(np.diff(offsets), max_len).clip(min=0).sum())
+    ids = np.empty(max(capacity, 1), dtype=np.int32)
+    id_offsets = np.zeros(n + 1, dtype=np.int64)
+    buf = np.ascontiguousarray(buf)
+    r = lib().TextToIdsBatchCsr(c_void_p(h), buf.ctypes.data, offsets.ctypes.data, n, ids.ctypes.data, capacity,
+                                id_offsets.ctypes.data, max_len, unk)
+    if r < 0:
+        raise RuntimeError(f"TextToIdsBatchCsr failed ({r}): {last_error()}")
+    return ids[:r], id_offsets
+
+
+def text_to_ids_batch_device(h, d_text, d_offsets, n_docs, total_bytes, d_ids, d_counts, max_len, unk=0, stream=0):
+    """Device-pointer entry: all arguments are raw device addresses (ints).  Asynchronous."""
+    r = lib().TextToIdsBatchDevice(c_void_p(h), c_void_p(d_text), c_void_p(d_offsets), n_docs, total_bytes,
+                                   c_void_p(d_ids), c_void_p(d_counts), max_len, unk, c_void_p(stream))
+    if r != 0:
+        raise RuntimeError(f"TextToIdsBatchDevice failed: {last_error()}")

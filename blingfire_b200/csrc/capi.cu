@@ -1,0 +1,397 @@
+// capi.cu -- the C ABI (include/blingfiretokdll_b200.h): model lifecycle, device residency of
+// the flattened tables, and the host-side batch pipeline around the kernels.
+//
+// Host code only orchestrates: every tokenizing entry point runs wp_kernel.cu on the GPU.
+// There is deliberately no CPU path; if CUDA is unavailable the calls fail loudly.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/blingfiretokdll_b200.h"
+#include "ldb.h"
+#include "lexer_tables.h"
+#include "wp_kernel.cuh"
+#include "wp_model.h"
+
+using namespace bfb200;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& e) { g_last_error = e; }
+bool cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return false;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  bool reserve(size_t n) {
+    if (n <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    if (!cuda_ok(cudaMalloc(&p, n * sizeof(T)), "cudaMalloc")) return false;
+    cap = n;
+    return true;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  bool reserve(size_t n) {
+    if (n <= cap) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    if (!cuda_ok(cudaMallocHost(&p, n * sizeof(T)), "cudaMallocHost")) return false;
+    cap = n;
+    return true;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// per-slot working set of the host batch pipeline
+struct Slot {
+  cudaStream_t stream = nullptr;
+  DevBuf<uint8_t> text;
+  DevBuf<int64_t> offsets;
+  DevBuf<int32_t> ids;
+  DevBuf<int32_t> counts;      // ndocs + 1 (trailing zero for the scan)
+  DevBuf<int64_t> row_off;     // ndocs + 1
+  DevBuf<int32_t> csr;
+  DevBuf<unsigned long long> counter;
+  PinBuf<int64_t> h_row_off;
+  PinBuf<int64_t> h_offsets;
+  PinBuf<int32_t> h_csr;       // only for the row-major host API
+  // bookkeeping of the chunk in flight
+  int64_t doc0 = 0, ndocs = 0;
+  void release() {
+    text.release(); offsets.release(); ids.release(); counts.release(); row_off.release(); csr.release();
+    counter.release(); h_row_off.release(); h_offsets.release(); h_csr.release();
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
+
+struct Model {
+  int device = 0;
+  int engine = 0;              // 1 = fused WordPiece kernel
+  bool has_wbd = false, has_seg = false;
+  LexerTables T;               // big host vectors are dropped after upload
+  WpBlob blob;
+  // device-resident model
+  void* d_trans = nullptr;
+  int32_t* d_tag = nullptr;
+  uint16_t* d_cls = nullptr;
+  uint8_t* d_blob = nullptr;
+  std::mutex mu;               // serialises the host-pointer entry points of this handle
+  Slot slots[2];
+  DevBuf<unsigned long long> dev_counter;   // for the device-pointer entry point
+
+  ~Model() {
+    cudaSetDevice(device);
+    for (auto& s : slots) s.release();
+    dev_counter.release();
+    if (d_trans) cudaFree(d_trans);
+    if (d_tag) cudaFree(d_tag);
+    if (d_cls) cudaFree(d_cls);
+    if (d_blob) cudaFree(d_blob);
+  }
+};
+
+template <typename T>
+bool upload(T** dst, const T* src, size_t n, size_t slack_elems = 0) {
+  if (!cuda_ok(cudaMalloc((void**)dst, (n + slack_elems) * sizeof(T)), "cudaMalloc(model)")) return false;
+  return cuda_ok(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy(model)");
+}
+
+Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
+  if (!cuda_ok(cudaGetDevice(&m->device), "cudaGetDevice")) return nullptr;
+  m->has_wbd = ldb.conf().get(kFuncWbd) != nullptr;
+  m->has_seg = ldb.conf().get(kFuncPosDict) != nullptr;
+  if (!m->has_wbd && !m->has_seg) { set_error("model has neither a [wbd] nor a [pos-dict] section"); return nullptr; }
+  if (m->has_wbd && !m->has_seg) {
+    std::string err;
+    if (!build_lexer_tables(ldb, &m->T, &err)) { set_error("lexer model: " + err); return nullptr; }
+    LexerTables& T = m->T;
+    if (T.fast.ok && T.charmap_one_to_one && T.max_token_length <= 420) {
+      build_wp_blob(T, &m->blob);
+      const size_t cells = (size_t)T.NS * ((size_t)T.NC + 1);
+      if (T.wide_states) { if (!upload((uint32_t**)&m->d_trans, T.trans32.data(), cells, 16)) return nullptr; }
+      else { if (!upload((uint16_t**)&m->d_trans, T.trans16.data(), cells, 16)) return nullptr; }
+      if (!upload(&m->d_tag, T.tag_of_state.data(), T.tag_of_state.size())) return nullptr;
+      if (!upload(&m->d_cls, T.cls_of_cp.data(), T.cls_of_cp.size())) return nullptr;
+      if (!upload(&m->d_blob, m->blob.bytes.data(), m->blob.bytes.size())) return nullptr;
+      m->engine = 1;
+      // the dense table is the bulk of the host footprint; the device copy is the one that serves
+      std::vector<uint16_t>().swap(T.trans16);
+      std::vector<uint32_t>().swap(T.trans32);
+    }
+  }
+  return m.release();
+}
+
+WpLaunch make_launch(const Model* m) {
+  WpLaunch L{};
+  L.blob = m->d_blob;
+  L.layout = m->blob.layout;
+  L.trans = m->d_trans;
+  L.wide = m->T.wide_states;
+  L.tag_of_state = m->d_tag;
+  L.cls_of_cp = m->d_cls;
+  L.NC1 = (uint32_t)m->T.NC + 1;
+  L.first_final = m->T.first_final;
+  L.cls_caret = m->T.cls_caret;
+  L.cls_dollar = m->T.cls_dollar;
+  L.max_token_length = m->T.max_token_length;
+  return L;
+}
+
+bool ensure_stream(Slot& s) {
+  if (s.stream) return true;
+  return cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+}
+
+// Enqueue one chunk [doc0, doc0+ndocs) of a host CSR batch on slot s: H2D, tokenize, scan, compact,
+// D2H of the row offsets.  Offsets stay absolute; the device text pointer is biased instead.
+bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, int64_t doc0, int64_t ndocs,
+                   int max_ids, int unk) {
+  if (!ensure_stream(s)) return false;
+  const int64_t b0 = offsets[doc0] & ~(int64_t)3;       // keep 32-bit word alignment of absolute offsets
+  const int64_t b1 = offsets[doc0 + ndocs];
+  const size_t nbytes = (size_t)(b1 - b0);
+  if (!s.text.reserve(nbytes + 64) || !s.offsets.reserve((size_t)ndocs + 1) || !s.counts.reserve((size_t)ndocs + 1) ||
+      !s.row_off.reserve((size_t)ndocs + 1) || !s.ids.reserve((size_t)ndocs * (size_t)max_ids) ||
+      !s.counter.reserve(1) || !s.h_row_off.reserve((size_t)ndocs + 1))
+    return false;
+  // a document yields at most one id per byte and at most max_ids ids
+  size_t csr_cap = 0;
+  for (int64_t d = doc0; d < doc0 + ndocs; ++d) {
+    const int64_t len = offsets[d + 1] - offsets[d];
+    if (len > 0) csr_cap += (size_t)std::min<int64_t>(len, max_ids);
+  }
+  if (!s.csr.reserve(csr_cap + 1)) return false;
+
+  if (nbytes && !cuda_ok(cudaMemcpyAsync(s.text.p, utf8 + b0, nbytes, cudaMemcpyHostToDevice, s.stream), "H2D text")) return false;
+  if (!cuda_ok(cudaMemcpyAsync(s.offsets.p, offsets + doc0, ((size_t)ndocs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream), "H2D offsets")) return false;
+
+  WpLaunch L = make_launch(m);
+  L.text = s.text.p - b0;            // biased: absolute offsets index it directly
+  L.offsets = s.offsets.p;
+  L.ndocs = ndocs;
+  L.text_bytes = b1;
+  L.ids = s.ids.p;
+  L.counts = s.counts.p;
+  L.max_ids = max_ids;
+  L.unk_id = unk;
+  L.work_counter = s.counter.p;
+  WpLaunchInfo info{};
+  if (!cuda_ok(wp_tokenize_launch(L, s.stream, &info), "tokenize launch")) return false;
+  if (!cuda_ok(wp_scan_counts(s.counts.p, s.row_off.p, ndocs, s.stream), "scan")) return false;
+  if (!cuda_ok(wp_compact_launch(s.ids.p, s.counts.p, s.row_off.p, ndocs, max_ids, s.csr.p, s.stream), "compact")) return false;
+  g_launches += info.launches + 2;
+  if (!cuda_ok(cudaMemcpyAsync(s.h_row_off.p, s.row_off.p, ((size_t)ndocs + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream), "D2H offsets")) return false;
+  s.doc0 = doc0; s.ndocs = ndocs;
+  return true;
+}
+
+// how many documents go into the next chunk: bounded text bytes and bounded id-matrix size
+int64_t chunk_docs(const int64_t* offsets, int64_t doc0, int64_t ndocs_total, int max_ids) {
+  const int64_t kMaxBytes = 64ll << 20;
+  const int64_t kMaxIdsCells = 160ll << 20;     // 640 MB of int32 per slot
+  const int64_t max_docs = std::max<int64_t>(1, kMaxIdsCells / std::max(1, max_ids));
+  int64_t d = doc0;
+  const int64_t start = offsets[doc0];
+  while (d < ndocs_total && d - doc0 < max_docs && (offsets[d + 1] - start <= kMaxBytes || d == doc0)) ++d;
+  return d - doc0;
+}
+
+// Runs the whole host batch through the two-slot pipeline.  `sink(slot)` consumes a finished
+// chunk (row offsets are in slot.h_row_off; ids are still on the device in slot.csr).
+template <typename Sink>
+bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, int max_ids, int unk, Sink sink) {
+  if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return false;
+  int64_t d = 0;
+  int c = 0;
+  int pending = -1;   // slot index of the chunk enqueued but not yet consumed
+  while (d < ndocs) {
+    const int64_t nd = chunk_docs(offsets, d, ndocs, max_ids);
+    Slot& s = m->slots[c & 1];
+    if (!enqueue_chunk(m, s, utf8, offsets, d, nd, max_ids, unk)) return false;
+    if (pending >= 0) {
+      Slot& ps = m->slots[pending];
+      if (!cuda_ok(cudaStreamSynchronize(ps.stream), "sync")) return false;
+      if (!sink(ps)) return false;
+    }
+    pending = c & 1;
+    d += nd; ++c;
+  }
+  if (pending >= 0) {
+    Slot& ps = m->slots[pending];
+    if (!cuda_ok(cudaStreamSynchronize(ps.stream), "sync")) return false;
+    if (!sink(ps)) return false;
+  }
+  return true;
+}
+
+bool check_batch_args(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, int max_ids) {
+  if (!m) { set_error("null model"); return false; }
+  if (m->engine != 1) { set_error("no GPU engine for this model type yet"); return false; }
+  if (ndocs < 0 || max_ids < 0 || (ndocs > 0 && (!utf8 || !offsets))) { set_error("bad batch arguments"); return false; }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int GetBlingFireTokVersion(void) { return 18 * 1000 + 0; }
+
+const char* BlingFireB200LastError(void) { return g_last_error.c_str(); }
+int64_t BlingFireB200KernelLaunches(void) { return g_launches.load(); }
+int BlingFireB200ModelEngine(void* h) { return h ? ((Model*)h)->engine : 0; }
+
+void* LoadModel(const char* path) {
+  try {
+    g_last_error.clear();
+    LdbImage ldb;
+    if (!ldb.load_file(path)) { set_error(ldb.error()); return nullptr; }
+    return finish_model(std::unique_ptr<Model>(new Model()), ldb);
+  } catch (const std::exception& e) { set_error(e.what()); return nullptr; }
+}
+
+void* SetModel(const unsigned char* bytes, int n) {
+  try {
+    g_last_error.clear();
+    if (!bytes || n <= 0) { set_error("empty image"); return nullptr; }
+    LdbImage ldb;
+    if (!ldb.set_image(bytes, (size_t)n)) { set_error(ldb.error()); return nullptr; }
+    return finish_model(std::unique_ptr<Model>(new Model()), ldb);
+  } catch (const std::exception& e) { set_error(e.what()); return nullptr; }
+}
+
+int FreeModel(void* h) {
+  if (!h) return 0;
+  delete (Model*)h;
+  return 1;
+}
+
+int TextToIdsBatchDevice(void* h, const char* d_utf8, const int64_t* d_offsets, int64_t ndocs, int64_t total_bytes,
+                         int32_t* d_ids, int32_t* d_counts, int max_ids, int unk, void* stream) {
+  try {
+    Model* m = (Model*)h;
+    if (!m || m->engine != 1) { set_error(m ? "no GPU engine for this model type yet" : "null model"); return -1; }
+    if (ndocs == 0) return 0;
+    if (ndocs < 0 || !d_utf8 || !d_offsets || !d_ids || !d_counts || max_ids < 0) { set_error("bad arguments"); return -1; }
+    if (!m->dev_counter.reserve(1)) return -1;
+    WpLaunch L = make_launch(m);
+    L.text = (const uint8_t*)d_utf8; L.offsets = d_offsets; L.ndocs = ndocs; L.text_bytes = total_bytes;
+    L.ids = d_ids; L.counts = d_counts; L.max_ids = max_ids; L.unk_id = unk; L.work_counter = m->dev_counter.p;
+    WpLaunchInfo info{};
+    if (!cuda_ok(wp_tokenize_launch(L, (cudaStream_t)stream, &info), "tokenize launch")) return -1;
+    g_launches += info.launches;
+    return 0;
+  } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
+int64_t TextToIdsBatchCsr(void* h, const char* utf8, const int64_t* offsets, int64_t ndocs, int32_t* ids_csr,
+                          int64_t capacity, int64_t* id_offsets, int max_ids, int unk) {
+  try {
+    Model* m = (Model*)h;
+    if (!check_batch_args(m, utf8, offsets, ndocs, max_ids)) return -1;
+    if (!id_offsets || (capacity > 0 && !ids_csr)) { set_error("bad output arguments"); return -1; }
+    std::lock_guard<std::mutex> lock(m->mu);
+    int64_t total = 0;
+    bool overflow = false;
+    id_offsets[0] = 0;
+    auto sink = [&](Slot& s) -> bool {
+      const int64_t n = s.h_row_off.p[s.ndocs];
+      for (int64_t i = 0; i < s.ndocs; ++i) id_offsets[s.doc0 + i + 1] = total + s.h_row_off.p[i + 1];
+      if (total + n > capacity) overflow = true;
+      else if (n > 0) {
+        if (!cuda_ok(cudaMemcpyAsync(ids_csr + total, s.csr.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream), "D2H ids")) return false;
+        if (!cuda_ok(cudaStreamSynchronize(s.stream), "sync")) return false;
+      }
+      total += n;
+      return true;
+    };
+    if (!run_pipeline(m, utf8, offsets, ndocs, max_ids, unk, sink)) return -1;
+    return overflow ? -total : total;
+  } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
+int64_t TextToIdsBatch(void* h, const char* utf8, const int64_t* offsets, int64_t ndocs, int32_t* ids, int32_t* counts,
+                       int max_ids, int unk) {
+  try {
+    Model* m = (Model*)h;
+    if (!check_batch_args(m, utf8, offsets, ndocs, max_ids)) return -1;
+    if (ndocs > 0 && (!ids || !counts)) { set_error("bad output arguments"); return -1; }
+    std::lock_guard<std::mutex> lock(m->mu);
+    int64_t total = 0;
+    auto sink = [&](Slot& s) -> bool {
+      const int64_t n = s.h_row_off.p[s.ndocs];
+      if (!s.h_csr.reserve((size_t)n + 1)) return false;
+      if (n > 0) {
+        if (!cuda_ok(cudaMemcpyAsync(s.h_csr.p, s.csr.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream), "D2H ids")) return false;
+        if (!cuda_ok(cudaStreamSynchronize(s.stream), "sync")) return false;
+      }
+      // rows beyond their count stay untouched, as in the reference (blingfiretokdll.cpp:1098-1101)
+      for (int64_t i = 0; i < s.ndocs; ++i) {
+        const int64_t a = s.h_row_off.p[i], b = s.h_row_off.p[i + 1];
+        counts[s.doc0 + i] = (int32_t)(b - a);
+        if (b > a) std::memcpy(ids + (s.doc0 + i) * (int64_t)max_ids, s.h_csr.p + a, (size_t)(b - a) * sizeof(int32_t));
+      }
+      total += n;
+      return true;
+    };
+    if (!run_pipeline(m, utf8, offsets, ndocs, max_ids, unk, sink)) return -1;
+    return total;
+  } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
+int TextToIds(void* h, const char* s, int n, int32_t* ids, const int max_ids, const int unk) {
+  // blingfiretokdll.cpp:1619-1646 -> :1121: parameter validation happens before any work
+  if (!h || n <= 0 || n > 1000000000 || !s) return 0;
+  Model* m = (Model*)h;
+  if (m->engine != 1) { set_error("no GPU engine for this model type yet"); return 0; }
+  if (max_ids <= 0 || !ids) return 0;
+  const int64_t offsets[2] = {0, n};
+  int32_t count = 0;
+  const int64_t r = TextToIdsBatch(h, s, offsets, 1, ids, &count, max_ids, unk);
+  return r < 0 ? 0 : (int)count;
+}
+
+int TextToIds_wp(void* h, const char* s, int n, int32_t* ids, const int max_ids, const int unk) {
+  Model* m = (Model*)h;
+  if (!m || !m->has_wbd || m->has_seg) return 0;
+  return TextToIds(h, s, n, ids, max_ids, unk);
+}
+
+int TextToIds_sp(void* h, const char* s, int n, int32_t* ids, const int max_ids, const int unk) {
+  Model* m = (Model*)h;
+  if (!m || !m->has_seg) return 0;
+  return TextToIds(h, s, n, ids, max_ids, unk);
+}
+
+int TextToWordsWithModel(const char*, int, char*, const int, void*) {
+  set_error("TextToWords: generic lexer engine not built yet");
+  return -1;
+}
+int TextToWords(const char* s, int n, char* out, const int max_out) { return TextToWordsWithModel(s, n, out, max_out, nullptr); }
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+/*
+ * blingfiretokdll_b200.h -- C ABI of the B200-native drop-in for BlingFire's TextToIds path.
+ *
+ * The first block re-declares, with identical names, argument meaning, ownership and return
+ * conventions, the entry points of the reference's blingfiretokdll that lie on the
+ * TextToIds / TextToWords hot path.  Each declaration cites the reference interface it
+ * replaces (paths relative to the reference checkout).  A caller that binds these symbols
+ * by name (dist-pypi/blingfire/__init__.py:229-253 via ctypes, nuget/lib/BlingFireUtils.cs:24-35
+ * via P/Invoke) can load this library instead of libblingfiretokdll.so without code changes.
+ *
+ * The second block is additive: the reference has no batch entry point (every export takes
+ * one document), and one call per document cannot feed a GPU.
+ *
+ * (The reference spells the returns `const int`; the qualifier is meaningless on a return
+ * type and is dropped here -- the ABI is identical.)
+ *
+ * Plain C: pointers and sizes only, caller-owned buffers, no exceptions cross this boundary
+ * (the reference may throw std::runtime_error through its C ABI, e.g. on a missing model
+ * file; here such cases return NULL / 0 / -1).
+ *
+ * There is NO CPU implementation behind these symbols: every tokenizing call runs on the
+ * current CUDA device and fails (0 / -1 / NULL, see BlingFireB200LastError) if no device or
+ * kernel image is available.
+ */
+#ifndef BLINGFIRETOKDLL_B200_H
+#define BLINGFIRETOKDLL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------
+ * Drop-in symbols (same names as the reference)
+ * ------------------------------------------------------------------------------------- */
+
+/* blingfiretokdll.h:25, blingfiretokdll.cpp:107-111.  Returns 18000 (algo version 18.0). */
+int GetBlingFireTokVersion(void);
+
+/* blingfiretokdll.h:48, blingfiretokdll.cpp:1077-1094.  Loads a compiled .bin LDB, flattens
+ * its automata and uploads them to the current CUDA device.  Returns an opaque handle,
+ * NULL on any failure (missing file, malformed image, CRC mismatch, unsupported model). */
+void* LoadModel(const char* pszLdbFileName);
+
+/* blingfiretokdll.h:47, blingfiretokdll.cpp:1055-1071.  Same, from a memory image (copied). */
+void* SetModel(const unsigned char* pImgBytes, int ModelByteCount);
+
+/* blingfiretokdll.h:101, blingfiretokdll.cpp:1653-1662.  0 if NULL, else frees and returns 1. */
+int FreeModel(void* ModelPtr);
+
+/* blingfiretokdll.h:93-100, blingfiretokdll.cpp:1619-1646.  Writes at most MaxIdsArrLength
+ * ids, leaves the rest of pIdsArr untouched, returns the number written.  Returns 0 for a
+ * NULL model/text, InUtf8StrByteCount <= 0 or > 1e9, invalid UTF-8 anywhere in the input,
+ * or normalisation overflow -- exactly like the reference. */
+int TextToIds(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
+                    int32_t* pIdsArr, const int MaxIdsArrLength, const int UnkId);
+
+/* blingfiretokdll.h:57-64 / :75-82, blingfiretokdll.cpp:1320-1335 / :1541-1552. */
+int TextToIds_wp(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
+                       int32_t* pIdsArr, const int MaxIdsArrLength, const int UnkId);
+int TextToIds_sp(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
+                       int32_t* pIdsArr, const int MaxIdsArrLength, const int UnkId);
+
+/* blingfiretokdll.h:41, blingfiretokdll.cpp:610-614.  Default word breaker.  Returns -1 on
+ * error, 0 for empty input, else the required output size including the trailing NUL (the
+ * output is copied only if it fits).  The reference embeds wbd.bin as a byte array; this
+ * library loads it from $BLINGFIRE_B200_WBD or <library dir>/wbd.bin on first use. */
+int TextToWords(const char* pInUtf8Str, int InUtf8StrByteCount,
+                      char* pOutUtf8Str, const int MaxOutUtf8StrByteCount);
+
+/* blingfiretokdll.h:39-40, blingfiretokdll.cpp:597-603.  hModel == NULL selects the default. */
+int TextToWordsWithModel(const char* pInUtf8Str, int InUtf8StrByteCount,
+                               char* pOutUtf8Str, const int MaxOutUtf8StrByteCount, void* hModel);
+
+/* ---------------------------------------------------------------------------------------
+ * Additive batch entry points (new)
+ * ------------------------------------------------------------------------------------- */
+
+/* Documents are a CSR byte buffer: document i = pUtf8[pOffsets[i] .. pOffsets[i+1]).
+ * For every i the pair (pCounts[i], pIds[i*MaxIdsPerDoc .. +pCounts[i])) equals what the
+ * reference's TextToIds returns for document i with the same MaxIdsArrLength and UnkId;
+ * entries of a row beyond pCounts[i] are left untouched.  HOST pointers; host<->device
+ * copies are pipelined inside the call.  Returns the total number of ids, or -1 on error. */
+int64_t TextToIdsBatch(void* ModelPtr, const char* pUtf8, const int64_t* pOffsets, int64_t DocCount,
+                       int32_t* pIds, int32_t* pCounts, int MaxIdsPerDoc, int UnkId);
+
+/* Same contract, compact output: ids of document i are pIdsCsr[pIdOffsets[i] .. pIdOffsets[i+1]),
+ * pIdOffsets has DocCount+1 entries.  pIdsCsr must hold CsrCapacity ids; if the batch
+ * produces more, nothing is copied and the required capacity is returned negated.
+ * HOST pointers.  This is the call bench.py times end to end. */
+int64_t TextToIdsBatchCsr(void* ModelPtr, const char* pUtf8, const int64_t* pOffsets, int64_t DocCount,
+                          int32_t* pIdsCsr, int64_t CsrCapacity, int64_t* pIdOffsets,
+                          int MaxIdsPerDoc, int UnkId);
+
+/* DEVICE pointers on the model's device, no copies, asynchronous on `cudaStream` (a
+ * cudaStream_t, NULL = legacy default stream).  dUtf8 must be 4-byte aligned with at least
+ * 8 readable bytes of slack after TotalBytes (any cudaMalloc'ed buffer qualifies).
+ * dIds is [DocCount][MaxIdsPerDoc] row-major.  Returns 0 on success, -1 on error. */
+int TextToIdsBatchDevice(void* ModelPtr, const char* dUtf8, const int64_t* dOffsets, int64_t DocCount,
+                         int64_t TotalBytes, int32_t* dIds, int32_t* dCounts,
+                         int MaxIdsPerDoc, int UnkId, void* cudaStream);
+
+/* Last error of the calling thread ("" if none).  Never NULL. */
+const char* BlingFireB200LastError(void);
+
+/* Number of GPU kernels this library has launched in this process (bench.py: gpu_launches). */
+int64_t BlingFireB200KernelLaunches(void);
+
+/* Which engine serves the model: 1 = fused WordPiece kernel (FastPath lexer models),
+ * 0 = none (model loaded but no GPU engine for it yet). */
+int BlingFireB200ModelEngine(void* ModelPtr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

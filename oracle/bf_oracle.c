@@ -884,7 +884,10 @@ static int text_to_ids_sp(const bfo_model* m, const char* s, int n, int32_t* ids
                     const int tf = res[k + 1], tt = res[k + 2];
                     starts[out] = offs[use_norm ? noffs[tf] : tf];
                     const int to_off = offs[use_norm ? noffs[tt] : tt];
-                    const int cs = utf8_size_of_lead(s + to_off);
+                    /* to_off == -1 for a token that is only the dummy prefix: the reference then
+                     * reads the byte BEFORE the input (blingfiretokdll.cpp:1527, out of bounds, value
+                     * unspecified).  The oracle pins that case to size 0. */
+                    const int cs = to_off < 0 ? 0 : utf8_size_of_lead(s + to_off);
                     ends[out] = to_off + (cs > 0 ? cs - 1 : 0);
                 }
                 out++;
@@ -956,6 +959,30 @@ int bfo_charmap_get(const bfo_model* m, int cp, int* out, int max_out) {
 }
 int bfo_fn_ini(const bfo_model* m, int fn) { return (fn >= 0 && fn < m->fn2ini_size) ? m->fn2ini[fn] : -1; }
 int bfo_has_seg(const bfo_model* m) { return m->has_seg; }
+
+/* bulk variants so the table cross-checks in tests/ do not pay one ctypes call per lookup */
+void bfo_dfa_get_dest_many(const bfo_model* m, const int* states, const int* iws, long n, int* out) {
+    for (long i = 0; i < n; ++i) out[i] = dfa_get_dest(&m->wbd_dfa, states[i], iws[i]);
+}
+void bfo_dfa_row(const bfo_model* m, int state, const int* iws, int n, int* out) {
+    for (int i = 0; i < n; ++i) out[i] = dfa_get_dest(&m->wbd_dfa, state, iws[i]);
+}
+void bfo_iwmap_many(const bfo_model* m, int from, int to, int* out) {
+    for (int iw = from; iw < to; ++iw) out[iw - from] = m->wbd_dfa.remap ? iwmap_get(&m->wbd_dfa.iwmap, iw) : iw;
+}
+void bfo_state_info_many(const bfo_model* m, const int* states, long n, int* finals, int* ows) {
+    for (long i = 0; i < n; ++i) { finals[i] = dfa_is_final(&m->wbd_dfa, states[i]); ows[i] = finals[i] ? dfa_get_ow(&m->wbd_dfa, states[i]) : -1; }
+}
+/* class of a code point as the lexer sees it: charmap (1->1 rows), clamp, class map */
+void bfo_lexer_class_many(const bfo_model* m, int from, int to, int* out) {
+    int norm[10];
+    for (int cp = from; cp < to; ++cp) {
+        int x = cp;
+        if (m->has_wbd_charmap) { int c = mmapf_get_copy(&m->wbd_charmap, cp, norm, 10); if (c == 1) x = norm[0]; else if (c != -1) { out[cp - from] = -2; continue; } }
+        if (x < IW_EPSILON) x = IW_EPSILON;
+        out[cp - from] = m->wbd_dfa.remap ? iwmap_get(&m->wbd_dfa.iwmap, x) : x;
+    }
+}
 
 /* ---- threaded batch driver (CPU baseline timing) ---- */
 typedef struct { const bfo_model* m; const char* utf8; const int64_t* offs; int64_t ndocs; int32_t* ids; int32_t* counts;

@@ -1,0 +1,199 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (blingfire_b200 -> libblingfiretokdll.so),
+against the oracle on the same inputs, against the committed golden fixtures (produced by the
+reference itself), and -- at BASELINE.json's full sizes -- through size-independent properties.
+Bit-exact: ids and counts are integers."""
+import base64
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from _common import GOLDEN, Oracle, fnv1a64_ids, have_data, model_path, read_lines
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_data(), reason="data/ not staged")]
+
+BERT_TEXT = ("Эpple pie. How do I renew my virtual smart card?: /Microsoft IT/ 'virtual' smart card certificates for "
+             "DirectAccess are valid for one year. In order to get to microsoft.com we need to type pi@1.2.1.2.")
+BERT_IDS = [1208, 9397, 2571, 11345, 1012, 2129, 2079, 1045, 20687, 2026, 7484, 6047, 4003, 1029, 1024, 1013, 7513,
+            2009, 1013, 1005, 7484, 1005, 6047, 4003, 17987, 2005, 3622, 6305, 9623, 2015, 2024, 9398, 2005, 2028,
+            2095, 1012, 1999, 2344, 2000, 2131, 2000, 7513, 1012, 4012, 2057, 2342, 2000, 2828, 14255, 1030, 1015,
+            1012, 1016, 1012, 1015, 1012, 1016, 1012]
+
+
+@pytest.fixture(scope="module")
+def bf():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    torch.zeros(1, device="cuda")
+    import blingfire_b200
+    return blingfire_b200
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+_models = {}
+
+
+def gpu_model(bf, name):
+    if name not in _models:
+        _models[name] = bf.load_model(model_path(name))
+        assert bf.lib().BlingFireB200ModelEngine(_models[name]) == 1, f"{name}: no GPU engine"
+    return _models[name]
+
+
+def check_batch(bf, oracle, name, docs, max_ids, unk):
+    h = gpu_model(bf, name)
+    ho = oracle.load(model_path(name))
+    buf, offs = bf.make_csr(docs)
+    ids, counts = bf.text_to_ids_batch(h, (buf, offs), max_ids, unk)
+    _, oids, ocounts = oracle.batch(ho, buf if len(buf) else np.zeros(1, np.uint8), offs, max_ids, unk, threads=8)
+    bad = np.nonzero(counts != ocounts)[0]
+    assert len(bad) == 0, f"{name}: count mismatch at docs {bad[:5]} gpu={counts[bad[:5]]} oracle={ocounts[bad[:5]]} {docs[bad[0]][:80]!r}"
+    mask = np.arange(max_ids)[None, :] < counts[:, None]
+    diff = np.nonzero(((ids != oids) & mask).any(axis=1))[0]
+    assert len(diff) == 0, f"{name}: id mismatch at docs {diff[:5]} {docs[diff[0]][:80]!r}"
+    assert (ids[~mask] == 0).all(), "tail of a row was written"
+    # the compact entry point agrees with the row-major one
+    cids, coffs = bf.text_to_ids_batch_csr(h, (buf, offs), max_ids, unk)
+    assert (np.diff(coffs) == counts).all()
+    assert (cids == ids[mask]).all()
+    oracle.free(ho)
+    return ids, counts
+
+
+def test_known_answer_bert(bf):
+    h = gpu_model(bf, "bert_base_tok.bin")
+    ids = bf.text_to_ids(h, BERT_TEXT, 128, 100, no_padding=True)   # README.md:111,131-135
+    assert ids.tolist() == BERT_IDS
+    padded = bf.text_to_ids(h, BERT_TEXT, 128, 100)
+    assert padded[:58].tolist() == BERT_IDS and (padded[58:] == 0).all()
+
+
+def test_edge_cases_vs_golden(bf, golden):
+    """Single-document TextToIds through the C ABI, incl. the untouched-tail contract."""
+    import ctypes
+    L = bf.lib()
+    for case in golden["edge_cases"]:
+        if case["model"] not in ("bert_base_tok.bin", "bert_base_cased_tok.bin", "bert_chinese.bin"):
+            continue
+        h = gpu_model(bf, case["model"])
+        data = base64.b64decode(case["input"])
+        out = np.full(case["max_ids"], -7, np.int32)
+        n = L.TextToIds(ctypes.c_void_p(h), data, len(data), out.ctypes.data, case["max_ids"], case["unk"])
+        assert n == case["count"], (case["model"], data[:40])
+        assert out[:n].tolist() == case["ids"], (case["model"], data[:40])
+        assert (out[n:] == -7).all(), "ids beyond the returned count must stay untouched"
+
+
+def test_corpus_digests_vs_golden(bf, golden):
+    for d in golden["digests"]:
+        if d["model"] not in ("bert_base_tok.bin", "bert_base_cased_tok.bin", "bert_chinese.bin"):
+            continue
+        lines = read_lines(d["corpus"], drop_empty=False)[: d["lines"]]
+        docs = [b" ".join(lines[i:i + d["group"]]) for i in range(0, len(lines), d["group"])]
+        h = gpu_model(bf, d["model"])
+        cids, coffs = bf.text_to_ids_batch_csr(h, docs, d["max_ids"], d["unk"])
+        assert int(coffs[-1]) == d["tokens"], d
+        assert f"{fnv1a64_ids(cids):016x}" == d["fnv1a64"], d
+
+
+@pytest.mark.parametrize("name,corpus,nlines,group,max_ids", [
+    ("bert_base_tok.bin", "test.txt", 40000, 1, 128),
+    ("bert_base_tok.bin", "test.txt", 40000, 12, 512),
+    ("bert_base_tok.bin", "test.txt", 30000, 60, 4096),        # multi-window documents
+    ("bert_base_tok.bin", "test.multi.txt", 20000, 3, 512),    # 2-4 byte code points
+    ("bert_base_cased_tok.bin", "test.txt", 20000, 5, 512),
+    ("bert_chinese.bin", "test.multi.txt", 20000, 2, 512),
+])
+def test_batch_matches_oracle_on_corpora(bf, oracle, name, corpus, nlines, group, max_ids):
+    lines = read_lines(corpus, drop_empty=False)[:nlines]
+    docs = [b" ".join(lines[i:i + group]) for i in range(0, len(lines), group)]
+    check_batch(bf, oracle, name, docs, max_ids, 100)
+
+
+def test_ragged_edge_and_invalid_documents(bf, oracle):
+    rng = random.Random(5)
+    lines = read_lines("test.multi.txt")[:3000] + read_lines("test.txt")[:3000]
+    docs = [b"", b" ", b"\xef\xbb\xbf", b"\xef\xbb\xbfhello", b"abc \xff def", b"\xe6\x88", b"hello\x00world", b"a" * 400,
+            b"a" * 1000 + b" " + b"b" * 700, "我".encode() * 900, b"ab" * 700 + b"\xff", b"." * 700, ("word " * 300).encode(),
+            b"x" * 513, b"y" * 511 + "é".encode(), ("é" * 700).encode(), b"\xf0\x9f\x98\x80" * 300, b"\x80" + b"a" * 600]
+    for _ in range(6000):
+        d = b" ".join(rng.choice(lines) for _ in range(rng.randint(1, 14)))
+        r = rng.random()
+        if r < 0.2:
+            d = d[: rng.randint(0, len(d))]
+        elif r < 0.3:
+            p = rng.randint(0, len(d))
+            d = d[:p] + bytes([rng.randint(0, 255)]) + d[p:]
+        elif r < 0.35:
+            d = bytes(rng.randint(0, 255) for _ in range(rng.randint(1, 60)))
+        docs.append(d)
+    for max_ids in (300, 7):
+        check_batch(bf, oracle, "bert_base_tok.bin", docs, max_ids, 100)
+
+
+def test_unaligned_offsets_and_unk_id(bf, oracle):
+    """Documents starting at every byte alignment; a non-default UnkId."""
+    docs = [b"x" * k + b" unaffable qwrtzx " + "naïve café".encode() for k in range(0, 9)] * 50
+    check_batch(bf, oracle, "bert_base_tok.bin", docs, 64, 7777)
+
+
+def test_device_entry_point_matches_host(bf, oracle):
+    import torch
+    import corpus
+    h = gpu_model(bf, "bert_base_tok.bin")
+    text, offs = corpus.gen_docs("EN", 20000, seed=2, fixed_len=512)
+    ids, counts = bf.text_to_ids_batch(h, (text, offs), 512, 100)
+    d_text = torch.empty(len(text) + 64, dtype=torch.uint8, device="cuda")
+    d_text[: len(text)].copy_(torch.from_numpy(text))
+    d_offs = torch.from_numpy(offs).cuda()
+    d_ids = torch.zeros((len(offs) - 1, 512), dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros(len(offs) - 1, dtype=torch.int32, device="cuda")
+    bf.text_to_ids_batch_device(h, d_text.data_ptr(), d_offs.data_ptr(), len(offs) - 1, int(offs[-1]),
+                                d_ids.data_ptr(), d_counts.data_ptr(), 512, 100, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (d_counts.cpu().numpy() == counts).all()
+    assert (d_ids.cpu().numpy() == ids).all()
+
+
+def test_full_size_properties(bf, oracle):
+    """cfg 2 at full size (1 M docs x ~512 B): properties that do not need the oracle on every doc.
+      * replica / rotation invariance: rotating the document order rotates the result rows
+      * concatenation: per-document counts sum to the CSR total
+      * a strided sample is checked id-for-id against the oracle."""
+    import corpus
+    n = 1_000_000
+    h = gpu_model(bf, "bert_base_tok.bin")
+    text, offs = corpus.cfg2(n)
+    cids, coffs = bf.text_to_ids_batch_csr(h, (text, offs), 512, 100)
+    counts = np.diff(coffs)
+    assert counts.min() > 0 and counts.max() <= 512
+    assert int(coffs[-1]) == len(cids)
+    # rotation by 15 625 docs (cfg 5's replica rule): same multiset of rows, rotated
+    rot = 15625
+    lens = np.diff(offs)
+    order = np.roll(np.arange(n), -rot)
+    r_offs = np.zeros(n + 1, np.int64)
+    np.cumsum(lens[order], out=r_offs[1:])
+    r_text = np.concatenate([text[offs[rot]:], text[:offs[rot]]])
+    rids, roffs = bf.text_to_ids_batch_csr(h, (r_text, r_offs), 512, 100)
+    assert (np.diff(roffs) == counts[order]).all()
+    assert (rids == np.concatenate([cids[coffs[rot]:], cids[:coffs[rot]]])).all()
+    # strided sample against the oracle
+    ho = oracle.load(model_path("bert_base_tok.bin"))
+    for d in range(0, n, 997):
+        doc = bytes(text[offs[d]:offs[d + 1]])
+        k, oids = oracle.text_to_ids(ho, doc, 512, 100)
+        assert k == counts[d] and (oids[:k] == cids[coffs[d]:coffs[d + 1]]).all(), d

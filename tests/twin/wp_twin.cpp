@@ -1,0 +1,175 @@
+// wp_twin.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// A sequential host driver around the product's own table builders (ldb.cpp,
+// lexer_tables.cpp, wp_model.cpp) and the product's own __host__ __device__ chunk routine
+// (wp_core.cuh).  It mirrors, step for step, what one warp of wp_kernel.cu does for one
+// document (decode -> classes -> sync points -> chunks -> windows with carry -> compaction),
+// so the algorithmic part of the CUDA path can be checked against the oracle on the CPU box,
+// where no GPU exists.  It is compiled into tests/twin/libwp_twin.so, is never linked into
+// the product library, and the product API has no route to it.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../blingfire_b200/csrc/ldb.h"
+#include "../../blingfire_b200/csrc/lexer_tables.h"
+#include "../../blingfire_b200/csrc/wp_core.cuh"
+#include "../../blingfire_b200/csrc/wp_model.h"
+
+using namespace bfb200;
+
+struct Twin {
+  LdbImage ldb;
+  LexerTables T;
+  WpBlob blob;
+  std::string err;
+};
+
+extern "C" {
+
+void* twin_load(const char* path) {
+  Twin* t = new Twin();
+  if (!t->ldb.load_file(path)) { t->err = t->ldb.error(); return t; }
+  if (!t->ldb.conf().get(kFuncWbd)) { t->err = "no [wbd]"; return t; }
+  if (!build_lexer_tables(t->ldb, &t->T, &t->err)) return t;
+  if (t->T.fast.ok && t->T.charmap_one_to_one) build_wp_blob(t->T, &t->blob);
+  return t;
+}
+void twin_free(void* h) { delete (Twin*)h; }
+const char* twin_error(void* h) { return ((Twin*)h)->err.c_str(); }
+int twin_fast_ok(void* h) { Twin* t = (Twin*)h; return t->err.empty() && t->T.fast.ok && t->T.charmap_one_to_one; }
+const char* twin_fast_why(void* h) { return ((Twin*)h)->T.fast.why_not.c_str(); }
+
+// table introspection for the exhaustive cross-check against the oracle's packed readers
+int twin_info(void* h, int what) {
+  Twin* t = (Twin*)h;
+  switch (what) {
+    case 0: return t->T.NS;
+    case 1: return t->T.NC;
+    case 2: return (int)t->T.first_final;
+    case 3: return (int)t->T.initial;
+    case 4: return (int)t->T.dead;
+    case 5: return t->T.wide_states ? 1 : 0;
+    case 6: return (int)t->T.cls_of_iw.size();
+    case 7: return (int)t->T.fn_ini.size();
+    case 8: return t->T.fast.K;
+    case 9: return t->T.fast.NT;
+    case 10: return t->T.max_depth;
+    case 11: return t->T.max_token_length;
+    case 12: return (int)t->blob.layout.total_bytes;
+    case 13: return t->blob.layout.num_rows;
+    default: return -1;
+  }
+}
+const void* twin_ptr(void* h, int what) {
+  Twin* t = (Twin*)h;
+  switch (what) {
+    case 0: return t->T.wide_states ? (const void*)t->T.trans32.data() : (const void*)t->T.trans16.data();
+    case 1: return t->T.orig_offset.data();
+    case 2: return t->T.cls_of_iw.data();
+    case 3: return t->T.cls_of_cp.data();
+    case 4: return t->T.ow_of_state.data();
+    case 5: return t->T.tag_of_state.data();
+    case 6: return t->T.fn_ini.data();
+    default: return nullptr;
+  }
+}
+
+// One document through the mirrored warp algorithm.  `window` plays the role of the
+// kernel's per-warp window capacity (in code points); small values stress the carry logic.
+int twin_text_to_ids(void* h, const char* s, int n, int32_t* ids, int max_ids, int unk, int window) {
+  Twin* t = (Twin*)h;
+  if (!twin_fast_ok(h)) return -2;
+  if (n <= 0 || n > 1000000000 || !s) return 0;
+  const LexerTables& T = t->T;
+  const WpTop top = make_wp_top(t->blob.bytes.data(), t->blob.layout);
+  const int max_tok = T.max_token_length;
+  if (window < max_tok + 40) window = max_tok + 40;
+
+  const uint8_t* b = (const uint8_t*)s;
+  int lo = 0, hi = n;
+  if (n >= 3 && b[0] == 0xEF && b[1] == 0xBB && b[2] == 0xBF) lo = 3;   // FAUtf8Utils.cpp:247-252
+  if (lo >= hi) return 0;
+
+  // strict UTF-8 validation of the whole document first (FAUtf8Utils.cpp:121-196)
+  {
+    int p = lo;
+    while (p < hi) {
+      const int c = b[p];
+      int len, cp;
+      if (c < 0x80) { p += 1; continue; }
+      if ((c & 0xE0) == 0xC0) { len = 2; cp = c & 0x1F; }
+      else if ((c & 0xF0) == 0xE0) { len = 3; cp = c & 0x0F; }
+      else if ((c & 0xF8) == 0xF0) { len = 4; cp = c & 0x07; }
+      else return 0;
+      if (p + len > hi) return 0;
+      for (int k = 1; k < len; ++k) { if ((b[p + k] & 0xC0) != 0x80) return 0; cp = (cp << 6) | (b[p + k] & 0x3F); }
+      const int need = cp <= 0x7F ? 1 : cp <= 0x7FF ? 2 : cp <= 0xFFFF ? 3 : cp <= 0x10FFFF ? 4 : 0;
+      if (need != len) return 0;
+      if ((cp & 0xFFFFF800) == 0xD800) return 0;
+      p += len;
+    }
+  }
+
+  std::vector<uint16_t> cls((size_t)window + 8);
+  std::vector<int32_t> ids_at((size_t)window + 8);
+  std::vector<uint8_t> has_id((size_t)window + 8);
+  std::vector<int> starts;
+  WpGlobal<uint16_t> g16{};
+  WpGlobal<uint32_t> g32{};
+  auto fill_g = [&](auto& g, const auto* trans) {
+    g.trans = trans; g.tag_of_state = T.tag_of_state.data(); g.cls_of_cp = T.cls_of_cp.data();
+    g.NC1 = (uint32_t)T.NC + 1; g.first_final = T.first_final; g.cls_caret = T.cls_caret; g.cls_dollar = T.cls_dollar;
+    g.max_token_length = max_tok;
+  };
+  if (T.wide_states) fill_g(g32, T.trans32.data()); else fill_g(g16, T.trans16.data());
+
+  int m = 0, bpos = lo, out = 0;
+  bool first = true;
+  for (;;) {
+    // fill the window with classes of further code points
+    while (m < window && bpos < hi) {
+      const int c = b[bpos];
+      int len = c < 0x80 ? 1 : (c & 0xE0) == 0xC0 ? 2 : (c & 0xF0) == 0xE0 ? 3 : 4;
+      int cp = c < 0x80 ? c : len == 2 ? c & 0x1F : len == 3 ? c & 0x0F : c & 0x07;
+      for (int k = 1; k < len; ++k) cp = (cp << 6) | (b[bpos + k] & 0x3F);
+      cls[m++] = cp < 128 ? top.ascii_cls[cp] : T.cls_of_cp[cp];
+      bpos += len;
+    }
+    const bool at_end = bpos >= hi;
+    if (m == 0) break;
+    std::fill(has_id.begin(), has_id.begin() + m, 0);
+    // chunk starts: sync points whose first class can start a match; position 0 always
+    starts.clear();
+    starts.push_back(0);
+    for (int p = 1; p < m; ++p) {
+      const uint8_t t1 = top.tc_of_class[cls[p - 1]], t2 = top.tc_of_class[cls[p]];
+      const bool sync = !((top.cross[t1] >> t2) & 1ull);
+      if (sync && top.ttop[t2] != 0xFF) starts.push_back(p);
+    }
+    const int limit = at_end ? m : m - max_tok;
+    int carry = at_end ? m : 0;
+    for (size_t i = 0; i < starts.size(); ++i) {
+      int fb = (i == 0 && first) ? -1 : starts[i];
+      int fe = i + 1 < starts.size() ? starts[i + 1] : m;
+      if (fb >= limit) break;
+      if (fe > limit) fe = limit;
+      int r;
+      if (T.wide_states) r = wp_chunk<uint32_t>(top, g32, cls.data(), m, at_end, fb, fe, unk, ids_at.data(), has_id.data());
+      else r = wp_chunk<uint16_t>(top, g16, cls.data(), m, at_end, fb, fe, unk, ids_at.data(), has_id.data());
+      if (r > carry) carry = r;
+      // exactness guard of the sync-point argument: a chunk must end exactly on the next start
+      if (i + 1 < starts.size() && starts[i + 1] <= limit && r != starts[i + 1]) return -3;
+    }
+    for (int p = 0; p < carry && p < m; ++p)
+      if (has_id[p]) { if (out < max_ids) ids[out] = ids_at[p]; ++out; }
+    if (at_end) break;
+    std::memmove(cls.data(), cls.data() + carry, sizeof(uint16_t) * (size_t)(m - carry));
+    m -= carry;
+    first = false;
+  }
+  return out < max_ids ? out : max_ids;
+}
+
+}  // extern "C"
