@@ -67,16 +67,18 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary over the samples taken inside [t0, t1] (the timed region); falls back to every
+        sample since start() (warm-up + timed region, all under load) if the region was too short."""
         if self.proc:
             self.proc.terminate()
             try:
@@ -85,7 +87,8 @@ class ClockSampler:
                 pass
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (ts, r) in self.rows if t0 is not None and t0 <= ts <= t1]
+        for r in (inside if len(inside) >= 3 else [r for (_, r) in self.rows]):
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -160,8 +163,8 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--docs", type=int, default=1_000_000)
     ap.add_argument("--ref-sample", type=int, default=200_000, help="documents per step of the CPU reference arm")
@@ -197,13 +200,8 @@ def main():
     n = args.docs
     text, offs = corpus.cfg2(n) if n == 1_000_000 else corpus.gen_docs("EN", n, seed=2, fixed_len=512)
     if rank > 0:
-        rot = (rank * 15625) % n
-        lens = np.diff(offs)
-        order = np.roll(np.arange(n), -rot)
-        new_offs = np.zeros(n + 1, np.int64)
-        np.cumsum(lens[order], out=new_offs[1:])
-        text = np.concatenate([text[offs[rot]:], text[:offs[rot]]])
-        offs = new_offs
+        from blingfire_b200 import sharding
+        text, offs = sharding.rotate_replica(text, offs, (rank * 15625) % n)
     nbytes = int(offs[-1])
 
     # pinned host copies (the e2e leg reads these), device-resident copies (the kernel-only leg)
@@ -228,28 +226,31 @@ def main():
             stats[0] = n; stats[1] = nbytes; stats[2] = d_counts.sum()
             dist.all_reduce(stats)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)   # let nvidia-smi come up; it samples through warm-up and the timed region
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = bf.kernel_launches()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
+    t_wall0 = time.time()
     ev[0].record(stream)
     for i in range(args.steps):
         step()
         ev[i + 1].record(stream)
     torch.cuda.synchronize()
+    t_wall1 = time.time()
     if world > 1:
         dist.barrier()
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[args.steps])
     launches = bf.kernel_launches() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     tokens = int(d_counts.sum().item())
 
     # max over ranks of the timed region; total units over all ranks
