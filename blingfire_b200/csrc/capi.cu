@@ -4,6 +4,7 @@
 // Host code only orchestrates: every tokenizing entry point runs wp_kernel.cu on the GPU.
 // There is deliberately no CPU path; if CUDA is unavailable the calls fail loudly.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -18,6 +19,7 @@
 
 #include "../../include/blingfiretokdll_b200.h"
 #include "ldb.h"
+#include "lex_kernel.cuh"
 #include "lexer_tables.h"
 #include "wp_kernel.cuh"
 #include "wp_model.h"
@@ -78,9 +80,13 @@ struct Slot {
   PinBuf<int64_t> h_row_off;
   PinBuf<int64_t> h_offsets;
   PinBuf<int32_t> h_csr;       // only for the row-major host API
+  // generic lexer engine scratch
+  DevBuf<uint16_t> lex_cls;
+  DevBuf<int32_t> lex_ncps, lex_tri, lex_tri_count;
   // bookkeeping of the chunk in flight
   int64_t doc0 = 0, ndocs = 0;
   void release() {
+    lex_cls.release(); lex_ncps.release(); lex_tri.release(); lex_tri_count.release();
     text.release(); offsets.release(); ids.release(); counts.release(); row_off.release(); csr.release();
     counter.release(); h_row_off.release(); h_offsets.release(); h_csr.release();
     if (stream) cudaStreamDestroy(stream);
@@ -99,6 +105,14 @@ struct Model {
   int32_t* d_tag = nullptr;
   uint16_t* d_cls = nullptr;
   uint8_t* d_blob = nullptr;
+  // generic lexer engine (any [wbd] model)
+  bool lex_ok = false;
+  int32_t* d_ow = nullptr;
+  int32_t* d_act_begin = nullptr;
+  int32_t* d_act_data = nullptr;
+  uint32_t* d_fn_ini = nullptr;
+  uint16_t* d_cls_words = nullptr;
+  PinBuf<int32_t> h_words;     // TextToWords staging: [ncps, tri_count, triples...]
   std::mutex mu;               // serialises the host-pointer entry points of this handle
   Slot slots[2];
   DevBuf<unsigned long long> dev_counter;   // for the device-pointer entry point
@@ -111,6 +125,12 @@ struct Model {
     if (d_tag) cudaFree(d_tag);
     if (d_cls) cudaFree(d_cls);
     if (d_blob) cudaFree(d_blob);
+    if (d_ow) cudaFree(d_ow);
+    if (d_act_begin) cudaFree(d_act_begin);
+    if (d_act_data) cudaFree(d_act_data);
+    if (d_fn_ini) cudaFree(d_fn_ini);
+    if (d_cls_words) cudaFree(d_cls_words);
+    h_words.release();
   }
 };
 
@@ -129,19 +149,31 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
     std::string err;
     if (!build_lexer_tables(ldb, &m->T, &err)) { set_error("lexer model: " + err); return nullptr; }
     LexerTables& T = m->T;
+    const size_t cells = (size_t)T.NS * ((size_t)T.NC + 1);
+    if (T.wide_states) { if (!upload((uint32_t**)&m->d_trans, T.trans32.data(), cells, 16)) return nullptr; }
+    else { if (!upload((uint16_t**)&m->d_trans, T.trans16.data(), cells, 16)) return nullptr; }
+    // generic lexer engine: serves TextToWords for every [wbd] model, and TextToIds for the
+    // grammars outside the FastPath shape
+    if (T.max_depth <= kMaxLexDepth) {
+      if (!upload(&m->d_ow, T.ow_of_state.data(), T.ow_of_state.size())) return nullptr;
+      if (!upload(&m->d_act_begin, T.act_begin.data(), T.act_begin.size())) return nullptr;
+      if (!upload(&m->d_act_data, T.act_data.data(), T.act_data.size(), 4)) return nullptr;
+      if (!upload(&m->d_fn_ini, T.fn_ini.data(), T.fn_ini.size(), 4)) return nullptr;
+      if (!upload(&m->d_cls_words, T.cls_words_of_cp.data(), T.cls_words_of_cp.size())) return nullptr;
+      m->lex_ok = true;
+    }
+    if (T.charmap_one_to_one && !upload(&m->d_cls, T.cls_of_cp.data(), T.cls_of_cp.size())) return nullptr;
     if (T.fast.ok && T.charmap_one_to_one && T.max_token_length <= 420) {
       build_wp_blob(T, &m->blob);
-      const size_t cells = (size_t)T.NS * ((size_t)T.NC + 1);
-      if (T.wide_states) { if (!upload((uint32_t**)&m->d_trans, T.trans32.data(), cells, 16)) return nullptr; }
-      else { if (!upload((uint16_t**)&m->d_trans, T.trans16.data(), cells, 16)) return nullptr; }
       if (!upload(&m->d_tag, T.tag_of_state.data(), T.tag_of_state.size())) return nullptr;
-      if (!upload(&m->d_cls, T.cls_of_cp.data(), T.cls_of_cp.size())) return nullptr;
       if (!upload(&m->d_blob, m->blob.bytes.data(), m->blob.bytes.size())) return nullptr;
       m->engine = 1;
-      // the dense table is the bulk of the host footprint; the device copy is the one that serves
-      std::vector<uint16_t>().swap(T.trans16);
-      std::vector<uint32_t>().swap(T.trans32);
+    } else if (m->lex_ok && T.charmap_one_to_one) {
+      m->engine = 2;
     }
+    // the dense table is the bulk of the host footprint; the device copy is the one that serves
+    std::vector<uint16_t>().swap(T.trans16);
+    std::vector<uint32_t>().swap(T.trans32);
   }
   return m.release();
 }
@@ -160,6 +192,34 @@ WpLaunch make_launch(const Model* m) {
   L.cls_dollar = m->T.cls_dollar;
   L.max_token_length = m->T.max_token_length;
   return L;
+}
+
+LexModelDev make_lex_model(const Model* m) {
+  LexModelDev d{};
+  d.trans = m->d_trans; d.wide = m->T.wide_states;
+  d.ow_of_state = m->d_ow; d.act_begin = m->d_act_begin; d.act_data = m->d_act_data; d.fn_ini = m->d_fn_ini;
+  d.fn_count = (int)m->T.fn_ini.size();
+  d.NC1 = (uint32_t)m->T.NC + 1; d.first_final = m->T.first_final; d.cls_caret = m->T.cls_caret; d.cls_dollar = m->T.cls_dollar;
+  d.initial = m->T.initial; d.max_depth = m->T.max_depth; d.max_token_length = m->T.max_token_length;
+  return d;
+}
+
+// b0 = 4-byte-aligned absolute offset the device text starts at, first_off = offsets[doc0]
+LexLaunch make_lex_launch(const Model*, Slot& s, int64_t first_off, int64_t b0, int64_t b1, int64_t ndocs,
+                          const uint16_t* cls_table, int tri_mul) {
+  LexLaunch X{};
+  X.text = s.text.p - b0;
+  X.offsets = s.offsets.p;
+  X.ndocs = ndocs;
+  X.text_bytes = b1;
+  X.base_offset = first_off;
+  X.cls_of_cp = cls_table;
+  X.cls_buf = s.lex_cls.p;
+  X.ncps = s.lex_ncps.p;
+  X.tri_buf = s.lex_tri.p;
+  X.tri_count = s.lex_tri_count.p;
+  X.tri_mul = tri_mul;
+  return X;
 }
 
 bool ensure_stream(Slot& s) {
@@ -190,18 +250,31 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
   if (nbytes && !cuda_ok(cudaMemcpyAsync(s.text.p, utf8 + b0, nbytes, cudaMemcpyHostToDevice, s.stream), "H2D text")) return false;
   if (!cuda_ok(cudaMemcpyAsync(s.offsets.p, offsets + doc0, ((size_t)ndocs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream), "H2D offsets")) return false;
 
-  WpLaunch L = make_launch(m);
-  L.text = s.text.p - b0;            // biased: absolute offsets index it directly
-  L.offsets = s.offsets.p;
-  L.ndocs = ndocs;
-  L.text_bytes = b1;
-  L.ids = s.ids.p;
-  L.counts = s.counts.p;
-  L.max_ids = max_ids;
-  L.unk_id = unk;
-  L.work_counter = s.counter.p;
   WpLaunchInfo info{};
-  if (!cuda_ok(wp_tokenize_launch(L, s.stream, &info), "tokenize launch")) return false;
+  if (m->engine == 2) {
+    // generic lexer: decode/classify -> Process_int triples -> wp post-pass
+    const size_t span = (size_t)(b1 - offsets[doc0]) + 8;
+    if (!s.lex_cls.reserve(span) || !s.lex_ncps.reserve((size_t)ndocs) || !s.lex_tri_count.reserve((size_t)ndocs) ||
+        !s.lex_tri.reserve(6 * span))
+      return false;
+    LexLaunch X = make_lex_launch(m, s, offsets[doc0], b0, b1, ndocs, m->d_cls, 2);
+    int nl = 0;
+    if (!cuda_ok(lex_launch(X, make_lex_model(m), s.stream, &nl), "lexer launch")) return false;
+    if (!cuda_ok(lex_wp_launch(X, s.ids.p, s.counts.p, max_ids, unk, s.stream, &nl), "post-pass launch")) return false;
+    info.launches = nl;
+  } else {
+    WpLaunch L = make_launch(m);
+    L.text = s.text.p - b0;            // biased: absolute offsets index it directly
+    L.offsets = s.offsets.p;
+    L.ndocs = ndocs;
+    L.text_bytes = b1;
+    L.ids = s.ids.p;
+    L.counts = s.counts.p;
+    L.max_ids = max_ids;
+    L.unk_id = unk;
+    L.work_counter = s.counter.p;
+    if (!cuda_ok(wp_tokenize_launch(L, s.stream, &info), "tokenize launch")) return false;
+  }
   if (!cuda_ok(wp_scan_counts(s.counts.p, s.row_off.p, ndocs, s.stream), "scan")) return false;
   if (!cuda_ok(wp_compact_launch(s.ids.p, s.counts.p, s.row_off.p, ndocs, max_ids, s.csr.p, s.stream), "compact")) return false;
   g_launches += info.launches + 2;
@@ -211,8 +284,9 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
 }
 
 // how many documents go into the next chunk: bounded text bytes and bounded id-matrix size
-int64_t chunk_docs(const int64_t* offsets, int64_t doc0, int64_t ndocs_total, int max_ids) {
-  const int64_t kMaxBytes = 64ll << 20;
+int64_t chunk_docs(const int64_t* offsets, int64_t doc0, int64_t ndocs_total, int max_ids, int engine) {
+  // the generic lexer keeps 26 scratch bytes per input byte (classes + triples)
+  const int64_t kMaxBytes = engine == 2 ? (8ll << 20) : (64ll << 20);
   const int64_t kMaxIdsCells = 160ll << 20;     // 640 MB of int32 per slot
   const int64_t max_docs = std::max<int64_t>(1, kMaxIdsCells / std::max(1, max_ids));
   int64_t d = doc0;
@@ -230,7 +304,7 @@ bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t nd
   int c = 0;
   int pending = -1;   // slot index of the chunk enqueued but not yet consumed
   while (d < ndocs) {
-    const int64_t nd = chunk_docs(offsets, d, ndocs, max_ids);
+    const int64_t nd = chunk_docs(offsets, d, ndocs, max_ids, m->engine);
     Slot& s = m->slots[c & 1];
     if (!enqueue_chunk(m, s, utf8, offsets, d, nd, max_ids, unk)) return false;
     if (pending >= 0) {
@@ -251,7 +325,7 @@ bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t nd
 
 bool check_batch_args(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, int max_ids) {
   if (!m) { set_error("null model"); return false; }
-  if (m->engine != 1) { set_error("no GPU engine for this model type yet"); return false; }
+  if (m->engine == 0) { set_error("no GPU engine for this model type yet"); return false; }
   if (ndocs < 0 || max_ids < 0 || (ndocs > 0 && (!utf8 || !offsets))) { set_error("bad batch arguments"); return false; }
   return true;
 }
@@ -368,7 +442,7 @@ int TextToIds(void* h, const char* s, int n, int32_t* ids, const int max_ids, co
   // blingfiretokdll.cpp:1619-1646 -> :1121: parameter validation happens before any work
   if (!h || n <= 0 || n > 1000000000 || !s) return 0;
   Model* m = (Model*)h;
-  if (m->engine != 1) { set_error("no GPU engine for this model type yet"); return 0; }
+  if (m->engine == 0) { set_error("no GPU engine for this model type yet"); return 0; }
   if (max_ids <= 0 || !ids) return 0;
   const int64_t offsets[2] = {0, n};
   int32_t count = 0;
@@ -388,9 +462,101 @@ int TextToIds_sp(void* h, const char* s, int n, int32_t* ids, const int max_ids,
   return TextToIds(h, s, n, ids, max_ids, unk);
 }
 
-int TextToWordsWithModel(const char*, int, char*, const int, void*) {
-  set_error("TextToWords: generic lexer engine not built yet");
-  return -1;
+// The reference embeds wbd.bin as a byte array and initialises it once under a mutex
+// (blingfiretokdll.cpp:114-133, :426-434).  Here the same model is loaded from
+// $BLINGFIRE_B200_WBD, or from wbd.bin next to this shared library, on first use.
+static Model* default_wbd_model() {
+  static std::mutex mu;
+  static Model* model = nullptr;
+  static bool tried = false;
+  std::lock_guard<std::mutex> lock(mu);
+  if (tried) return model;
+  tried = true;
+  std::string path;
+  if (const char* env = std::getenv("BLINGFIRE_B200_WBD")) path = env;
+  if (path.empty()) {
+    Dl_info info;
+    if (dladdr((const void*)&default_wbd_model, &info) && info.dli_fname) {
+      path = info.dli_fname;
+      const size_t slash = path.find_last_of('/');
+      path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/wbd.bin";
+    }
+  }
+  model = (Model*)LoadModel(path.c_str());
+  if (!model) set_error("default word-breaking model not found (" + path + "): " + g_last_error);
+  return model;
+}
+
+// blingfiretokdll.cpp:415-566 (TextToWordsWithOffsetsWithModel without offsets).  The lexer
+// (decode, classes, Process_int with every nested call) runs on the GPU; the host only turns the
+// (Tag, From, To) triples back into the ' '-joined UTF-8 string, like the reference's
+// ostringstream loop (:507-552).
+int TextToWordsWithModel(const char* s, int n, char* out, const int max_out, void* hModel) {
+  try {
+    Model* m = hModel ? (Model*)hModel : default_wbd_model();
+    if (!m) return -1;
+    if (n == 0) return 0;                                           // :446-448
+    if (n < 0 || n > 1000000000 || !s) return -1;                   // :449-454
+    if (!m->has_wbd || !m->lex_ok) { set_error("model has no lexer engine"); return -1; }
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
+    Slot& sl = m->slots[0];
+    if (!ensure_stream(sl)) return -1;
+    const size_t nb = (size_t)n;
+    if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve(2) || !sl.lex_cls.reserve(nb + 8) || !sl.lex_ncps.reserve(1) ||
+        !sl.lex_tri_count.reserve(1) || !sl.lex_tri.reserve(3 * nb + 8) || !m->h_words.reserve(3 * nb + 16))
+      return -1;
+    const int64_t offs[2] = {0, n};
+    if (!cuda_ok(cudaMemcpyAsync(sl.text.p, s, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return -1;
+    if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return -1;
+    LexLaunch X = make_lex_launch(m, sl, 0, 0, n, 1, m->d_cls_words, 1);   // MaxOut = 3 * MaxBuffSize (:492-499)
+    int nl = 0;
+    if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return -1;
+    g_launches += nl;
+    int32_t* hw = m->h_words.p;
+    if (!cuda_ok(cudaMemcpyAsync(hw, sl.lex_ncps.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return -1;
+    if (!cuda_ok(cudaMemcpyAsync(hw + 1, sl.lex_tri_count.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return -1;
+    if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
+    const int ncps = hw[0], rn = hw[1];
+    if (ncps <= 0) return -1;                                       // invalid UTF-8 or nothing decoded (:475-478)
+    if (rn < 0 || rn > 3 * ncps || rn % 3 != 0) return -1;          // :500-502
+    if (rn > 0) {
+      if (!cuda_ok(cudaMemcpyAsync(hw + 2, sl.lex_tri.p, (size_t)rn * 4, cudaMemcpyDeviceToHost, sl.stream), "D2H triples")) return -1;
+      if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
+    }
+    // code point -> byte offset of the (already validated) input, BOM skipped like the decoder
+    std::vector<int> cp_off((size_t)ncps + 1);
+    {
+      int p = (n >= 3 && (uint8_t)s[0] == 0xEF && (uint8_t)s[1] == 0xBB && (uint8_t)s[2] == 0xBF) ? 3 : 0;
+      for (int i = 0; i < ncps; ++i) {
+        cp_off[i] = p;
+        const uint8_t c = (uint8_t)s[p];
+        p += c < 0x80 ? 1 : (c & 0xE0) == 0xC0 ? 2 : (c & 0xF0) == 0xE0 ? 3 : 4;
+      }
+      cp_off[ncps] = p;
+    }
+    std::string os;
+    os.reserve(nb + (size_t)rn / 3 + 2);
+    bool added = false;
+    const int32_t* tri = hw + 2;
+    for (int i = 0; i < rn; i += 3) {
+      if (tri[i] == 4) continue;                                    // WBD_IGNORE_TAG (:511-514)
+      const int from = tri[i + 1], to = tri[i + 2];
+      if (from < 0 || from > ncps || to >= ncps || to < -1) return -1;
+      if (added) os.push_back(' ');
+      for (int b = cp_off[from]; b < cp_off[to + 1]; ++b) {
+        char c = s[b];
+        if (c == 0) c = 0x20;                                       // U+0000 -> U+0020 (:482)
+        if (c == ' ') c = '_';                                      // ' ' is the delimiter (:546)
+        os.push_back(c);
+      }
+      added = true;
+    }
+    os.push_back('\0');                                             // :555
+    const int len = (int)os.size();
+    if (len <= max_out && out) std::memcpy(out, os.data(), os.size());
+    return len;
+  } catch (const std::exception& e) { set_error(e.what()); return -1; }
 }
 int TextToWords(const char* s, int n, char* out, const int max_out) { return TextToWordsWithModel(s, n, out, max_out, nullptr); }
 

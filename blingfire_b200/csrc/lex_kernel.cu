@@ -1,0 +1,135 @@
+// lex_kernel.cu -- the generic lexer engine on the GPU: any [wbd] grammar (contexts, IW_ANY,
+// tag-less actions, nested calls), used for TextToWords (wbd.bin) and for TextToIds on lexer
+// models outside the FastPath shape.  Correctness-first: the grammar-agnostic path does not
+// attempt the chunk parallelism of wp_kernel.cu.
+//
+//   lex_decode_kernel   warp per document: strict UTF-8 decode + class lookup, compacted into
+//                       a per-document class array (FAStrUtf8ToArray + [FANormalize] + GetNewIw)
+//   lex_run_kernel      THREAD per document: FALexTools_t::Process_int with an explicit frame
+//                       stack (lex_core.cuh) -> (Tag, From, To) triples
+//   lex_wp_kernel       thread per document: TextToIdsWithOffsets_wp's post-pass over the triples
+#include "lex_kernel.cuh"
+
+#include "utf8_warp.cuh"
+
+namespace bfb200 {
+
+namespace {
+
+constexpr int kDecodeWarps = 8;
+
+__global__ void __launch_bounds__(kDecodeWarps * 32) lex_decode_kernel(const LexLaunch p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t* text32 = reinterpret_cast<const uint32_t*>(p.text);
+  const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
+  for (int64_t doc = warp; doc < p.ndocs; doc += nwarps) {
+    int64_t lo = __ldg(p.offsets + doc);
+    const int64_t hi = __ldg(p.offsets + doc + 1);
+    const int64_t n = hi - lo;
+    int result = 0;   // number of code points, -1 = invalid input, 0 = nothing to do
+    if (n > 0 && n <= 1000000000) {
+      if (n >= 3) {   // BOM (FAUtf8Utils.cpp:247-252)
+        const uint32_t b0 = __ldg(p.text + lo), b1 = __ldg(p.text + lo + 1), b2 = __ldg(p.text + lo + 2);
+        if (b0 == 0xEF && b1 == 0xBB && b2 == 0xBF) lo += 3;
+      }
+      uint16_t* cls = p.cls_buf + (__ldg(p.offsets + doc) - p.base_offset);
+      int m = 0;
+      unsigned bad = 0, sumlen = 0;
+      for (int64_t bpos = lo; bpos < hi;) {
+        const int64_t bs = bpos & ~(int64_t)3;
+        const int64_t pos0 = bs + lane * 4;
+        uint32_t w0, w1;
+        utf8_load_words(text32, pos0, padded_bytes, &w0, &w1);
+        const Utf8Lane d = utf8_decode_lane(w0, w1, pos0, bpos, hi);
+        bad |= d.bad; sumlen += d.sumlen;
+        const int cnt = __popc(d.start_mask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        int idx = m + incl - cnt;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (d.start_mask & (1u << k)) cls[idx++] = __ldg(p.cls_of_cp + d.cp[k]);
+        m += __shfl_sync(0xffffffffu, incl, 31);
+        bpos = bs + 128;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sumlen += __shfl_xor_sync(0xffffffffu, sumlen, o);
+      const bool invalid = __any_sync(0xffffffffu, bad != 0) || (int64_t)sumlen != hi - lo;
+      result = invalid ? -1 : m;
+    } else if (n != 0) {
+      result = -1;
+    }
+    if (lane == 0) p.ncps[doc] = result;
+  }
+}
+
+template <typename TE>
+__global__ void __launch_bounds__(128) lex_run_kernel(const LexLaunch p, const LexGlobal<TE> g) {
+  const int64_t doc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (doc >= p.ndocs) return;
+  const int n = p.ncps[doc];
+  int count = 0;
+  if (n > 0) {
+    const int64_t rel = __ldg(p.offsets + doc) - p.base_offset;
+    count = lex_process<TE>(g, p.cls_buf + rel, n, p.tri_buf + 3 * (int64_t)p.tri_mul * rel, 3 * p.tri_mul * n);
+  }
+  p.tri_count[doc] = count;
+}
+
+__global__ void __launch_bounds__(128) lex_wp_kernel(const LexLaunch p, int32_t* ids, int32_t* counts, int max_ids, int unk) {
+  const int64_t doc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (doc >= p.ndocs) return;
+  int c = 0;
+  if (p.ncps[doc] > 0) {
+    const int64_t rel = __ldg(p.offsets + doc) - p.base_offset;
+    c = wp_postpass(p.tri_buf + 3 * (int64_t)p.tri_mul * rel, p.tri_count[doc], ids + doc * (int64_t)max_ids, max_ids, unk);
+  }
+  counts[doc] = c;
+}
+
+}  // namespace
+
+cudaError_t lex_launch(const LexLaunch& p, const LexModelDev& m, cudaStream_t stream, int* launches) {
+  if (p.ndocs <= 0) return cudaSuccess;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t grid = (p.ndocs + kDecodeWarps - 1) / kDecodeWarps;
+  if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+  lex_decode_kernel<<<(int)grid, kDecodeWarps * 32, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int64_t g2 = (p.ndocs + 127) / 128;
+  if (m.wide) {
+    LexGlobal<uint32_t> g{};
+    g.trans = reinterpret_cast<const uint32_t*>(m.trans);
+    g.ow_of_state = m.ow_of_state; g.act_begin = m.act_begin; g.act_data = m.act_data; g.fn_ini = m.fn_ini; g.fn_count = m.fn_count;
+    g.NC1 = m.NC1; g.first_final = m.first_final; g.cls_caret = m.cls_caret; g.cls_dollar = m.cls_dollar; g.initial = m.initial;
+    g.max_depth = m.max_depth; g.max_token_length = m.max_token_length;
+    lex_run_kernel<uint32_t><<<(int)g2, 128, 0, stream>>>(p, g);
+  } else {
+    LexGlobal<uint16_t> g{};
+    g.trans = reinterpret_cast<const uint16_t*>(m.trans);
+    g.ow_of_state = m.ow_of_state; g.act_begin = m.act_begin; g.act_data = m.act_data; g.fn_ini = m.fn_ini; g.fn_count = m.fn_count;
+    g.NC1 = m.NC1; g.first_final = m.first_final; g.cls_caret = m.cls_caret; g.cls_dollar = m.cls_dollar; g.initial = m.initial;
+    g.max_depth = m.max_depth; g.max_token_length = m.max_token_length;
+    lex_run_kernel<uint16_t><<<(int)g2, 128, 0, stream>>>(p, g);
+  }
+  if (launches) *launches += 2;
+  return cudaGetLastError();
+}
+
+cudaError_t lex_wp_launch(const LexLaunch& p, int32_t* ids, int32_t* counts, int max_ids, int unk, cudaStream_t stream, int* launches) {
+  if (p.ndocs <= 0) return cudaSuccess;
+  lex_wp_kernel<<<(int)((p.ndocs + 127) / 128), 128, 0, stream>>>(p, ids, counts, max_ids, unk);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace bfb200

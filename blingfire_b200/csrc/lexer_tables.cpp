@@ -180,6 +180,13 @@ bool build_lexer_tables(const LdbImage& ldb, LexerTables* T, std::string* err) {
   T->cls_of_iw.assign(max_iw, (uint16_t)NC);
   for (size_t iw = 0; iw < max_iw; ++iw) T->cls_of_iw[iw] = (uint16_t)cls((int)iw);
 
+  T->cls_words_of_cp.assign((size_t)kMaxCodePoint + 1, (uint16_t)NC);
+  for (int cp = 0; cp <= kMaxCodePoint; ++cp) {
+    int x = cp == 0 ? 0x20 : cp;                                          // blingfiretokdll.cpp:482
+    if (x < kIwEpsilon) x = kIwEpsilon;                                   // FALexTools_t.h:259-261
+    T->cls_words_of_cp[cp] = (uint16_t)cls(x);
+  }
+
   T->charmap_one_to_one = true;
   if (T->has_charmap) {
     int tmp[16];

@@ -62,6 +62,9 @@ struct LexerTables {
   uint32_t cls_caret = 0, cls_dollar = 0;   // classes of IW_L_ANCHOR / IW_R_ANCHOR (NC if unmapped)
   std::vector<uint16_t> cls_of_cp;     // [0x110000] combined charmap+clamp+class (1->1 charmaps only)
   std::vector<uint16_t> cls_of_iw;     // [max_iw+1] plain class map (general path)
+  // TextToWords' view of a code point (blingfiretokdll.cpp:475-482): NO charmap, U+0000 -> U+0020,
+  // then the lexer's clamp and the class map
+  std::vector<uint16_t> cls_words_of_cp;   // [0x110000]
 
   // general charmap (1->N); only filled when !charmap_one_to_one
   std::vector<uint8_t> norm_count;     // [0x110000] 0..10, 0xFF = unmapped (keep code point)

@@ -197,3 +197,73 @@ def test_full_size_properties(bf, oracle):
         doc = bytes(text[offs[d]:offs[d + 1]])
         k, oids = oracle.text_to_ids(ho, doc, 512, 100)
         assert k == counts[d] and (oids[:k] == cids[coffs[d]:coffs[d + 1]]).all(), d
+
+
+# ---- generic lexer engine: TextToWords (cfg 1) and TextToIds on non-FastPath grammars ----
+
+def test_text_to_words_vs_golden(bf, golden):
+    """Default word breaker through the C ABI against outputs of the reference itself."""
+    import ctypes
+    L = bf.lib()
+    for w in golden["words"]:
+        data = base64.b64decode(w["input"])
+        cap = 2 * len(data) + 16
+        out = ctypes.create_string_buffer(cap)
+        n = L.TextToWords(data, len(data), out, cap)
+        assert n == w["ret"], data[:40]
+        if n > 0:
+            assert out.raw[:n] == base64.b64decode(w["out"]), data[:40]
+
+
+def test_cfg1_text_to_words_10k_ascii_lines(bf, oracle):
+    """BASELINE cfg 1: default TextToWords on the first 10 000 pure-ASCII lines <= 120 B, byte for
+    byte against the oracle; plus the too-small-buffer and README examples."""
+    import ctypes
+    L = bf.lib()
+    ho = oracle.load(model_path("wbd.bin"))
+    lines = [l for l in read_lines("test.txt") if len(l) <= 120 and all(c < 128 for c in l)][:10000]
+    assert len(lines) == 10000
+    out = ctypes.create_string_buffer(1024)
+    for l in lines:
+        n = L.TextToWords(l, len(l), out, 1024)
+        n2, s2 = oracle.text_to_words(ho, l, 1024)
+        assert n == n2 and out.raw[:n] == s2, l
+    # README.md:72-74
+    s = "I saw a girl with a telescope.".encode()
+    n = L.TextToWords(s, len(s), out, 1024)
+    assert out.raw[:n - 1] == b"I saw a girl with a telescope ."
+    # output does not fit: the required size is returned, nothing is copied (blingfiretokdll.cpp:560-565)
+    small = ctypes.create_string_buffer(b"\x7f" * 8, 8)
+    assert L.TextToWords(s, len(s), small, 8) == n and small.raw == b"\x7f" * 8
+    assert L.TextToWords(b"", 0, out, 1024) == 0
+    assert L.TextToWords(b"\xff\xfe", 2, out, 1024) == -1
+
+
+def test_text_to_words_with_model_multilingual(bf, oracle):
+    import ctypes
+    L = bf.lib()
+    for name in ("wbd.bin", "wbd_chuni.bin", "sbd.bin"):
+        h = bf.load_model(model_path(name))
+        ho = oracle.load(model_path(name))
+        out = ctypes.create_string_buffer(1 << 16)
+        for l in read_lines("test.multi.txt")[:1500] + [b"a\x00b c", b"can't won't cannot U.S.A. 3.14 e-mail", b"x" * 700]:
+            n = L.TextToWordsWithModel(l, len(l), out, 1 << 16, ctypes.c_void_p(h))
+            n2, s2 = oracle.text_to_words(ho, l, 1 << 16)
+            assert n == n2 and (n <= 0 or out.raw[:n] == s2), (name, l[:60])
+        bf.free_model(h)
+
+
+def test_generic_engine_text_to_ids(bf, oracle):
+    """TextToIds on a lexer model outside the FastPath shape (wbd.bin: contexts, tag-less actions,
+    nested calls) goes through the generic engine + exact post-pass."""
+    h = bf.load_model(model_path("wbd.bin"))
+    assert bf.lib().BlingFireB200ModelEngine(h) == 2
+    ho = oracle.load(model_path("wbd.bin"))
+    docs = read_lines("test.txt")[:3000] + read_lines("test.multi.txt")[:1000] + [b"", b"\xff", b"a" * 900]
+    buf, offs = bf.make_csr(docs)
+    ids, counts = bf.text_to_ids_batch(h, (buf, offs), 64, 100)
+    _, oids, ocounts = oracle.batch(ho, buf, offs, 64, 100, threads=4)
+    assert (counts == ocounts).all()
+    mask = np.arange(64)[None, :] < counts[:, None]
+    assert (ids[mask] == oids[mask]).all()
+    bf.free_model(h)

@@ -14,6 +14,7 @@
 
 #include "../../blingfire_b200/csrc/ldb.h"
 #include "../../blingfire_b200/csrc/lexer_tables.h"
+#include "../../blingfire_b200/csrc/lex_core.cuh"
 #include "../../blingfire_b200/csrc/wp_core.cuh"
 #include "../../blingfire_b200/csrc/wp_model.h"
 
@@ -75,6 +76,33 @@ const void* twin_ptr(void* h, int what) {
     default: return nullptr;
   }
 }
+
+// The generic lexer (lex_core.cuh) over UTF-32 input, whole document as one span.
+// mode 0: TextToIds view of the symbols (charmap + clamp + class); mode 1: TextToWords view.
+int twin_lex_process(void* h, const int* cps, int n, int32_t* out, int max_out, int mode) {
+  Twin* t = (Twin*)h;
+  if (!t->err.empty()) return -2;
+  const LexerTables& T = t->T;
+  if (mode == 0 && !T.charmap_one_to_one) return -2;
+  std::vector<uint16_t> cls((size_t)n + 1);
+  for (int i = 0; i < n; ++i) {
+    const int cp = cps[i];
+    const bool in_range = cp >= 0 && cp <= kMaxCodePoint;
+    cls[i] = !in_range ? (uint16_t)T.NC : (mode == 0 ? T.cls_of_cp[cp] : T.cls_words_of_cp[cp]);
+  }
+  auto run = [&](auto& g, const auto* trans) {
+    g.trans = trans; g.ow_of_state = T.ow_of_state.data(); g.act_begin = T.act_begin.data(); g.act_data = T.act_data.data();
+    g.fn_ini = T.fn_ini.data(); g.fn_count = (int)T.fn_ini.size(); g.NC1 = (uint32_t)T.NC + 1; g.first_final = T.first_final;
+    g.cls_caret = T.cls_caret; g.cls_dollar = T.cls_dollar; g.initial = T.initial; g.max_depth = T.max_depth;
+    g.max_token_length = T.max_token_length;
+    return lex_process(g, cls.data(), n, out, max_out);
+  };
+  if (T.wide_states) { LexGlobal<uint32_t> g{}; return run(g, T.trans32.data()); }
+  LexGlobal<uint16_t> g{};
+  return run(g, T.trans16.data());
+}
+
+int twin_wp_postpass(const int32_t* res, int rn, int32_t* ids, int max_ids, int unk) { return wp_postpass(res, rn, ids, max_ids, unk); }
 
 // One document through the mirrored warp algorithm.  `window` plays the role of the
 // kernel's per-warp window capacity (in code points); small values stress the carry logic.
