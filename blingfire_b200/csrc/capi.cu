@@ -21,6 +21,8 @@
 #include "ldb.h"
 #include "lex_kernel.cuh"
 #include "lexer_tables.h"
+#include "seg_tables.h"
+#include "sp_kernel.cuh"
 #include "wp_kernel.cuh"
 #include "wp_model.h"
 
@@ -80,13 +82,14 @@ struct Slot {
   PinBuf<int64_t> h_row_off;
   PinBuf<int64_t> h_offsets;
   PinBuf<int32_t> h_csr;       // only for the row-major host API
+  DevBuf<uint8_t> sp_arena;    // [pos-dict] engine: per-warp scratch for documents beyond the smem window
   // generic lexer engine scratch
   DevBuf<uint16_t> lex_cls;
   DevBuf<int32_t> lex_ncps, lex_tri, lex_tri_count;
   // bookkeeping of the chunk in flight
   int64_t doc0 = 0, ndocs = 0;
   void release() {
-    lex_cls.release(); lex_ncps.release(); lex_tri.release(); lex_tri_count.release();
+    lex_cls.release(); lex_ncps.release(); lex_tri.release(); lex_tri_count.release(); sp_arena.release();
     text.release(); offsets.release(); ids.release(); counts.release(); row_off.release(); csr.release();
     counter.release(); h_row_off.release(); h_offsets.release(); h_csr.release();
     if (stream) cudaStreamDestroy(stream);
@@ -113,6 +116,14 @@ struct Model {
   uint32_t* d_fn_ini = nullptr;
   uint16_t* d_cls_words = nullptr;
   PinBuf<int32_t> h_words;     // TextToWords staging: [ncps, tri_count, triples...]
+  // [pos-dict] engine (Unigram-LM / BPE over the Mealy automaton)
+  SegTables S;
+  DaEntry* d_da = nullptr;
+  uint16_t* d_sym = nullptr;
+  SegInfo* d_info = nullptr;
+  uint8_t* d_norm_count = nullptr;
+  uint32_t* d_norm_first = nullptr;
+  int32_t* d_norm_values = nullptr;
   std::mutex mu;               // serialises the host-pointer entry points of this handle
   Slot slots[2];
   DevBuf<unsigned long long> dev_counter;   // for the device-pointer entry point
@@ -130,6 +141,12 @@ struct Model {
     if (d_act_data) cudaFree(d_act_data);
     if (d_fn_ini) cudaFree(d_fn_ini);
     if (d_cls_words) cudaFree(d_cls_words);
+    if (d_da) cudaFree(d_da);
+    if (d_sym) cudaFree(d_sym);
+    if (d_info) cudaFree(d_info);
+    if (d_norm_count) cudaFree(d_norm_count);
+    if (d_norm_first) cudaFree(d_norm_first);
+    if (d_norm_values) cudaFree(d_norm_values);
     h_words.release();
   }
 };
@@ -175,7 +192,33 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
     std::vector<uint16_t>().swap(T.trans16);
     std::vector<uint32_t>().swap(T.trans32);
   }
+  if (m->has_seg) {
+    // blingfiretokdll.cpp:1636-1645: a [pos-dict] model is served by the segmentation engine
+    std::string err;
+    SegTables& S = m->S;
+    if (!build_seg_tables(ldb, &S, &err)) { set_error("segmentation model: " + err); return nullptr; }
+    if (S.max_arc_len > 1024) { set_error("segmentation model: tokens longer than 1024 symbols are not served"); return nullptr; }
+    if (!upload(&m->d_da, S.da.data(), S.da.size(), 8)) return nullptr;
+    if (!upload(&m->d_sym, S.sym_of_cp.data(), S.sym_of_cp.size())) return nullptr;
+    if (!upload(&m->d_info, S.info.data(), S.info.size(), 1)) return nullptr;
+    if (S.has_charmap) {
+      if (!upload(&m->d_norm_count, S.norm_count.data(), S.norm_count.size())) return nullptr;
+      if (!upload(&m->d_norm_first, S.norm_first.data(), S.norm_first.size())) return nullptr;
+      if (!upload(&m->d_norm_values, S.norm_values.data(), S.norm_values.size(), 16)) return nullptr;
+    }
+    m->engine = 3;
+  }
   return m.release();
+}
+
+SpModelDev make_sp_model(const Model* m) {
+  SpModelDev d{};
+  const SegTables& S = m->S;
+  d.da = m->d_da; d.root = S.root; d.sym_of_cp = m->d_sym; d.info = m->d_info; d.info_count = (int)S.info.size();
+  d.norm_count = S.has_charmap ? m->d_norm_count : nullptr; d.norm_first = m->d_norm_first; d.norm_values = m->d_norm_values;
+  d.tok_algo = S.tok_algo; d.id_offset = S.id_offset; d.use_raw_bytes = S.use_raw_bytes; d.no_dummy_prefix = S.no_dummy_prefix;
+  d.delim_inside_tokens = S.delim_inside_tokens; d.max_arc_len = S.max_arc_len;
+  return d;
 }
 
 WpLaunch make_launch(const Model* m) {
@@ -237,7 +280,7 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
   const size_t nbytes = (size_t)(b1 - b0);
   if (!s.text.reserve(nbytes + 64) || !s.offsets.reserve((size_t)ndocs + 1) || !s.counts.reserve((size_t)ndocs + 1) ||
       !s.row_off.reserve((size_t)ndocs + 1) || !s.ids.reserve((size_t)ndocs * (size_t)max_ids) ||
-      !s.counter.reserve(1) || !s.h_row_off.reserve((size_t)ndocs + 1))
+      !s.counter.reserve(2) || !s.h_row_off.reserve((size_t)ndocs + 2))
     return false;
   // a document yields at most one id per byte and at most max_ids ids
   size_t csr_cap = 0;
@@ -251,7 +294,29 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
   if (!cuda_ok(cudaMemcpyAsync(s.offsets.p, offsets + doc0, ((size_t)ndocs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream), "H2D offsets")) return false;
 
   WpLaunchInfo info{};
-  if (m->engine == 2) {
+  if (m->engine == 3) {
+    // [pos-dict] engine.  Documents whose symbols exceed the shared-memory window use a per-warp
+    // arena sized for the longest document of the chunk; the grid shrinks if the arena would not fit.
+    int64_t max_len = 0;
+    for (int64_t d = doc0; d < doc0 + ndocs; ++d) max_len = std::max(max_len, offsets[d + 1] - offsets[d]);
+    int64_t cap64 = (m->S.has_charmap ? 2 * (max_len + 1) : max_len + 1) + 2;
+    if (cap64 <= 1024) cap64 = 16;                       // everything fits the window: arena unused
+    if (cap64 > (1ll << 28)) { set_error("document too large for the segmentation engine"); return false; }
+    const int cap = (int)cap64;
+    const int64_t per_warp = sp_arena_bytes_per_warp(cap, m->S.max_arc_len);
+    int warps = sp_preferred_warps();
+    const int64_t budget = 6ll << 30;
+    if (per_warp * warps > budget) warps = (int)std::max<int64_t>(8, (budget / per_warp) / 8 * 8);
+    if (per_warp * warps > (24ll << 30)) { set_error("document too large for the segmentation engine arena"); return false; }
+    if (!s.sp_arena.reserve((size_t)(per_warp * warps)) || !s.counter.reserve(2)) return false;
+    SpLaunch X{};
+    X.text = s.text.p - b0; X.offsets = s.offsets.p; X.ndocs = ndocs; X.text_bytes = b1;
+    X.ids = s.ids.p; X.counts = s.counts.p; X.max_ids = max_ids; X.unk_id = unk;
+    X.work_counter = s.counter.p; X.arena = s.sp_arena.p; X.arena_stride = per_warp; X.arena_cap = cap; X.grid_warps = warps;
+    int nl = 0;
+    if (!cuda_ok(sp_tokenize_launch(X, make_sp_model(m), s.stream, &nl), "segmentation launch")) return false;
+    info.launches = nl;
+  } else if (m->engine == 2) {
     // generic lexer: decode/classify -> Process_int triples -> wp post-pass
     const size_t span = (size_t)(b1 - offsets[doc0]) + 8;
     if (!s.lex_cls.reserve(span) || !s.lex_ncps.reserve((size_t)ndocs) || !s.lex_tri_count.reserve((size_t)ndocs) ||
@@ -279,8 +344,23 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
   if (!cuda_ok(wp_compact_launch(s.ids.p, s.counts.p, s.row_off.p, ndocs, max_ids, s.csr.p, s.stream), "compact")) return false;
   g_launches += info.launches + 2;
   if (!cuda_ok(cudaMemcpyAsync(s.h_row_off.p, s.row_off.p, ((size_t)ndocs + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream), "D2H offsets")) return false;
+  // the kernel's error word sits right after the work counter (only the [pos-dict] engine sets it)
+  s.h_row_off.p[ndocs + 1] = 0;
+  if (m->engine == 3 &&
+      !cuda_ok(cudaMemcpyAsync(s.h_row_off.p + ndocs + 1, s.counter.p + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream), "D2H flag"))
+    return false;
   s.doc0 = doc0; s.ndocs = ndocs;
   return true;
+}
+
+// a kernel that could not serve a document exactly raises a flag instead of guessing
+bool chunk_ok(Slot& s) {
+  const int64_t flag = s.h_row_off.p[s.ndocs + 1] & 0xffffffffll;
+  if (flag == 0) return true;
+  set_error(flag == 2 ? "a document exceeds the segmentation engine's arena" :
+            flag == 3 ? "BPE arc scratch overflow (more than 32 vocabulary matches per symbol on average)" :
+                        "kernel reported an error");
+  return false;
 }
 
 // how many documents go into the next chunk: bounded text bytes and bounded id-matrix size
@@ -310,7 +390,7 @@ bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t nd
     if (pending >= 0) {
       Slot& ps = m->slots[pending];
       if (!cuda_ok(cudaStreamSynchronize(ps.stream), "sync")) return false;
-      if (!sink(ps)) return false;
+      if (!chunk_ok(ps) || !sink(ps)) return false;
     }
     pending = c & 1;
     d += nd; ++c;
@@ -318,7 +398,7 @@ bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t nd
   if (pending >= 0) {
     Slot& ps = m->slots[pending];
     if (!cuda_ok(cudaStreamSynchronize(ps.stream), "sync")) return false;
-    if (!sink(ps)) return false;
+    if (!chunk_ok(ps) || !sink(ps)) return false;
   }
   return true;
 }

@@ -1,0 +1,539 @@
+// sp_kernel.cu -- TextToIdsWithOffsets_sp (blingfiretokdll.cpp:1349-1535) on the GPU for the
+// [pos-dict] models: the shared front end (dummy prefix, UTF-8 decode or raw bytes, FANormalize,
+// whitespace -> U+2581 collapse), then
+//   * Unigram-LM best path  FATokenSegmentationTools_1best_t::Process        (.h:174-279)
+//   * BPE / BPE-opt / BPE-opt-with-merges  FATokenSegmentationTools_1best_bpe[_with_merges]_t::Process (.h:125-316)
+// over the Mealy MPH automaton laid out as a double-array (seg_tables.h): one 16-byte gather per
+// GetDestOw.  Integer work plus fp64 adds in the reference's operand order (no FMA: there is no
+// multiply to contract).
+//
+// One document per warp, persistent grid, documents handed out by an atomic counter.  Symbols
+// live in a shared-memory window when the document fits, in the warp's global arena otherwise.
+//   Unigram: lanes enumerate the arcs of up to 32 start positions in parallel; the relaxation
+//            runs in start order (the reference's order: ties keep the earlier start) with the
+//            arcs of one start spread over the lanes; back-trace by one lane; ordered emission.
+//   BPE:     tokens never contain U+2581 past their first symbol (checked at load), so the
+//            U+2581-delimited segments are independent: one lane per segment takes the bpe-opt
+//            whole-word shortcut; the remaining segments are processed warp-cooperatively
+//            (arc enumeration -> (rank,id,start) bitonic sort -> the reference's greedy claim).
+#include "sp_kernel.cuh"
+
+#include <cfloat>
+
+#include "utf8_warp.cuh"
+
+namespace bfb200 {
+
+namespace {
+
+constexpr int kSpWarps = 8;
+constexpr int kSpThreads = kSpWarps * 32;
+constexpr int kSpWin = 1024;              // symbols in the shared-memory window
+constexpr int kTileArcs = 1024;           // arc slots of one tile of start positions (Unigram)
+constexpr int kArcsPerSym = 32;           // arena capacity for BPE arcs, per symbol of capacity
+
+struct Arc3 { int start, end, id; float rank; };   // 16 B
+
+// per-warp workspace (shared memory or arena) for documents of up to `cap` symbols
+struct Work {
+  int32_t* sym;        // [cap+2] symbols (code points or bytes); later reused for ids
+  int32_t* tmp;        // [cap+2] staging; Unigram: begin[]; BPE: ids_at[]
+  double* score;       // [cap]   Unigram best score; BPE: segment-start list (int32 view)
+  int32_t* bid;        // [cap]   Unigram best id; BPE: first-arc index, then tos[]
+  uint8_t* flag;       // [cap+4] token-start marks / BPE intermediate[]
+  int2* tile;          // [kTileArcs] Unigram arc tile {end, key}
+  int cap;
+};
+
+__host__ __device__ inline int64_t align16(int64_t v) { return (v + 15) & ~(int64_t)15; }
+__host__ __device__ inline int64_t work_bytes(int cap) {
+  return align16(4ll * (cap + 2)) * 2 + align16(8ll * cap) + align16(4ll * cap) + align16(cap + 4) + align16(8ll * kTileArcs);
+}
+__device__ inline Work make_work(uint8_t* base, int cap) {
+  Work w; int64_t o = 0;
+  w.sym = (int32_t*)(base + o); o += align16(4ll * (cap + 2));
+  w.tmp = (int32_t*)(base + o); o += align16(4ll * (cap + 2));
+  w.score = (double*)(base + o); o += align16(8ll * cap);
+  w.bid = (int32_t*)(base + o); o += align16(4ll * cap);
+  w.flag = base + o; o += align16(cap + 4);
+  w.tile = (int2*)(base + o);
+  w.cap = cap;
+  return w;
+}
+
+__device__ __forceinline__ bool sp_is_white(int c) {   // blingfiretokdll.h:17-21
+  return c <= 0x20 || c == 0xa0 || (c >= 0x2000 && c <= 0x200f) || c == 0x202f || c == 0x205f || c == 0x2060 ||
+         c == 0x2420 || c == 0x2424 || c == 0x3000 || c == 0xfeff;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// GetDestOw on the double-array (FAMealyDfa_pack_triv.cpp:69-244); q is the state's base
+__device__ __forceinline__ bool da_step(const SpModelDev& m, uint32_t& q, int c, int& ow, bool& fin) {
+  if ((unsigned)c > 0x10FFFFu) return false;
+  const uint16_t s = __ldg(m.sym_of_cp + c);
+  if (s == kNoSym) return false;
+  const uint4 e = __ldg(reinterpret_cast<const uint4*>(m.da) + ((size_t)q + s));
+  if (e.x != q) return false;
+  ow = (int)e.z; fin = (e.y & kDaFinalBit) != 0; q = e.y & ~kDaFinalBit;
+  return true;
+}
+
+// I2Info row (FAMultiMap_pack_fixed.cpp:140-162); an unusable key yields {unk, 0}
+__device__ __forceinline__ void sp_info(const SpModelDev& m, int key, int unk, int& id, float& score) {
+  id = unk; score = 0.0f;
+  if (key >= 0 && key < m.info_count) {
+    const int2 v = __ldg(reinterpret_cast<const int2*>(m.info) + key);
+    id = v.x; score = __int_as_float(v.y);
+  }
+}
+
+// ---- front end: counts (store=false) or writes (store=true) the raw symbol stream -----------
+// Returns the number of raw symbols incl. the dummy prefix, or -1 on invalid UTF-8 / no symbols.
+// blingfiretokdll.cpp:1372-1412
+__device__ int sp_raw_symbols(const SpModelDev& m, const uint8_t* text, int64_t lo0, int64_t hi, int64_t padded_bytes,
+                              int32_t* out, bool store, int lane) {
+  int64_t lo = lo0;
+  if (hi - lo >= 3) {
+    const uint32_t b0 = __ldg(text + lo), b1 = __ldg(text + lo + 1), b2 = __ldg(text + lo + 2);
+    if (b0 == 0xEF && b1 == 0xBB && b2 == 0xBF) lo += 3;   // both decoders skip the BOM
+  }
+  const int off = m.no_dummy_prefix ? 0 : 1;
+  if (store && off && lane == 0) out[0] = kSpDelim;
+  int cnt = 0;
+  if (m.use_raw_bytes) {                                    // FAStrUtf8AsBytesToArray
+    if (store) for (int64_t p = lo + lane; p < hi; p += 32) out[off + (p - lo)] = (int)__ldg(text + p);
+    cnt = (int)(hi - lo);
+  } else {                                                  // FAStrUtf8ToArray
+    const uint32_t* text32 = reinterpret_cast<const uint32_t*>(text);
+    unsigned bad = 0, sumlen = 0;
+    for (int64_t bpos = lo; bpos < hi;) {
+      const int64_t bs = bpos & ~(int64_t)3;
+      const int64_t pos0 = bs + lane * 4;
+      uint32_t w0, w1;
+      utf8_load_words(text32, pos0, padded_bytes, &w0, &w1);
+      const Utf8Lane d = utf8_decode_lane(w0, w1, pos0, bpos, hi);
+      bad |= d.bad; sumlen += d.sumlen;
+      const int c = __popc(d.start_mask);
+      const int incl = warp_incl_scan(c, lane);
+      if (store) {
+        int idx = off + cnt + incl - c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (d.start_mask & (1u << k)) out[idx++] = (int)d.cp[k];
+      }
+      cnt += __shfl_sync(0xffffffffu, incl, 31);
+      bpos = bs + 128;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sumlen += __shfl_xor_sync(0xffffffffu, sumlen, o);
+    if (__any_sync(0xffffffffu, bad != 0) || (int64_t)sumlen != hi - lo) return -1;
+  }
+  if (cnt <= 0) return -1;                                  // BuffSize <= 0 (:1409)
+  return cnt + off;
+}
+
+// FANormalize over src[0..n) (FAUtils_cl.h:311-369): returns the normalized length; writes dst when given.
+__device__ int sp_normalize(const SpModelDev& m, const int32_t* src, int n, int32_t* dst, int lane) {
+  int total = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    int c = 0, cp = 0; unsigned nc = 0xFF;
+    if (i < n) {
+      cp = src[i];
+      nc = ((unsigned)cp <= 0x10FFFFu) ? (unsigned)__ldg(m.norm_count + cp) : 0xFFu;
+      c = nc == 0xFF ? 1 : (int)nc;
+    }
+    const int incl = warp_incl_scan(c, lane);
+    if (dst && i < n) {
+      const int o = total + incl - c;
+      if (nc == 0xFF) dst[o] = cp;
+      else { const uint32_t f = __ldg(m.norm_first + cp); for (int k = 0; k < c; ++k) dst[o + k] = __ldg(m.norm_values + f + k); }
+    }
+    total += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  return total;
+}
+
+// whitespace runs -> one U+2581, one trailing U+2581 dropped (blingfiretokdll.cpp:1462-1496).
+// A white symbol is kept iff the previous OUTPUT symbol is not U+2581, which is equivalent to
+//   i == 0  ||  (src[i-1] is not white && src[i-1] != U+2581).
+__device__ int sp_collapse(const int32_t* src, int n, int32_t* dst, int lane) {
+  int total = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    bool keep = false; int c = 0;
+    if (i < n) {
+      c = src[i];
+      const bool w = sp_is_white(c);
+      if (!w || i == 0) keep = true;
+      else { const int p = src[i - 1]; keep = !sp_is_white(p) && p != kSpDelim; }
+      if (w) c = kSpDelim;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) dst[total + __popc(bal & bf_lanemask_lt())] = c;
+    total += __popc(bal);
+  }
+  __syncwarp();
+  if (total > 1 && dst[total - 1] == kSpDelim) --total;     // :1491-1493
+  return total;
+}
+
+// ordered emission of the tokens marked in w.flag (bit 1) with ids taken from idsrc[]
+__device__ int sp_emit(const Work& w, const int32_t* idsrc, int N, int32_t* row, int max_ids, int unk, int id_offset,
+                       bool map_unknown, int lane) {
+  int out = 0;
+  for (int p0 = 0; p0 < N; p0 += 32) {
+    const int q = p0 + lane;
+    const bool f = q < N && (w.flag[q] & 2);
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int rank = out + __popc(bal & bf_lanemask_lt());
+    if (f && rank < max_ids) {
+      int id = idsrc[q];
+      if (map_unknown && id == -1) id = unk;
+      row[rank] = id + id_offset;                           // ids[k] = id + IdOffset, UNK included (:1516)
+    }
+    out += __popc(bal);
+  }
+  return out < max_ids ? out : max_ids;
+}
+
+// =====================================================================================
+// Unigram-LM best path (FATokenSegmentationTools_1best_t.h:174-279)
+// =====================================================================================
+__device__ int sp_unigram(const SpModelDev& m, Work& w, int N, int32_t* row, int max_ids, int unk, int lane) {
+  int32_t* begin = w.tmp;
+  for (int i = lane; i < N; i += 32) { w.score[i] = -(double)FLT_MAX; w.bid[i] = -1; begin[i] = -1; w.flag[i] = 0; }
+  __syncwarp();
+  int per = m.max_arc_len < 1 ? 1 : m.max_arc_len;          // an upper bound of the arcs of one start
+  if (per > kTileArcs) per = kTileArcs;
+  int S = kTileArcs / per; if (S > 32) S = 32;
+  for (int t0 = 0; t0 < N; t0 += S) {
+    // ---- phase A: lane l enumerates the arcs of start t0 + l (:196-224) ----
+    const int start = t0 + lane;
+    int narc = 0;
+    if (lane < S && start < N) {
+      uint32_t q = m.root; int sum = 0;
+      for (int i = start; i < N; ++i) {
+        int ow; bool fin;
+        if (!da_step(m, q, w.sym[i], ow, fin)) break;
+        sum += ow;
+        if (fin && narc < per) { w.tile[lane * per + narc] = make_int2(i, sum); ++narc; }
+        if (q == 0) break;                                   // a leaf: every further step fails
+      }
+    }
+    __syncwarp();
+    // ---- phase B: relax in start order; the arcs of one start end at distinct positions ----
+    const int ns = min(S, N - t0);
+    for (int l = 0; l < ns; ++l) {
+      const int st = t0 + l;
+      const int cnt = __shfl_sync(0xffffffffu, narc, l);
+      const double prev = st > 0 ? w.score[st - 1] : 0.0;
+      if (cnt > 0) {
+        for (int k = lane; k < cnt; k += 32) {               // AddArc (:118-142)
+          const int2 a = w.tile[l * per + k];
+          int id; float sc;
+          sp_info(m, a.y, -1, id, sc);
+          const double cand = (double)sc + prev;
+          if (w.score[a.x] < cand) { begin[a.x] = st; w.bid[a.x] = id; w.score[a.x] = cand; }
+        }
+      } else if (lane == 0) {                                // AddUnknownArc (:145-171)
+        const double cand = (double)(-100000.0f) + prev;
+        if (w.score[st] < cand) {
+          begin[st] = st; w.bid[st] = -1; w.score[st] = cand;
+          if (st > 0 && w.bid[st - 1] == -1) begin[st] = begin[st - 1];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // ---- back-trace (:227-257): mark token starts, move each token's id to its start slot ----
+  if (lane == 0) {
+    int end = N - 1;
+    while (end >= 0) {
+      const int b = begin[end];
+      const int id = w.bid[end];
+      if (b < 0) { w.flag[0] |= 2; w.sym[0] = id; break; }   // never-set arc: the reference emits it first and stops
+      w.flag[b] |= 2;
+      w.sym[b] = id;                                         // symbols before `end` are not read again
+      end = b - 1;
+    }
+  }
+  __syncwarp();
+  return sp_emit(w, w.sym, N, row, max_ids, unk, m.id_offset, true, lane);
+}
+
+// =====================================================================================
+// BPE family (FATokenSegmentationTools_1best_bpe_t.h:125-316, ..._with_merges_t.h)
+// =====================================================================================
+__device__ __forceinline__ bool arc_less(const Arc3& a, const Arc3& b, bool merges) {
+  if (merges) {                                              // ..._with_merges_t.h:242-262: bigger ranks first
+    if (a.rank > b.rank) return true;
+    if (a.rank < b.rank) return false;
+  }
+  if (a.id != b.id) return a.id < b.id;                      // ..._bpe_t.h:238-255
+  return a.start < b.start;
+}
+
+__device__ __forceinline__ int count_arcs_from(const SpModelDev& m, const Work& w, int s, int b) {
+  uint32_t q = m.root; int cnt = 0;
+  for (int i = s; i < b; ++i) {
+    int ow; bool fin;
+    if (!da_step(m, q, w.sym[i], ow, fin)) break;
+    if (fin) ++cnt;
+    if (q == 0) break;
+  }
+  return cnt;
+}
+
+// One segment [a, b), warp-cooperatively.  `arcs` is warp-private scratch of arc_cap entries.
+// Tokens are written position-indexed: ids_at[start], w.flag[start] |= 2.  false = scratch overflow.
+__device__ bool bpe_segment(const SpModelDev& m, Work& w, int N, int a, int b, int unk, Arc3* arcs, int arc_cap,
+                            int32_t* ids_at, int lane, bool fast, bool merges) {
+  // ---- arcs of every start, grouped by start (count -> scan -> write) ----
+  int total = 0;
+  for (int s0 = a; s0 < b; s0 += 32) {
+    const int s = s0 + lane;
+    const int cnt = s < b ? count_arcs_from(m, w, s, b) : 0;
+    const int incl = warp_incl_scan(cnt, lane);
+    if (s < b) w.bid[s] = total + incl - cnt;
+    total += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  const int L = b - a;
+  if ((int64_t)total + 2ll * ((int64_t)total + L) + 4 > (int64_t)arc_cap) return false;
+  for (int s0 = a; s0 < b; s0 += 32) {
+    const int s = s0 + lane;
+    if (s < b) {
+      int wr = w.bid[s];
+      uint32_t q = m.root; int sum = 0;
+      for (int i = s; i < b; ++i) {
+        int ow; bool fin;
+        if (!da_step(m, q, w.sym[i], ow, fin)) break;
+        sum += ow;
+        if (fin) {
+          Arc3 A; A.start = s; A.end = i;
+          sp_info(m, sum, unk, A.id, A.rank);
+          if (!merges) A.rank = 0.0f;
+          arcs[wr++] = A;
+        }
+        if (q == 0) break;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- the reference's arc vector for this segment: bpe-opt at the start, unknown runs (:188-230) ----
+  Arc3* fin_arcs = arcs + total;
+  int nfin = 0;
+  if (lane == 0) {
+    for (int s = a; s < b; ++s) {
+      const int first = w.bid[s];
+      const int cnt = ((s + 1 < b) ? w.bid[s + 1] : total) - first;
+      const bool tok_start = w.sym[s] == kSpDelim;
+      const int cnt0 = nfin;
+      int ff = s;
+      for (int k = 0; k < cnt; ++k) {
+        const Arc3 A = arcs[first + k];
+        const bool boundary = (A.end < N - 1) ? (w.sym[A.end + 1] == kSpDelim) : true;
+        if (fast && tok_start && boundary && cnt0 < nfin) { fin_arcs[cnt0] = A; nfin = cnt0 + 1; ff = A.end; }
+        else fin_arcs[nfin++] = A;
+      }
+      if (cnt == 0) {
+        if (nfin > 0 && fin_arcs[nfin - 1].id == unk) fin_arcs[nfin - 1].end = s;   // compares ids (:219-225)
+        else { Arc3 U; U.start = s; U.end = s; U.id = unk; U.rank = 0.0f; fin_arcs[nfin++] = U; }
+      }
+      if (fast) s = ff;
+    }
+  }
+  nfin = __shfl_sync(0xffffffffu, nfin, 0);
+  __syncwarp();
+  // ---- sort (:238-262): bitonic network over a power-of-two padded copy ----
+  int P = 1; while (P < nfin) P <<= 1;
+  for (int i = nfin + lane; i < P; i += 32) { Arc3 Z; Z.start = 0x7fffffff; Z.end = 0; Z.id = 0x7fffffff; Z.rank = -FLT_MAX; fin_arcs[i] = Z; }
+  __syncwarp();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += 32) {
+        const int l = i ^ j;
+        if (l > i) {
+          const Arc3 x = fin_arcs[i], y = fin_arcs[l];
+          const bool up = (i & k) == 0;
+          if (up ? arc_less(y, x, merges) : arc_less(x, y, merges)) { fin_arcs[i] = y; fin_arcs[l] = x; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // ---- greedy claim in sorted order (:264-296); intermediate[] = bit 0 of w.flag, tos[] = w.bid ----
+  for (int i = a + lane; i < b; i += 32) { w.flag[i] = 0; w.bid[i] = i; ids_at[i] = unk; }
+  __syncwarp();
+  if (lane == 0) {
+    for (int k = 0; k < nfin; ++k) {
+      const Arc3 A = fin_arcs[k];
+      // position b starts the next segment: no arc crosses it, so it is never an intermediate
+      const bool end_free = (A.end + 1 >= b) || (w.flag[A.end + 1] & 1) == 0;
+      if ((w.flag[A.start] & 1) == 0 && end_free) {
+        w.bid[A.start] = A.end; ids_at[A.start] = A.id;
+        for (int j = A.start + 1; j <= A.end; ++j) w.flag[j] |= 1;
+      }
+    }
+    // tokens: follow tos[] from the segment start (:299-313).  (tos[] starts as the identity; the
+    // reference's zero-initialised tos[] would loop forever on an unclaimed start, which a
+    // vocabulary with all single symbols never produces.)
+    for (int s = a; s < b; ++s) { w.flag[s] |= 2; s = w.bid[s]; }
+  }
+  __syncwarp();
+  return true;
+}
+
+__device__ int sp_bpe(const SpModelDev& m, Work& w, int N, int32_t* row, int max_ids, int unk, Arc3* arcs, int arc_cap,
+                      int lane, bool* overflow) {
+  const bool merges = m.tok_algo == kTokenizeBpeOptWithMerges;
+  const bool fast = merges || m.tok_algo == kTokenizeBpeOpt;
+  int32_t* ids_at = w.tmp;
+  int32_t* seg = reinterpret_cast<int32_t*>(w.score);       // segment starts (w.score is unused by BPE)
+  int nseg = 0;
+  for (int p0 = 0; p0 < N; p0 += 32) {
+    const int p = p0 + lane;
+    const bool f = p < N && (p == 0 || (!m.delim_inside_tokens && w.sym[p] == kSpDelim));
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (f) seg[nseg + __popc(bal & bf_lanemask_lt())] = p;
+    nseg += __popc(bal);
+    if (p < N) w.flag[p] = 0;
+  }
+  __syncwarp();
+  for (int g0 = 0; g0 < nseg; g0 += 32) {
+    // ---- one lane per segment: the bpe-opt whole-word shortcut ----
+    // Walking from the segment start, an arc that ends exactly at the segment end after a shorter
+    // arc was already seen makes the reference keep ONLY that arc and skip the interior starts
+    // (:188-206,:228-230); a one-symbol segment with an arc is a single arc as well.
+    const int g = g0 + lane;
+    bool hard = false; int a = 0, b = 0;
+    if (g < nseg) {
+      a = seg[g]; b = g + 1 < nseg ? seg[g + 1] : N;
+      uint32_t q = m.root; int sum = 0, narcs = 0, whole_key = -1; bool whole = false;
+      for (int i = a; i < b; ++i) {
+        int ow; bool fin;
+        if (!da_step(m, q, w.sym[i], ow, fin)) break;
+        sum += ow;
+        if (fin) { if (i == b - 1 && (narcs > 0 || b - a == 1)) { whole = true; whole_key = sum; } ++narcs; }
+        if (q == 0) break;
+      }
+      const bool tok_start = w.sym[a] == kSpDelim;
+      if (whole && ((fast && tok_start) || b - a == 1)) {
+        int id; float r;
+        sp_info(m, whole_key, unk, id, r);
+        ids_at[a] = id; w.flag[a] = 2;
+      } else hard = true;
+    }
+    // ---- the other segments of this round, one at a time, warp-cooperatively ----
+    unsigned hb = __ballot_sync(0xffffffffu, hard);
+    while (hb) {
+      const int l = __ffs(hb) - 1; hb &= hb - 1;
+      const int sa = __shfl_sync(0xffffffffu, a, l), sb = __shfl_sync(0xffffffffu, b, l);
+      if (!bpe_segment(m, w, N, sa, sb, unk, arcs, arc_cap, ids_at, lane, fast, merges)) { *overflow = true; return 0; }
+    }
+  }
+  __syncwarp();
+  return sp_emit(w, ids_at, N, row, max_ids, unk, m.id_offset, false, lane);
+}
+
+template <bool kBpe>
+__global__ void __launch_bounds__(kSpThreads, 1) sp_tokenize_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * kSpWarps + warp;
+  Work ws = make_work(smem + (size_t)warp * work_bytes(kSpWin), kSpWin);
+  uint8_t* my_arena = p.arena + (size_t)gwarp * p.arena_stride;
+  Work wa = make_work(my_arena, p.arena_cap);
+  Arc3* arcs = reinterpret_cast<Arc3*>(my_arena + work_bytes(p.arena_cap));
+  const int arc_cap = p.arena_cap * kArcsPerSym + 4096;
+  const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
+
+  for (;;) {
+    unsigned long long d64 = 0;
+    if (lane == 0) d64 = atomicAdd(p.work_counter, 1ull);
+    d64 = __shfl_sync(0xffffffffu, d64, 0);
+    if ((int64_t)d64 >= p.ndocs) break;
+    const int64_t doc = (int64_t)d64;
+    const int64_t lo = __ldg(p.offsets + doc), hi = __ldg(p.offsets + doc + 1);
+    const int64_t n = hi - lo;
+    int result = 0;
+    if (n > 0 && n <= 1000000000) {                                      // :1362
+      const int nraw = sp_raw_symbols(m, p.text, lo, hi, padded_bytes, nullptr, false, lane);
+      bool ok = nraw > 0;
+      const int64_t need = (m.norm_count ? 2 * (n + 1) : (int64_t)nraw) + 2;   // staging bound (:1423)
+      const bool fits_smem = need <= kSpWin;
+      if (ok && !fits_smem && need > (int64_t)p.arena_cap) { ok = false; if (lane == 0) atomicExch(error_flag, 2); }
+      if (ok) {
+        Work& w = fits_smem ? ws : wa;
+        sp_raw_symbols(m, p.text, lo, hi, padded_bytes, w.sym, true, lane);
+        __syncwarp();
+        int N = nraw;
+        int32_t* cur = w.sym; int32_t* other = w.tmp;
+        if (m.norm_count) {
+          const int nn = sp_normalize(m, cur, N, nullptr, lane);
+          if (nn <= 0 || (int64_t)nn > 2 * (n + 1)) ok = false;          // :1442-1446
+          else { sp_normalize(m, cur, N, other, lane); __syncwarp(); N = nn; int32_t* t = cur; cur = other; other = t; }
+        }
+        if (ok) {
+          N = sp_collapse(cur, N, other, lane);
+          __syncwarp();
+          if (other != w.sym) { for (int i = lane; i < N; i += 32) w.sym[i] = other[i]; __syncwarp(); }
+          if (N > 0) {
+            int32_t* row = p.ids + doc * (int64_t)p.max_ids;
+            if (kBpe) {
+              bool overflow = false;
+              result = sp_bpe(m, w, N, row, p.max_ids, p.unk_id, arcs, arc_cap, lane, &overflow);
+              if (overflow) { result = 0; if (lane == 0) atomicExch(error_flag, 3); }
+            } else {
+              result = sp_unigram(m, w, N, row, p.max_ids, p.unk_id, lane);
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) p.counts[doc] = result;
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+int64_t sp_arena_bytes_per_warp(int cap, int) {
+  return align16(work_bytes(cap) + 16ll * ((int64_t)cap * kArcsPerSym + 4096) + 256);
+}
+
+int sp_preferred_warps() {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms * kSpWarps;
+}
+
+cudaError_t sp_tokenize_launch(const SpLaunch& p, const SpModelDev& m, cudaStream_t stream, int* launches) {
+  if (p.ndocs <= 0) return cudaSuccess;
+  const bool bpe = m.tok_algo == kTokenizeBpe || m.tok_algo == kTokenizeBpeOpt || m.tok_algo == kTokenizeBpeOptWithMerges;
+  const size_t smem = (size_t)kSpWarps * work_bytes(kSpWin);
+  auto kern = bpe ? sp_tokenize_kernel<true> : sp_tokenize_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int grid = p.grid_warps / kSpWarps;
+  if (grid < 1) return cudaErrorInvalidValue;
+  const int64_t needed = (p.ndocs + kSpWarps - 1) / kSpWarps;
+  if (needed < grid) grid = (int)needed;
+  e = cudaMemsetAsync(p.work_counter, 0, 16, stream);   // counter (8 B) + error flag (4 B)
+  if (e != cudaSuccess) return e;
+  int* err = reinterpret_cast<int*>(p.work_counter + 1);
+  kern<<<grid, kSpThreads, smem, stream>>>(p, m, err);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace bfb200

@@ -1,0 +1,49 @@
+// sp_kernel.cuh -- launch interface of the [pos-dict] (SentencePiece-style) engines: Unigram-LM
+// best path and BPE over the Mealy MPH automaton (sp_kernel.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "seg_tables.h"
+
+namespace bfb200 {
+
+struct SpModelDev {
+  const DaEntry* da;             // double-array automaton
+  uint32_t root;
+  const uint16_t* sym_of_cp;     // [0x110000]
+  const SegInfo* info;           // [info_count]
+  int info_count;
+  const uint8_t* norm_count;     // [0x110000] or nullptr (no charmap)
+  const uint32_t* norm_first;
+  const int32_t* norm_values;
+  int tok_algo, id_offset;
+  bool use_raw_bytes, no_dummy_prefix, delim_inside_tokens;
+  int max_arc_len;
+};
+
+struct SpLaunch {
+  const uint8_t* text;           // biased: absolute offsets index it
+  const int64_t* offsets;        // [ndocs+1]
+  int64_t ndocs;
+  int64_t text_bytes;
+  int32_t* ids;                  // [ndocs][max_ids]
+  int32_t* counts;               // [ndocs]
+  int max_ids, unk_id;
+  unsigned long long* work_counter;
+  // per-warp global scratch for documents that do not fit the shared-memory window
+  uint8_t* arena;                // [grid_warps][arena_stride] bytes
+  int64_t arena_stride;          // bytes per warp
+  int arena_cap;                 // symbols a warp's arena region can hold
+  int grid_warps;                // warps the launch may use (arena rows)
+};
+
+// bytes of arena one warp needs to process documents of up to `cap` symbols
+int64_t sp_arena_bytes_per_warp(int cap, int max_arc_len);
+// preferred number of warps in the grid on the current device
+int sp_preferred_warps();
+
+cudaError_t sp_tokenize_launch(const SpLaunch& p, const SpModelDev& m, cudaStream_t stream, int* launches);
+
+}  // namespace bfb200

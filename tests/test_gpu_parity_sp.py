@@ -1,0 +1,156 @@
+"""Parity of the [pos-dict] GPU engines (Unigram-LM: xlm_roberta_base / xlnet; BPE: gpt2 / roberta /
+bpe_example) through the C ABI against the oracle and the golden fixtures.  Bit-exact: ids are
+integers; the Unigram scores are fp64 sums evaluated in the reference's operand order, and any
+deviation would show up as a different segmentation."""
+import base64
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from _common import GOLDEN, Oracle, fnv1a64_ids, have_data, model_path, read_lines
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_data(), reason="data/ not staged")]
+
+SP_MODELS = [("gpt2.bin", 0), ("xlm_roberta_base.bin", 3), ("roberta.bin", 3), ("xlnet.bin", 0), ("bpe_example.bin", 0)]
+
+
+@pytest.fixture(scope="module")
+def bf():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    torch.zeros(1, device="cuda")
+    import blingfire_b200
+    return blingfire_b200
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+_models = {}
+
+
+def gpu_model(bf, name):
+    if name not in _models:
+        _models[name] = bf.load_model(model_path(name))
+        assert bf.lib().BlingFireB200ModelEngine(_models[name]) == 3, f"{name}: no segmentation engine"
+    return _models[name]
+
+
+def check_batch(bf, oracle, name, docs, max_ids, unk):
+    h = gpu_model(bf, name)
+    ho = oracle.load(model_path(name))
+    buf, offs = docs if isinstance(docs, tuple) else bf.make_csr(docs)
+    ids, counts = bf.text_to_ids_batch(h, (buf, offs), max_ids, unk)
+    _, oids, ocounts = oracle.batch(ho, buf if len(buf) else np.zeros(1, np.uint8), offs, max_ids, unk, threads=16)
+    bad = np.nonzero(counts != ocounts)[0]
+    def show(i):
+        return bytes(buf[offs[i]:offs[i + 1]])[:80]
+    assert len(bad) == 0, f"{name}: count mismatch at docs {bad[:5]} gpu={counts[bad[:5]]} oracle={ocounts[bad[:5]]} {show(bad[0])!r}"
+    mask = np.arange(max_ids)[None, :] < counts[:, None]
+    diff = np.nonzero(((ids != oids) & mask).any(axis=1))[0]
+    assert len(diff) == 0, f"{name}: id mismatch at docs {diff[:5]} {show(diff[0])!r} gpu={ids[diff[0]][:12]} oracle={oids[diff[0]][:12]}"
+    assert (ids[~mask] == 0).all()
+    oracle.free(ho)
+
+
+def test_known_answer_xlnet(bf):
+    # blingfiretokdll.cpp:1341-1347
+    h = gpu_model(bf, "xlnet.bin")
+    ids = bf.text_to_ids(h, "Sergei Alonichau I saw a girl with a \ttelescope.", 64, 0, no_padding=True)
+    assert ids.tolist() == [14363, 651, 7201, 25263, 35, 685, 24, 1615, 33, 24, 16163, 9]
+
+
+def test_edge_cases_vs_golden(bf, golden):
+    import ctypes
+    L = bf.lib()
+    names = {m for m, _ in SP_MODELS}
+    for case in golden["edge_cases"]:
+        if case["model"] not in names:
+            continue
+        h = gpu_model(bf, case["model"])
+        data = base64.b64decode(case["input"])
+        out = np.full(case["max_ids"], -7, np.int32)
+        n = L.TextToIds(ctypes.c_void_p(h), data, len(data), out.ctypes.data, case["max_ids"], case["unk"])
+        assert n == case["count"], (case["model"], data[:40], n, case["count"])
+        assert out[:n].tolist() == case["ids"], (case["model"], data[:40])
+        assert (out[n:] == -7).all()
+
+
+def test_corpus_digests_vs_golden(bf, golden):
+    names = {m for m, _ in SP_MODELS}
+    for d in golden["digests"]:
+        if d["model"] not in names:
+            continue
+        lines = read_lines(d["corpus"], drop_empty=False)[: d["lines"]]
+        docs = [b" ".join(lines[i:i + d["group"]]) for i in range(0, len(lines), d["group"])]
+        h = gpu_model(bf, d["model"])
+        cids, coffs = bf.text_to_ids_batch_csr(h, docs, d["max_ids"], d["unk"])
+        assert int(coffs[-1]) == d["tokens"], d
+        assert f"{fnv1a64_ids(cids):016x}" == d["fnv1a64"], d
+
+
+@pytest.mark.parametrize("name,unk", SP_MODELS)
+def test_batch_matches_oracle_on_corpora(bf, oracle, name, unk):
+    lines = read_lines("test.txt", drop_empty=False)[:12000]
+    docs = [b" ".join(lines[i:i + 6]) for i in range(0, len(lines), 6)]
+    check_batch(bf, oracle, name, docs, 512, unk)
+    lines = read_lines("test.multi.txt", drop_empty=False)[:6000]
+    check_batch(bf, oracle, name, [b" ".join(lines[i:i + 2]) for i in range(0, len(lines), 2)], 300, unk)
+
+
+@pytest.mark.parametrize("name,unk", SP_MODELS)
+def test_ragged_invalid_and_long_documents(bf, oracle, name, unk):
+    rng = random.Random(17)
+    lines = read_lines("test.multi.txt")[:3000] + read_lines("test.txt")[:3000]
+    docs = [b"", b" ", b"  a  b  ", b"\xef\xbb\xbf", b"\xef\xbb\xbfhello", b"abc \xff def", b"hello\x00world", b"a" * 400,
+            b"-" * 300, b"-" * 3000, b"\xc2\xa0nbsp\xc2\xa0", "▁already▁marked ▁".encode(), "我爱北京".encode() * 200,
+            b"\t\ttabs\n\nnl  ", b"x", b"!", "é".encode() * 900, ("word " * 1500).encode(), b"ab" * 2500,
+            b" ".join(lines[:400]), b"".join(lines[400:500])]
+    for _ in range(2500):
+        d = b" ".join(rng.choice(lines) for _ in range(rng.randint(1, 14)))
+        r = rng.random()
+        if r < 0.2:
+            d = d[: rng.randint(0, len(d))]
+        elif r < 0.3:
+            p = rng.randint(0, len(d))
+            d = d[:p] + bytes([rng.randint(0, 255)]) + d[p:]
+        elif r < 0.35:
+            d = bytes(rng.randint(0, 255) for _ in range(rng.randint(1, 60)))
+        docs.append(d)
+    for max_ids in (2048, 7):
+        check_batch(bf, oracle, name, docs, max_ids, unk)
+
+
+def test_unk_id_colliding_with_a_real_id(bf, oracle):
+    """The BPE unknown-run merge compares ids (..._bpe_t.h:219-225): UnkId equal to a real token id
+    changes the result.  Reproduced, not fixed."""
+    docs = [b"hello \x01\x02 world!!", b"!!! \x7f\x7f ???", "▁x▁".encode(), b"a\x00b"] * 20
+    for unk in (0, 1, 50256, 220):
+        check_batch(bf, oracle, "gpt2.bin", docs, 64, unk)
+
+
+def test_cfg3_gpt2_log_uniform_lengths(bf, oracle):
+    """BASELINE cfg 3 (sample): gpt2.bin, documents log-uniform 64..4096 B, seed 3."""
+    import corpus
+    text, offs = corpus.gen_docs("EN", 20000, seed=3, fixed_len=0)
+    check_batch(bf, oracle, "gpt2.bin", (text, offs), 4096, 0)
+
+
+def test_cfg4_xlmr_multilingual(bf, oracle):
+    """BASELINE cfg 4 (sample): xlm_roberta_base.bin, multilingual ~512 B docs with 2-4 byte code points
+    (a 4-byte code point every 16th doc), seed 4."""
+    import corpus
+    text, offs = corpus.gen_docs("MULTI", 20000, seed=4, fixed_len=512, emoji_every=16)
+    check_batch(bf, oracle, "xlm_roberta_base.bin", (text, offs), 512, 3)

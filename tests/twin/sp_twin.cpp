@@ -1,0 +1,196 @@
+// sp_twin.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Sequential host driver over the product's own [pos-dict] table builder (seg_tables.cpp): the
+// double-array Mealy automaton, the symbol map, the I2Info array and the flattened charmap.
+// It runs the reference's algorithms in their sequential form over THOSE tables, so that
+// tests/test_seg_tables.py can check the flattening against the oracle (which reads the packed
+// image) on the CPU box.  The GPU kernels (sp_kernel.cu) are checked against the oracle
+// directly in tests/test_gpu_parity_sp.py.  Never linked into the product.
+#include <algorithm>
+#include <cfloat>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../blingfire_b200/csrc/ldb.h"
+#include "../../blingfire_b200/csrc/seg_tables.h"
+
+using namespace bfb200;
+
+struct SpTwin {
+  LdbImage ldb;
+  SegTables S;
+  std::string err;
+};
+
+static bool is_white(int c) {
+  return c <= 0x20 || c == 0xa0 || (c >= 0x2000 && c <= 0x200f) || c == 0x202f || c == 0x205f || c == 0x2060 ||
+         c == 0x2420 || c == 0x2424 || c == 0x3000 || c == 0xfeff;
+}
+
+static bool step(const SegTables& S, uint32_t* q, int c, int* ow, bool* fin) {
+  if ((unsigned)c > 0x10FFFFu) return false;
+  return S.step(q, S.sym_of_cp[c], ow, fin);
+}
+
+extern "C" {
+
+void* sptwin_load(const char* path) {
+  SpTwin* t = new SpTwin();
+  if (!t->ldb.load_file(path)) { t->err = t->ldb.error(); return t; }
+  if (!build_seg_tables(t->ldb, &t->S, &t->err) && t->err.empty()) t->err = "build failed";
+  return t;
+}
+void sptwin_free(void* h) { delete (SpTwin*)h; }
+const char* sptwin_error(void* h) { return ((SpTwin*)h)->err.c_str(); }
+int sptwin_info(void* h, int what) {
+  const SegTables& S = ((SpTwin*)h)->S;
+  switch (what) {
+    case 0: return (int)S.da.size();
+    case 1: return S.alphabet;
+    case 2: return (int)S.info.size();
+    case 3: return S.max_arc_len;
+    case 4: return S.delim_inside_tokens ? 1 : 0;
+    case 5: return S.tok_algo;
+    case 6: return S.id_offset;
+    case 7: return S.use_raw_bytes ? 1 : 0;
+    case 8: return S.has_charmap ? 1 : 0;
+    default: return -1;
+  }
+}
+
+int sptwin_text_to_ids(void* h, const char* s, int n, int32_t* ids, int max_ids, int unk) {
+  SpTwin* t = (SpTwin*)h;
+  if (!t->err.empty()) return -2;
+  const SegTables& S = t->S;
+  if (n <= 0 || n > 1000000000 || !s) return 0;
+  const uint8_t* b = (const uint8_t*)s;
+  int lo = 0;
+  if (n >= 3 && b[0] == 0xEF && b[1] == 0xBB && b[2] == 0xBF) lo = 3;
+  std::vector<int> buf;
+  if (!S.no_dummy_prefix) buf.push_back(kSpDelim);
+  const size_t off = buf.size();
+  if (S.use_raw_bytes) {
+    for (int p = lo; p < n; ++p) buf.push_back(b[p]);
+  } else {
+    int p = lo;
+    while (p < n) {
+      const int c = b[p];
+      int len, cp;
+      if (c < 0x80) { len = 1; cp = c; }
+      else if ((c & 0xE0) == 0xC0) { len = 2; cp = c & 0x1F; }
+      else if ((c & 0xF0) == 0xE0) { len = 3; cp = c & 0x0F; }
+      else if ((c & 0xF8) == 0xF0) { len = 4; cp = c & 0x07; }
+      else return 0;
+      if (p + len > n) return 0;
+      for (int k = 1; k < len; ++k) { if ((b[p + k] & 0xC0) != 0x80) return 0; cp = (cp << 6) | (b[p + k] & 0x3F); }
+      const int need = cp <= 0x7F ? 1 : cp <= 0x7FF ? 2 : cp <= 0xFFFF ? 3 : cp <= 0x10FFFF ? 4 : 0;
+      if (need != len || (cp & 0xFFFFF800) == 0xD800) return 0;
+      buf.push_back(cp);
+      p += len;
+    }
+  }
+  if (buf.size() == off) return 0;
+  if (S.has_charmap) {
+    std::vector<int> nb;
+    for (int cp : buf) {
+      const uint8_t c = ((unsigned)cp <= 0x10FFFFu) ? S.norm_count[cp] : 0xFF;
+      if (c == 0xFF) nb.push_back(cp);
+      else for (int k = 0; k < c; ++k) nb.push_back(S.norm_values[S.norm_first[cp] + k]);
+    }
+    if (nb.empty() || (int64_t)nb.size() > 2ll * (n + 1)) return 0;
+    buf.swap(nb);
+  }
+  {
+    size_t j = 0;
+    for (size_t i = 0; i < buf.size(); ++i) {
+      const int c = buf[i];
+      if (!is_white(c)) buf[j++] = c;
+      else if (j == 0 || buf[j - 1] != kSpDelim) buf[j++] = kSpDelim;
+    }
+    if (j > 1 && buf[j - 1] == kSpDelim) --j;
+    buf.resize(j);
+  }
+  const int N = (int)buf.size();
+  if (N == 0) return 0;
+  std::vector<int> res;   // (id, from, to)
+  const bool bpe = S.tok_algo == kTokenizeBpe || S.tok_algo == kTokenizeBpeOpt || S.tok_algo == kTokenizeBpeOptWithMerges;
+  if (!bpe) {
+    struct A { int begin, id; double score; };
+    std::vector<A> best(N, A{-1, -1, -(double)FLT_MAX});
+    for (int start = 0; start < N; ++start) {
+      uint32_t q = S.root; int sum = 0; bool unknown = true;
+      for (int i = start; i < N; ++i) {
+        int ow; bool fin;
+        if (!step(S, &q, buf[i], &ow, &fin)) break;
+        sum += ow;
+        if (fin) {
+          if (sum < 0 || sum >= (int)S.info.size()) return -3;
+          const SegInfo si = S.info[sum];
+          const double prev = start > 0 ? best[start - 1].score : 0;
+          if (best[i].score < si.score + prev) best[i] = A{start, si.id, si.score + prev};
+          unknown = false;
+        }
+      }
+      if (unknown) {
+        const double prev = start > 0 ? best[start - 1].score : 0;
+        if (best[start].score < -100000.0f + prev) {
+          best[start] = A{start, -1, -100000.0f + prev};
+          if (start > 0 && best[start - 1].id == -1) best[start].begin = best[start - 1].begin;
+        }
+      }
+    }
+    std::vector<int> rev;
+    int end = N - 1;
+    while (end >= 0) { const A& a = best[end]; rev.push_back(a.id != -1 ? a.id : unk); end = a.begin - 1; if (a.begin < 0) break; }
+    for (auto it = rev.rbegin(); it != rev.rend(); ++it) res.push_back(*it);
+  } else {
+    const bool merges = S.tok_algo == kTokenizeBpeOptWithMerges;
+    const bool fast = merges || S.tok_algo == kTokenizeBpeOpt;
+    struct Arc { int start, end, id; float rank; };
+    std::vector<Arc> arcs;
+    for (int start = 0; start < N; ++start) {
+      uint32_t q = S.root; int sum = 0; bool unknown = true;
+      const bool tok_start = buf[start] == kSpDelim;
+      const size_t cnt0 = arcs.size(); int ff = start;
+      for (int i = start; i < N; ++i) {
+        int ow; bool fin;
+        if (!step(S, &q, buf[i], &ow, &fin)) break;
+        sum += ow;
+        if (fin) {
+          if (sum < 0 || sum >= (int)S.info.size()) return -3;
+          const SegInfo si = S.info[sum];
+          const bool opt = fast && tok_start && ((i < N - 1) ? buf[i + 1] == kSpDelim : true) && cnt0 < arcs.size();
+          const Arc a{start, i, si.id, merges ? si.score : 0.0f};
+          if (!opt) arcs.push_back(a); else { arcs[cnt0] = a; arcs.resize(cnt0 + 1); ff = i; }
+          unknown = false;
+        }
+      }
+      if (unknown) {
+        if (!arcs.empty() && arcs.back().id == unk) arcs.back().end = start;
+        else arcs.push_back(Arc{start, start, unk, 0.0f});
+      }
+      if (fast) start = ff;
+    }
+    std::sort(arcs.begin(), arcs.end(), [&](const Arc& x, const Arc& y) {
+      if (merges) { if (x.rank > y.rank) return true; if (x.rank < y.rank) return false; }
+      if (x.id != y.id) return x.id < y.id;
+      return x.start < y.start;
+    });
+    std::vector<int> tos(N), tid(N, unk);
+    std::vector<uint8_t> inter(N + 1, 0);
+    for (int i = 0; i < N; ++i) tos[i] = i;
+    for (const Arc& a : arcs)
+      if (!inter[a.start] && (a.end + 1 == N || !inter[a.end + 1])) {
+        tos[a.start] = a.end; tid[a.start] = a.id;
+        for (int j = a.start + 1; j <= a.end; ++j) inter[j] = 1;
+      }
+    for (int s2 = 0; s2 < N; ++s2) { res.push_back(tid[s2]); s2 = tos[s2]; }
+  }
+  int out = 0;
+  for (size_t k = 0; k < res.size() && out < max_ids; ++k) ids[out++] = res[k] + S.id_offset;
+  return out;
+}
+
+}  // extern "C"
