@@ -90,6 +90,9 @@ def text_to_ids(h, s, max_len, unk=0, no_padding=False):
     s_bytes = s.encode("utf-8") if isinstance(s, str) else bytes(s)
     o = np.zeros(max_len, dtype=np.int32)
     t_count = lib().TextToIds(c_void_p(h), s_bytes, len(s_bytes), o.ctypes.data, max_len, unk)
+    if t_count == 0 and s_bytes and last_error():
+        # 0 is also a legitimate result (empty / invalid input); a GPU-side failure must not hide behind it
+        raise RuntimeError(f"TextToIds failed: {last_error()}")
     out_count = min(max_len, t_count) if no_padding else max_len
     return o.view(np.uint32)[:out_count]
 

@@ -83,13 +83,14 @@ struct Slot {
   PinBuf<int64_t> h_offsets;
   PinBuf<int32_t> h_csr;       // only for the row-major host API
   DevBuf<uint8_t> sp_arena;    // [pos-dict] engine: per-warp scratch for documents beyond the smem window
+  DevBuf<uint8_t> sp_overflow; // [pos-dict] BPE: grid-wide arc scratch for segments beyond the private one
   // generic lexer engine scratch
   DevBuf<uint16_t> lex_cls;
   DevBuf<int32_t> lex_ncps, lex_tri, lex_tri_count;
   // bookkeeping of the chunk in flight
   int64_t doc0 = 0, ndocs = 0;
   void release() {
-    lex_cls.release(); lex_ncps.release(); lex_tri.release(); lex_tri_count.release(); sp_arena.release();
+    lex_cls.release(); lex_ncps.release(); lex_tri.release(); lex_tri_count.release(); sp_arena.release(); sp_overflow.release();
     text.release(); offsets.release(); ids.release(); counts.release(); row_off.release(); csr.release();
     counter.release(); h_row_off.release(); h_offsets.release(); h_csr.release();
     if (stream) cudaStreamDestroy(stream);
@@ -300,7 +301,10 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
     int64_t max_len = 0;
     for (int64_t d = doc0; d < doc0 + ndocs; ++d) max_len = std::max(max_len, offsets[d + 1] - offsets[d]);
     int64_t cap64 = (m->S.has_charmap ? 2 * (max_len + 1) : max_len + 1) + 2;
-    if (cap64 <= 1024) cap64 = 16;                       // everything fits the window: arena unused
+    const bool is_bpe = m->S.tok_algo == kTokenizeBpe || m->S.tok_algo == kTokenizeBpeOpt || m->S.tok_algo == kTokenizeBpeOptWithMerges;
+    // Unigram keeps everything in the window when the document fits; BPE always keeps its arc
+    // scratch (32 arcs per symbol of capacity) in the arena
+    if (cap64 <= kSpWindow && !is_bpe) cap64 = 16;
     if (cap64 > (1ll << 28)) { set_error("document too large for the segmentation engine"); return false; }
     const int cap = (int)cap64;
     const int64_t per_warp = sp_arena_bytes_per_warp(cap, m->S.max_arc_len);
@@ -309,7 +313,10 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
     if (per_warp * warps > budget) warps = (int)std::max<int64_t>(8, (budget / per_warp) / 8 * 8);
     if (per_warp * warps > (24ll << 30)) { set_error("document too large for the segmentation engine arena"); return false; }
     if (!s.sp_arena.reserve((size_t)(per_warp * warps)) || !s.counter.reserve(2)) return false;
+    const int64_t ovf_entries = is_bpe ? sp_overflow_entries(cap, m->S.max_arc_len) : 1;
+    if (!s.sp_overflow.reserve((size_t)ovf_entries * 16)) return false;
     SpLaunch X{};
+    X.overflow = s.sp_overflow.p; X.overflow_cap = ovf_entries;
     X.text = s.text.p - b0; X.offsets = s.offsets.p; X.ndocs = ndocs; X.text_bytes = b1;
     X.ids = s.ids.p; X.counts = s.counts.p; X.max_ids = max_ids; X.unk_id = unk;
     X.work_counter = s.counter.p; X.arena = s.sp_arena.p; X.arena_stride = per_warp; X.arena_cap = cap; X.grid_warps = warps;
@@ -404,6 +411,7 @@ bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t nd
 }
 
 bool check_batch_args(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, int max_ids) {
+  g_last_error.clear();
   if (!m) { set_error("null model"); return false; }
   if (m->engine == 0) { set_error("no GPU engine for this model type yet"); return false; }
   if (ndocs < 0 || max_ids < 0 || (ndocs > 0 && (!utf8 || !offsets))) { set_error("bad batch arguments"); return false; }

@@ -28,9 +28,9 @@ namespace {
 
 constexpr int kSpWarps = 8;
 constexpr int kSpThreads = kSpWarps * 32;
-constexpr int kSpWin = 1024;              // symbols in the shared-memory window
+constexpr int kSpWin = kSpWindow;         // symbols in the shared-memory window
 constexpr int kTileArcs = 1024;           // arc slots of one tile of start positions (Unigram)
-constexpr int kArcsPerSym = 32;           // arena capacity for BPE arcs, per symbol of capacity
+constexpr int kArcsPerSym = 8;            // warp-private BPE arc scratch, per symbol of capacity
 
 struct Arc3 { int start, end, id; float rank; };   // 16 B
 
@@ -294,7 +294,9 @@ __device__ __forceinline__ int count_arcs_from(const SpModelDev& m, const Work& 
 
 // One segment [a, b), warp-cooperatively.  `arcs` is warp-private scratch of arc_cap entries.
 // Tokens are written position-indexed: ids_at[start], w.flag[start] |= 2.  false = scratch overflow.
-__device__ bool bpe_segment(const SpModelDev& m, Work& w, int N, int a, int b, int unk, Arc3* arcs, int arc_cap,
+struct ArcScratch { Arc3* priv; int64_t priv_cap; Arc3* ovf; int64_t ovf_cap; int* lock; };
+
+__device__ bool bpe_segment(const SpModelDev& m, Work& w, int N, int a, int b, int unk, const ArcScratch& scratch,
                             int32_t* ids_at, int lane, bool fast, bool merges) {
   // ---- arcs of every start, grouped by start (count -> scan -> write) ----
   int total = 0;
@@ -307,7 +309,17 @@ __device__ bool bpe_segment(const SpModelDev& m, Work& w, int N, int a, int b, i
   }
   __syncwarp();
   const int L = b - a;
-  if ((int64_t)total + 2ll * ((int64_t)total + L) + 4 > (int64_t)arc_cap) return false;
+  // raw arcs + the reference's arc vector (<= total + L entries) padded to a power of two
+  const int64_t need = (int64_t)total + 2ll * ((int64_t)total + L) + 4;
+  Arc3* arcs = scratch.priv;
+  bool locked = false;
+  if (need > scratch.priv_cap) {
+    if (need > scratch.ovf_cap) return false;
+    if (lane == 0) { while (atomicCAS(scratch.lock, 0, 1) != 0) __nanosleep(200); __threadfence(); }
+    __syncwarp();
+    arcs = scratch.ovf;
+    locked = true;
+  }
   for (int s0 = a; s0 < b; s0 += 32) {
     const int s = s0 + lane;
     if (s < b) {
@@ -389,10 +401,11 @@ __device__ bool bpe_segment(const SpModelDev& m, Work& w, int N, int a, int b, i
     for (int s = a; s < b; ++s) { w.flag[s] |= 2; s = w.bid[s]; }
   }
   __syncwarp();
+  if (locked && lane == 0) { __threadfence(); atomicExch(scratch.lock, 0); }
   return true;
 }
 
-__device__ int sp_bpe(const SpModelDev& m, Work& w, int N, int32_t* row, int max_ids, int unk, Arc3* arcs, int arc_cap,
+__device__ int sp_bpe(const SpModelDev& m, Work& w, int N, int32_t* row, int max_ids, int unk, const ArcScratch& scratch,
                       int lane, bool* overflow) {
   const bool merges = m.tok_algo == kTokenizeBpeOptWithMerges;
   const bool fast = merges || m.tok_algo == kTokenizeBpeOpt;
@@ -437,7 +450,7 @@ __device__ int sp_bpe(const SpModelDev& m, Work& w, int N, int32_t* row, int max
     while (hb) {
       const int l = __ffs(hb) - 1; hb &= hb - 1;
       const int sa = __shfl_sync(0xffffffffu, a, l), sb = __shfl_sync(0xffffffffu, b, l);
-      if (!bpe_segment(m, w, N, sa, sb, unk, arcs, arc_cap, ids_at, lane, fast, merges)) { *overflow = true; return 0; }
+      if (!bpe_segment(m, w, N, sa, sb, unk, scratch, ids_at, lane, fast, merges)) { *overflow = true; return 0; }
     }
   }
   __syncwarp();
@@ -452,8 +465,12 @@ __global__ void __launch_bounds__(kSpThreads, 1) sp_tokenize_kernel(const SpLaun
   Work ws = make_work(smem + (size_t)warp * work_bytes(kSpWin), kSpWin);
   uint8_t* my_arena = p.arena + (size_t)gwarp * p.arena_stride;
   Work wa = make_work(my_arena, p.arena_cap);
-  Arc3* arcs = reinterpret_cast<Arc3*>(my_arena + work_bytes(p.arena_cap));
-  const int arc_cap = p.arena_cap * kArcsPerSym + 4096;
+  ArcScratch scratch;
+  scratch.priv = reinterpret_cast<Arc3*>(my_arena + work_bytes(p.arena_cap));
+  scratch.priv_cap = (int64_t)p.arena_cap * kArcsPerSym + 4096;
+  scratch.ovf = reinterpret_cast<Arc3*>(p.overflow);
+  scratch.ovf_cap = p.overflow_cap;
+  scratch.lock = error_flag + 1;
   const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
 
   for (;;) {
@@ -490,7 +507,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sp_tokenize_kernel(const SpLaun
             int32_t* row = p.ids + doc * (int64_t)p.max_ids;
             if (kBpe) {
               bool overflow = false;
-              result = sp_bpe(m, w, N, row, p.max_ids, p.unk_id, arcs, arc_cap, lane, &overflow);
+              result = sp_bpe(m, w, N, row, p.max_ids, p.unk_id, scratch, lane, &overflow);
               if (overflow) { result = 0; if (lane == 0) atomicExch(error_flag, 3); }
             } else {
               result = sp_unigram(m, w, N, row, p.max_ids, p.unk_id, lane);
@@ -508,6 +525,15 @@ __global__ void __launch_bounds__(kSpThreads, 1) sp_tokenize_kernel(const SpLaun
 
 int64_t sp_arena_bytes_per_warp(int cap, int) {
   return align16(work_bytes(cap) + 16ll * ((int64_t)cap * kArcsPerSym + 4096) + 256);
+}
+
+int64_t sp_overflow_entries(int cap, int max_arc_len) {
+  // a start has at most min(max_arc_len, cap) arcs; see `need` in bpe_segment
+  const int64_t per = max_arc_len < cap ? max_arc_len : cap;
+  const int64_t total = (int64_t)cap * per;
+  const int64_t need = total + 2 * (total + cap) + 64;
+  const int64_t limit = (2ll << 30) / 16;          // 2 GB
+  return need < limit ? need : limit;
 }
 
 int sp_preferred_warps() {

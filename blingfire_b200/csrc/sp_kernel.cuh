@@ -9,6 +9,10 @@
 
 namespace bfb200 {
 
+// symbols (after normalisation staging) a document may have to be served from shared memory;
+// 8 warps x 27 KB of workspace = 216 KB per CTA
+constexpr int kSpWindow = 896;
+
 struct SpModelDev {
   const DaEntry* da;             // double-array automaton
   uint32_t root;
@@ -37,7 +41,14 @@ struct SpLaunch {
   int64_t arena_stride;          // bytes per warp
   int arena_cap;                 // symbols a warp's arena region can hold
   int grid_warps;                // warps the launch may use (arena rows)
+  // BPE: a segment whose arcs do not fit the warp's private scratch takes this grid-wide region
+  // under a spin lock (rare: long runs of one character have dozens of vocabulary matches per start)
+  uint8_t* overflow;             // [overflow_cap] 16-byte arc entries
+  int64_t overflow_cap;
 };
+
+// arc entries the shared overflow region must hold for documents of up to `cap` symbols
+int64_t sp_overflow_entries(int cap, int max_arc_len);
 
 // bytes of arena one warp needs to process documents of up to `cap` symbols
 int64_t sp_arena_bytes_per_warp(int cap, int max_arc_len);
