@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -70,8 +71,12 @@ struct PinBuf {
 };
 
 // per-slot working set of the host batch pipeline
+constexpr int kSlots = 4;    // chunks in flight in the host pipeline
+constexpr int kAhead = 2;    // chunks enqueued behind the one whose counts the host waits for
+
 struct Slot {
   cudaStream_t stream = nullptr;
+  cudaEvent_t counts_ready = nullptr;   // recorded after the chunk's row offsets were copied to the host
   DevBuf<uint8_t> text;
   DevBuf<int64_t> offsets;
   DevBuf<int32_t> ids;
@@ -93,6 +98,8 @@ struct Slot {
     lex_cls.release(); lex_ncps.release(); lex_tri.release(); lex_tri_count.release(); sp_arena.release(); sp_overflow.release();
     text.release(); offsets.release(); ids.release(); counts.release(); row_off.release(); csr.release();
     counter.release(); h_row_off.release(); h_offsets.release(); h_csr.release();
+    if (counts_ready) cudaEventDestroy(counts_ready);
+    counts_ready = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -126,7 +133,7 @@ struct Model {
   uint32_t* d_norm_first = nullptr;
   int32_t* d_norm_values = nullptr;
   std::mutex mu;               // serialises the host-pointer entry points of this handle
-  Slot slots[2];
+  Slot slots[kSlots];
   DevBuf<unsigned long long> dev_counter;   // for the device-pointer entry point
 
   ~Model() {
@@ -268,6 +275,7 @@ LexLaunch make_lex_launch(const Model*, Slot& s, int64_t first_off, int64_t b0, 
 
 bool ensure_stream(Slot& s) {
   if (s.stream) return true;
+  if (!cuda_ok(cudaEventCreateWithFlags(&s.counts_ready, cudaEventDisableTiming), "cudaEventCreate")) return false;
   return cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
 }
 
@@ -356,6 +364,7 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
   if (m->engine == 3 &&
       !cuda_ok(cudaMemcpyAsync(s.h_row_off.p + ndocs + 1, s.counter.p + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream), "D2H flag"))
     return false;
+  if (!cuda_ok(cudaEventRecord(s.counts_ready, s.stream), "event record")) return false;
   s.doc0 = doc0; s.ndocs = ndocs;
   return true;
 }
@@ -373,7 +382,9 @@ bool chunk_ok(Slot& s) {
 // how many documents go into the next chunk: bounded text bytes and bounded id-matrix size
 int64_t chunk_docs(const int64_t* offsets, int64_t doc0, int64_t ndocs_total, int max_ids, int engine) {
   // the generic lexer keeps 26 scratch bytes per input byte (classes + triples)
-  const int64_t kMaxBytes = engine == 2 ? (8ll << 20) : (64ll << 20);
+  // chunk size of the host pipeline; BLINGFIRE_B200_CHUNK_MB overrides it (tuning knob)
+  static const int64_t env_mb = [] { const char* e = std::getenv("BLINGFIRE_B200_CHUNK_MB"); return e ? std::atoll(e) : 0ll; }();
+  const int64_t kMaxBytes = engine == 2 ? (8ll << 20) : ((env_mb > 0 ? env_mb : 32) << 20);
   const int64_t kMaxIdsCells = 160ll << 20;     // 640 MB of int32 per slot
   const int64_t max_docs = std::max<int64_t>(1, kMaxIdsCells / std::max(1, max_ids));
   int64_t d = doc0;
@@ -382,31 +393,58 @@ int64_t chunk_docs(const int64_t* offsets, int64_t doc0, int64_t ndocs_total, in
   return d - doc0;
 }
 
-// Runs the whole host batch through the two-slot pipeline.  `sink(slot)` consumes a finished
-// chunk (row offsets are in slot.h_row_off; ids are still on the device in slot.csr).
-template <typename Sink>
-bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, int max_ids, int unk, Sink sink) {
+// Runs the whole host batch through a three-slot pipeline so that the H2D copy of chunk c, the
+// kernels of chunk c-1 and the D2H copy of chunk c-2 overlap (PCIe is full duplex).
+//   issue(slot)   called in chunk order once the chunk's row offsets are on the host
+//                 (slot.h_row_off); enqueues the asynchronous D2H of the ids on slot.stream
+//   finish(slot)  called in chunk order once that D2H has completed (host-side post-processing)
+template <typename Issue, typename Finish>
+bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, int max_ids, int unk,
+                  Issue issue, Finish finish) {
   if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return false;
+  bool copying[kSlots] = {};
+  auto settle = [&](int si) -> bool {   // wait for the ids copy of the chunk that last used slot si
+    if (!copying[si]) return true;
+    copying[si] = false;
+    Slot& s = m->slots[si];
+    if (!cuda_ok(cudaStreamSynchronize(s.stream), "sync")) return false;
+    return finish(s);
+  };
+  auto counts_ready = [&](int si) -> bool {   // kernels of the chunk in slot si are done
+    Slot& s = m->slots[si];
+    if (!cuda_ok(cudaEventSynchronize(s.counts_ready), "event sync")) return false;
+    if (!chunk_ok(s) || !issue(s)) return false;
+    copying[si] = true;
+    return true;
+  };
   int64_t d = 0;
   int c = 0;
-  int pending = -1;   // slot index of the chunk enqueued but not yet consumed
+  static const bool trace = std::getenv("BLINGFIRE_B200_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  double t_settle = 0, t_enqueue = 0, t_counts = 0;
   while (d < ndocs) {
+    const int si = c % kSlots;
+    double t0 = now();
+    if (!settle(si)) return false;
+    double t1 = now();
     const int64_t nd = chunk_docs(offsets, d, ndocs, max_ids, m->engine);
-    Slot& s = m->slots[c & 1];
-    if (!enqueue_chunk(m, s, utf8, offsets, d, nd, max_ids, unk)) return false;
-    if (pending >= 0) {
-      Slot& ps = m->slots[pending];
-      if (!cuda_ok(cudaStreamSynchronize(ps.stream), "sync")) return false;
-      if (!chunk_ok(ps) || !sink(ps)) return false;
-    }
-    pending = c & 1;
+    if (!enqueue_chunk(m, m->slots[si], utf8, offsets, d, nd, max_ids, unk)) return false;
+    double t2 = now();
+    // chunk c-kAhead: its kernels had kAhead chunks of queued work behind them, so the copy
+    // engines and the SMs never wait for the host
+    if (c >= kAhead && !counts_ready((c - kAhead) % kSlots)) return false;
+    double t3 = now();
+    t_settle += t1 - t0; t_enqueue += t2 - t1; t_counts += t3 - t2;
     d += nd; ++c;
   }
-  if (pending >= 0) {
-    Slot& ps = m->slots[pending];
-    if (!cuda_ok(cudaStreamSynchronize(ps.stream), "sync")) return false;
-    if (!chunk_ok(ps) || !sink(ps)) return false;
-  }
+  if (trace)
+    std::fprintf(stderr, "[bfb200] pipeline: %d chunks, loop %.2f ms (settle %.2f, enqueue %.2f, wait-counts %.2f)\n", c,
+                 now() - t_begin, t_settle, t_enqueue, t_counts);
+  for (int k = c >= kAhead ? c - kAhead : 0; k < c; ++k)       // the chunks whose counts were not consumed yet
+    if (!counts_ready(k % kSlots)) return false;
+  for (int k = c >= kSlots ? c - kSlots : 0; k < c; ++k)       // the chunks still copying, oldest first
+    if (!settle(k % kSlots)) return false;
   return true;
 }
 
@@ -481,18 +519,18 @@ int64_t TextToIdsBatchCsr(void* h, const char* utf8, const int64_t* offsets, int
     int64_t total = 0;
     bool overflow = false;
     id_offsets[0] = 0;
-    auto sink = [&](Slot& s) -> bool {
+    auto issue = [&](Slot& s) -> bool {
       const int64_t n = s.h_row_off.p[s.ndocs];
       for (int64_t i = 0; i < s.ndocs; ++i) id_offsets[s.doc0 + i + 1] = total + s.h_row_off.p[i + 1];
       if (total + n > capacity) overflow = true;
-      else if (n > 0) {
-        if (!cuda_ok(cudaMemcpyAsync(ids_csr + total, s.csr.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream), "D2H ids")) return false;
-        if (!cuda_ok(cudaStreamSynchronize(s.stream), "sync")) return false;
-      }
+      else if (n > 0 &&
+               !cuda_ok(cudaMemcpyAsync(ids_csr + total, s.csr.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream), "D2H ids"))
+        return false;
       total += n;
       return true;
     };
-    if (!run_pipeline(m, utf8, offsets, ndocs, max_ids, unk, sink)) return -1;
+    auto finish = [&](Slot&) -> bool { return true; };
+    if (!run_pipeline(m, utf8, offsets, ndocs, max_ids, unk, issue, finish)) return -1;
     return overflow ? -total : total;
   } catch (const std::exception& e) { set_error(e.what()); return -1; }
 }
@@ -505,23 +543,24 @@ int64_t TextToIdsBatch(void* h, const char* utf8, const int64_t* offsets, int64_
     if (ndocs > 0 && (!ids || !counts)) { set_error("bad output arguments"); return -1; }
     std::lock_guard<std::mutex> lock(m->mu);
     int64_t total = 0;
-    auto sink = [&](Slot& s) -> bool {
+    auto issue = [&](Slot& s) -> bool {
       const int64_t n = s.h_row_off.p[s.ndocs];
       if (!s.h_csr.reserve((size_t)n + 1)) return false;
-      if (n > 0) {
-        if (!cuda_ok(cudaMemcpyAsync(s.h_csr.p, s.csr.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream), "D2H ids")) return false;
-        if (!cuda_ok(cudaStreamSynchronize(s.stream), "sync")) return false;
-      }
+      if (n > 0 && !cuda_ok(cudaMemcpyAsync(s.h_csr.p, s.csr.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream), "D2H ids"))
+        return false;
+      total += n;
+      return true;
+    };
+    auto finish = [&](Slot& s) -> bool {
       // rows beyond their count stay untouched, as in the reference (blingfiretokdll.cpp:1098-1101)
       for (int64_t i = 0; i < s.ndocs; ++i) {
         const int64_t a = s.h_row_off.p[i], b = s.h_row_off.p[i + 1];
         counts[s.doc0 + i] = (int32_t)(b - a);
         if (b > a) std::memcpy(ids + (s.doc0 + i) * (int64_t)max_ids, s.h_csr.p + a, (size_t)(b - a) * sizeof(int32_t));
       }
-      total += n;
       return true;
     };
-    if (!run_pipeline(m, utf8, offsets, ndocs, max_ids, unk, sink)) return -1;
+    if (!run_pipeline(m, utf8, offsets, ndocs, max_ids, unk, issue, finish)) return -1;
     return total;
   } catch (const std::exception& e) { set_error(e.what()); return -1; }
 }

@@ -367,22 +367,29 @@ __global__ void __launch_bounds__(1024) wp_scan_kernel(const int32_t* __restrict
 }  // namespace
 
 cudaError_t wp_tokenize_launch(const WpLaunch& p, cudaStream_t stream, WpLaunchInfo* info) {
-  int dev = 0, sms = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (e != cudaSuccess) return e;
   const size_t blob_bytes = ((size_t)p.layout.total_bytes + 127) & ~(size_t)127;
   const size_t smem = blob_bytes + (size_t)kWarpsPerCta * kWarpSmem;
   auto kern = p.wide ? wp_tokenize_kernel<uint32_t> : wp_tokenize_kernel<uint16_t>;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the launch geometry depends on (device, kernel variant, smem size) only: resolve it once
+  struct Geo { int dev = -1; size_t smem = 0; int grid = 0; };
+  static thread_local Geo cache[2];
+  Geo& geo = cache[p.wide ? 1 : 0];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  if (geo.dev != dev || geo.smem != smem) {
+    int sms = 0, per_sm = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    geo.dev = dev; geo.smem = smem; geo.grid = sms * per_sm;
+  }
   // persistent grid: a whole number of CTAs per SM
-  int grid = sms * per_sm;
+  int grid = geo.grid;
   const int64_t needed = (p.ndocs + kWarpsPerCta - 1) / kWarpsPerCta;
   if (needed < grid) grid = (int)(needed > 0 ? needed : 1);
   e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), stream);
