@@ -1,0 +1,82 @@
+#!/usr/bin/env python3
+"""Side measurements for BASELINE.md's results table: the configurations other than the bench line
+(cfg 1 TextToWords, cfg 3 gpt2, cfg 4 xlm-r), through the host-pointer C ABI, next to the reference's
+CPU path on a sample.  Not the contract benchmark (that is bench.py on cfg 2)."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
+    sys.path.insert(0, p)
+
+
+def ref_cpu(model, text, offs, n, max_ids, unk, threads):
+    L = ctypes.CDLL(os.path.join(ROOT, "oracle", "librefdriver.so"))
+    L.ref_time_batch.restype = ctypes.c_double
+    L.ref_time_batch.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    ref = os.path.join(ROOT, "oracle", "_ref", "libblingfiretokdll.so")
+    tok = ctypes.c_int64(0)
+    so = np.ascontiguousarray(offs[: n + 1])
+    secs = L.ref_time_batch(ref.encode(), model.encode(), text.ctypes.data, so.ctypes.data, n, max_ids, unk, threads,
+                            ctypes.byref(tok), None)
+    return int(so[-1]) / secs / 1e9, tok.value / secs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--docs", type=int, default=200_000)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    import blingfire_b200 as bf
+    import corpus
+    from _common import model_path, read_lines
+    torch.cuda.set_device(0)
+    torch.zeros(1, device="cuda")
+    cores = len(os.sched_getaffinity(0))
+    out = {"cores": cores}
+
+    # cfg 1: default TextToWords on 10k short ASCII lines (per-call API)
+    lines = [l for l in read_lines("test.txt") if len(l) <= 120 and all(c < 128 for c in l)][:10000]
+    L = bf.lib()
+    buf = ctypes.create_string_buffer(1024)
+    L.TextToWords(lines[0], len(lines[0]), buf, 1024)
+    t0 = time.perf_counter()
+    for l in lines:
+        L.TextToWords(l, len(l), buf, 1024)
+    dt = time.perf_counter() - t0
+    nb = sum(len(l) for l in lines)
+    out["cfg1_TextToWords_10k_lines"] = {"MB_per_s": nb / dt / 1e6, "us_per_call": dt / len(lines) * 1e6, "bytes": nb}
+
+    for name, cfg, model, unk, max_ids, gen in [
+        ("cfg3_gpt2", 3, "gpt2.bin", 0, 4096, lambda n: corpus.gen_docs("EN", n, seed=3, fixed_len=0)),
+        ("cfg4_xlmr", 4, "xlm_roberta_base.bin", 3, 512, lambda n: corpus.gen_docs("MULTI", n, seed=4, fixed_len=512, emoji_every=16)),
+        ("cfg2_bert_host_api", 2, "bert_base_tok.bin", 100, 512, lambda n: corpus.gen_docs("EN", n, seed=2, fixed_len=512)),
+    ]:
+        text, offs = gen(args.docs)
+        h = bf.load_model(model_path(model))
+        ids, idoffs = bf.text_to_ids_batch_csr(h, (text, offs), max_ids, unk)   # warm-up (allocations)
+        ts = []
+        for _ in range(args.reps):
+            t0 = time.perf_counter()
+            ids, idoffs = bf.text_to_ids_batch_csr(h, (text, offs), max_ids, unk)
+            ts.append(time.perf_counter() - t0)
+        dt = min(ts)
+        ns = min(args.docs, 50000)
+        cpu_gbs, cpu_tps = ref_cpu(model_path(model), text, offs, ns, max_ids, unk, cores)
+        out[name] = {"docs": args.docs, "bytes": int(offs[-1]), "tokens": int(idoffs[-1]), "e2e_GB_per_s": int(offs[-1]) / dt / 1e9,
+                     "e2e_tokens_per_s": int(idoffs[-1]) / dt, "cpu_ref_GB_per_s": cpu_gbs, "cpu_threads": cores,
+                     "note": "host pageable numpy buffers through TextToIdsBatchCsr"}
+        bf.free_model(h)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
