@@ -188,7 +188,7 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
       m->lex_ok = true;
     }
     if (T.charmap_one_to_one && !upload(&m->d_cls, T.cls_of_cp.data(), T.cls_of_cp.size())) return nullptr;
-    if (T.fast.ok && T.charmap_one_to_one && T.max_token_length <= 420) {
+    if (T.fast.ok && T.charmap_one_to_one && T.max_token_length <= 400) {
       build_wp_blob(T, &m->blob);
       if (!upload(&m->d_tag, T.tag_of_state.data(), T.tag_of_state.size())) return nullptr;
       if (!upload(&m->d_blob, m->blob.bytes.data(), m->blob.bytes.size())) return nullptr;

@@ -27,9 +27,9 @@ namespace {
 
 constexpr int kWarpsPerCta = 16;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kWin = 640;            // window capacity in code points (per warp)
+constexpr int kWin = 576;            // window capacity in code points (per warp)
 constexpr int kBlockBytes = 128;     // bytes consumed per decode step (32 lanes x uchar4)
-constexpr int kWarpSmem = kWin * (2 + 4 + 1 + 2);   // cls u16, ids_at i32, has_id u8, starts u16
+constexpr int kWarpSmem = kWin * (2 + 4 + 1 + 2 + 2);   // cls u16, ids_at i32, has_id u8, starts u16, order u16
 
 static_assert(kWin % 32 == 0, "window must be a multiple of the warp size");
 
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
   uint16_t* cls = reinterpret_cast<uint16_t*>(wbase + kWin * 4);
   uint16_t* starts = reinterpret_cast<uint16_t*>(wbase + kWin * 6);
   uint8_t* has_id = wbase + kWin * 8;
+  uint16_t* order = reinterpret_cast<uint16_t*>(wbase + kWin * 9 + (kWin & 1));
 
   const uint32_t* text32 = reinterpret_cast<const uint32_t*>(p.text);
   const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
@@ -175,7 +176,9 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
 
     // Documents that may not fit one window are validated up front, because ids are
     // emitted window by window and an invalid byte anywhere must yield 0 ids.
-    const bool multi = run && (hi - lo0) > (kWin - kBlockBytes);
+    // a document of up to kWin-3 bytes always fits one window (its code points <= its bytes; the
+    // first decode block may start up to 3 bytes before the document)
+    const bool multi = run && (hi - lo0) > (kWin - 4);
     if (multi) {
       unsigned bad = 0, sumlen = 0;
       for (int64_t bpos = lo0; bpos < hi;) {
@@ -202,8 +205,11 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
       for (;;) {
         // ---- fill the window: decode, validate, classify, compact ----
         unsigned bad = 0;
-        while (m + kBlockBytes <= kWin && bpos < hi) {
+        while (bpos < hi) {
           const int64_t bs = bpos & ~(int64_t)3;
+          // the block [bpos, min(bs+128, hi)) yields at most that many code points
+          const int64_t blk_end = bs + kBlockBytes < hi ? bs + kBlockBytes : hi;
+          if (m + (int)(blk_end - bpos) > kWin) break;
           const int64_t pos0 = bs + lane * 4;
           uint32_t w0, w1;
           load_words(text32, pos0, padded_bytes, &w0, &w1);
@@ -259,23 +265,51 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
         }
         __syncwarp();
 
-        // ---- one lane per chunk: the reference's loops, verbatim in structure ----
+        // ---- order the chunks by length class (counting sort over the chunk list), so that the 32
+        // chunks of a round cost about the same and the lanes of the warp stay together ----
         const int limit = at_end ? m : m - max_tok;
         int carry = at_end ? m : 0;
+        {
+          int cnt0 = 0, cnt1 = 0, cnt2 = 0;     // chunks of length <= 2, 3..4, 5..7 (the rest is class 3)
+          for (int base = 0; base < nst; base += 32) {
+            const int i = base + lane;
+            int cl = 4;
+            if (i < nst) { const int len = (i + 1 < nst ? (int)starts[i + 1] : m) - (int)starts[i]; cl = len <= 2 ? 0 : len <= 4 ? 1 : len <= 7 ? 2 : 3; }
+            cnt0 += __popc(__ballot_sync(0xffffffffu, cl == 0));
+            cnt1 += __popc(__ballot_sync(0xffffffffu, cl == 1));
+            cnt2 += __popc(__ballot_sync(0xffffffffu, cl == 2));
+          }
+          int o0 = 0, o1 = cnt0, o2 = cnt0 + cnt1, o3 = cnt0 + cnt1 + cnt2;
+          for (int base = 0; base < nst; base += 32) {
+            const int i = base + lane;
+            int cl = 4;
+            if (i < nst) { const int len = (i + 1 < nst ? (int)starts[i + 1] : m) - (int)starts[i]; cl = len <= 2 ? 0 : len <= 4 ? 1 : len <= 7 ? 2 : 3; }
+            const unsigned b0 = __ballot_sync(0xffffffffu, cl == 0), b1 = __ballot_sync(0xffffffffu, cl == 1);
+            const unsigned b2 = __ballot_sync(0xffffffffu, cl == 2), b3 = __ballot_sync(0xffffffffu, cl == 3);
+            const unsigned lt = lanemask_lt();
+            if (cl == 0) order[o0 + __popc(b0 & lt)] = (uint16_t)i;
+            else if (cl == 1) order[o1 + __popc(b1 & lt)] = (uint16_t)i;
+            else if (cl == 2) order[o2 + __popc(b2 & lt)] = (uint16_t)i;
+            else if (cl == 3) order[o3 + __popc(b3 & lt)] = (uint16_t)i;
+            o0 += __popc(b0); o1 += __popc(b1); o2 += __popc(b2); o3 += __popc(b3);
+          }
+        }
+        __syncwarp();
+
+        // ---- one lane per chunk: the reference's loops, verbatim in structure ----
         for (int base = 0; base < nst; base += 32) {
-          const int i = base + lane;
-          int fb = limit, fe = limit;
-          if (i < nst) {
-            fb = starts[i];
-            fe = i + 1 < nst ? starts[i + 1] : m;
+          const int k = base + lane;
+          if (k < nst) {
+            const int i = order[k];
+            int fb = starts[i];
+            int fe = i + 1 < nst ? (int)starts[i + 1] : m;
             if (fe > limit) fe = limit;
             if (i == 0 && first) fb = -1;
+            if (fb < fe) {
+              const int r = wp_chunk<TE>(top, g, cls, m, at_end, fb, fe, p.unk_id, ids_at, has_id);
+              carry = max(carry, r);
+            }
           }
-          if (fb < fe || (fb < limit && fb == -1)) {
-            const int r = wp_chunk<TE>(top, g, cls, m, at_end, fb, fe, p.unk_id, ids_at, has_id);
-            carry = max(carry, r);
-          }
-          if (__all_sync(0xffffffffu, fb >= limit)) break;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) carry = max(carry, __shfl_xor_sync(0xffffffffu, carry, o));
