@@ -97,6 +97,22 @@ def text_to_ids(h, s, max_len, unk=0, no_padding=False):
     return o.view(np.uint32)[:out_count]
 
 
+def utf8text_to_ids_with_offsets(h, s_bytes, max_len, unk=0, no_padding=False):
+    """dist-pypi/blingfire/__init__.py:272-285: (ids uint32, start offsets int32, end offsets int32)."""
+    L = lib()
+    L.TextToIdsWithOffsets.restype = c_int
+    L.TextToIdsWithOffsets.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int]
+    ids = np.zeros(max_len, dtype=np.int32)
+    starts = np.zeros(max_len, dtype=np.int32)
+    ends = np.zeros(max_len, dtype=np.int32)
+    t_count = L.TextToIdsWithOffsets(c_void_p(h), s_bytes, len(s_bytes), ids.ctypes.data, starts.ctypes.data, ends.ctypes.data,
+                                     max_len, unk)
+    if t_count == 0 and s_bytes and last_error():
+        raise RuntimeError(f"TextToIdsWithOffsets failed: {last_error()}")
+    out_count = min(max_len, t_count) if no_padding else max_len
+    return ids.view(np.uint32)[:out_count], starts[:out_count], ends[:out_count]
+
+
 def text_to_words_with_model(h, s):
     """dist-pypi/blingfire/__init__.py:105-122."""
     s_bytes = s.encode("utf-8")

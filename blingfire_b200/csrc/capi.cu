@@ -91,11 +91,12 @@ struct Slot {
   DevBuf<uint8_t> sp_overflow; // [pos-dict] BPE: grid-wide arc scratch for segments beyond the private one
   // generic lexer engine scratch
   DevBuf<uint16_t> lex_cls;
-  DevBuf<int32_t> lex_ncps, lex_tri, lex_tri_count;
+  DevBuf<int32_t> lex_ncps, lex_tri, lex_tri_count, lex_boff;
   // bookkeeping of the chunk in flight
   int64_t doc0 = 0, ndocs = 0;
   void release() {
-    lex_cls.release(); lex_ncps.release(); lex_tri.release(); lex_tri_count.release(); sp_arena.release(); sp_overflow.release();
+    lex_cls.release(); lex_ncps.release(); lex_tri.release(); lex_tri_count.release(); lex_boff.release();
+    sp_arena.release(); sp_overflow.release();
     text.release(); offsets.release(); ids.release(); counts.release(); row_off.release(); csr.release();
     counter.release(); h_row_off.release(); h_offsets.release(); h_csr.release();
     if (counts_ready) cudaEventDestroy(counts_ready);
@@ -575,6 +576,61 @@ int TextToIds(void* h, const char* s, int n, int32_t* ids, const int max_ids, co
   int32_t count = 0;
   const int64_t r = TextToIdsBatch(h, s, offsets, 1, ids, &count, max_ids, unk);
   return r < 0 ? 0 : (int)count;
+}
+
+// blingfiretokdll.cpp:1563-1609 -> TextToIdsWithOffsets_wp (:1108-1314) with offsets.  Served by the
+// generic lexer engine (decode with byte offsets -> Process_int triples -> the exact post-pass);
+// the fused kernel does not carry offsets.  [pos-dict] models: not served yet (returns 0).
+int TextToIdsWithOffsets(void* h, const char* s, int n, int32_t* ids, int* starts, int* ends, const int max_ids, const int unk) {
+  try {
+    if (!h || n <= 0 || n > 1000000000 || !s) return 0;              // :1121
+    if (!starts || !ends) return TextToIds(h, s, n, ids, max_ids, unk);
+    Model* m = (Model*)h;
+    g_last_error.clear();
+    if (m->has_seg) { set_error("TextToIdsWithOffsets is not served for [pos-dict] models yet"); return 0; }
+    if (!m->has_wbd || !m->lex_ok || !m->d_cls) { set_error("model has no lexer engine with a 1->1 charmap"); return 0; }
+    if (max_ids <= 0 || !ids) return 0;
+    std::lock_guard<std::mutex> lock(m->mu);
+    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return 0;
+    Slot& sl = m->slots[0];
+    if (!ensure_stream(sl)) return 0;
+    const size_t nb = (size_t)n;
+    if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve(2) || !sl.lex_cls.reserve(nb + 8) || !sl.lex_ncps.reserve(1) ||
+        !sl.lex_tri_count.reserve(1) || !sl.lex_tri.reserve(6 * nb + 8) || !sl.lex_boff.reserve(nb + 8) ||
+        !sl.ids.reserve(3 * (size_t)max_ids) || !sl.counts.reserve(2) || !m->h_words.reserve(3 * (size_t)max_ids + 16))
+      return 0;
+    const int64_t offs[2] = {0, n};
+    if (!cuda_ok(cudaMemcpyAsync(sl.text.p, s, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return 0;
+    if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return 0;
+    LexLaunch X = make_lex_launch(m, sl, 0, 0, n, 1, m->d_cls, 2);
+    X.boff_buf = sl.lex_boff.p;
+    int nl = 0;
+    if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return 0;
+    int32_t* d_ids = sl.ids.p;
+    if (!cuda_ok(lex_wp_offsets_launch(X, d_ids, d_ids + max_ids, d_ids + 2 * (size_t)max_ids, sl.counts.p, max_ids, unk, sl.stream, &nl),
+                 "post-pass launch"))
+      return 0;
+    g_launches += nl;
+    int32_t* hw = m->h_words.p;
+    if (!cuda_ok(cudaMemcpyAsync(hw, sl.counts.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return 0;
+    if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return 0;
+    const int count = hw[0];
+    if (count <= 0 || count > max_ids) return 0;
+    for (int k = 0; k < 3; ++k)
+      if (!cuda_ok(cudaMemcpyAsync(hw + 4 + (size_t)k * max_ids, d_ids + (size_t)k * max_ids, (size_t)count * 4, cudaMemcpyDeviceToHost, sl.stream), "D2H rows"))
+        return 0;
+    if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return 0;
+    std::memcpy(ids, hw + 4, (size_t)count * 4);                     // the rest of the arrays stays untouched
+    std::memcpy(starts, hw + 4 + (size_t)max_ids, (size_t)count * 4);
+    std::memcpy(ends, hw + 4 + 2 * (size_t)max_ids, (size_t)count * 4);
+    return count;
+  } catch (const std::exception& e) { set_error(e.what()); return 0; }
+}
+
+int TextToIdsWithOffsets_wp(void* h, const char* s, int n, int32_t* ids, int* starts, int* ends, const int max_ids, const int unk) {
+  Model* m = (Model*)h;
+  if (!m || !m->has_wbd || m->has_seg) return 0;
+  return TextToIdsWithOffsets(h, s, n, ids, starts, ends, max_ids, unk);
 }
 
 int TextToIds_wp(void* h, const char* s, int n, int32_t* ids, const int max_ids, const int unk) {

@@ -34,7 +34,9 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) lex_decode_kernel(const Lex
         const uint32_t b0 = __ldg(p.text + lo), b1 = __ldg(p.text + lo + 1), b2 = __ldg(p.text + lo + 2);
         if (b0 == 0xEF && b1 == 0xBB && b2 == 0xBF) lo += 3;
       }
-      uint16_t* cls = p.cls_buf + (__ldg(p.offsets + doc) - p.base_offset);
+      const int64_t doc_lo = __ldg(p.offsets + doc);
+      uint16_t* cls = p.cls_buf + (doc_lo - p.base_offset);
+      int32_t* boff = p.boff_buf ? p.boff_buf + (doc_lo - p.base_offset) : nullptr;
       int m = 0;
       unsigned bad = 0, sumlen = 0;
       for (int64_t bpos = lo; bpos < hi;) {
@@ -54,7 +56,10 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) lex_decode_kernel(const Lex
         int idx = m + incl - cnt;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (d.start_mask & (1u << k)) cls[idx++] = __ldg(p.cls_of_cp + d.cp[k]);
+          if (d.start_mask & (1u << k)) {
+            if (boff) boff[idx] = (int32_t)(pos0 + k - doc_lo);   // offsets count from the document start, BOM included
+            cls[idx++] = __ldg(p.cls_of_cp + d.cp[k]);
+          }
         m += __shfl_sync(0xffffffffu, incl, 31);
         bpos = bs + 128;
       }
@@ -93,7 +98,77 @@ __global__ void __launch_bounds__(128) lex_wp_kernel(const LexLaunch p, int32_t*
   counts[doc] = c;
 }
 
+// FAUtf8Size of a lead byte (FAUtf8Utils.cpp:23-42)
+__device__ __forceinline__ int utf8_size_of_lead(unsigned ch) {
+  if ((ch & 0x80) == 0x00) return 1;
+  if ((ch & 0xE0) == 0xC0) return 2;
+  if ((ch & 0xF0) == 0xE0) return 3;
+  if ((ch & 0xF8) == 0xF0) return 4;
+  return 0;
+}
+
+// TextToIdsWithOffsets_wp's post-pass including offsets (blingfiretokdll.cpp:1207-1313).  The
+// charmap is 1 -> 1 for every model served here, so pNormOffsets is the identity.
+__global__ void __launch_bounds__(128) lex_wp_offsets_kernel(const LexLaunch p, int32_t* ids, int32_t* starts, int32_t* ends,
+                                                             int32_t* counts, int max_ids, int unk) {
+  const int64_t doc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (doc >= p.ndocs) return;
+  int out = 0;
+  if (p.ncps[doc] > 0) {
+    const int64_t doc_lo = __ldg(p.offsets + doc);
+    const int64_t rel = doc_lo - p.base_offset;
+    const int32_t* res = p.tri_buf + 3 * (int64_t)p.tri_mul * rel;
+    const int32_t* boff = p.boff_buf + rel;
+    const uint8_t* text = p.text + doc_lo;
+    const int rn = p.tri_count[doc];
+    int32_t* oi = ids + doc * (int64_t)max_ids;
+    int32_t* os = starts + doc * (int64_t)max_ids;
+    int32_t* oe = ends + doc * (int64_t)max_ids;
+    auto emit = [&](int id, int from, int to) {
+      oi[out] = id;
+      os[out] = boff[from];
+      const int to_off = boff[to];
+      const int cs = utf8_size_of_lead(text[to_off]);
+      oe[out] = to_off + (cs > 0 ? cs - 1 : 0);
+      ++out;
+    };
+    for (int i = 0; i < rn; i += 3) {
+      const int tag = res[i];
+      if (tag == 4) continue;
+      if (tag == 1) {
+        const int tfrom = res[i + 1], tto = res[i + 2];
+        int j = i + 3, nsub = 0;
+        bool covered = false;
+        if (j < rn) {
+          int expect = tfrom, stag = res[j], sfrom = res[j + 1], sto = res[j + 2];
+          while (j <= rn && stag > 4 && expect == sfrom) {
+            expect = sto + 1; ++nsub; j += 3;
+            if (j < rn) { stag = res[j]; sfrom = res[j + 1]; sto = res[j + 2]; }
+          }
+          if (nsub > 0 && expect - 1 == tto) {
+            for (int k = 0; k < nsub && out < max_ids; ++k) { const int ti = (k + 1) * 3 + i; emit(res[ti], res[ti + 1], res[ti + 2]); }
+            covered = true;
+          }
+        }
+        if (!covered && out < max_ids) emit(unk, tfrom, tto);
+        i = j - 3;
+      }
+      if (out >= max_ids) break;
+    }
+  }
+  counts[doc] = out;
+}
+
 }  // namespace
+
+cudaError_t lex_wp_offsets_launch(const LexLaunch& p, int32_t* ids, int32_t* starts, int32_t* ends, int32_t* counts,
+                                  int max_ids, int unk, cudaStream_t stream, int* launches) {
+  if (p.ndocs <= 0) return cudaSuccess;
+  if (!p.boff_buf) return cudaErrorInvalidValue;
+  lex_wp_offsets_kernel<<<(int)((p.ndocs + 127) / 128), 128, 0, stream>>>(p, ids, starts, ends, counts, max_ids, unk);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
 
 cudaError_t lex_launch(const LexLaunch& p, const LexModelDev& m, cudaStream_t stream, int* launches) {
   if (p.ndocs <= 0) return cudaSuccess;

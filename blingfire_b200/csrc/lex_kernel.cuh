@@ -33,9 +33,13 @@ struct LexLaunch {
   int32_t* tri_buf;           // [3 * tri_mul * chunk bytes] triples of document d at 3*tri_mul*(offsets[d]-base_offset)
   int32_t* tri_count;         // [ndocs] ints written (3 per triple)
   int tri_mul;                // capacity in triples per code point: 1 (TextToWords, :492) or 2 (TextToIds_wp, :1194)
+  int32_t* boff_buf;          // optional [chunk bytes]: byte offset (from the document start) of every code point
 };
 
 cudaError_t lex_launch(const LexLaunch& p, const LexModelDev& m, cudaStream_t stream, int* launches);
 cudaError_t lex_wp_launch(const LexLaunch& p, int32_t* ids, int32_t* counts, int max_ids, int unk, cudaStream_t stream, int* launches);
+// the post-pass with offsets (blingfiretokdll.cpp:1263-1273,1289-1297); needs p.boff_buf
+cudaError_t lex_wp_offsets_launch(const LexLaunch& p, int32_t* ids, int32_t* starts, int32_t* ends, int32_t* counts,
+                                  int max_ids, int unk, cudaStream_t stream, int* launches);
 
 }  // namespace bfb200

@@ -62,6 +62,18 @@ int TextToIds_wp(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
 int TextToIds_sp(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
                        int32_t* pIdsArr, const int MaxIdsArrLength, const int UnkId);
 
+/* blingfiretokdll.h:83-92 / :49-58, blingfiretokdll.cpp:1563-1609 / :1108-1314.  Same as TextToIds
+ * plus, for every id, the byte offsets of the first byte of its first character and of the LAST
+ * byte of its last character in the input (UnkId tokens take the offsets of their word).  Entries
+ * beyond the returned count stay untouched in all three arrays.  Served for lexer ([wbd]) models;
+ * [pos-dict] models return 0 here for now (use TextToIds). */
+int TextToIdsWithOffsets(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
+                         int32_t* pIdsArr, int* pStartOffsets, int* pEndOffsets,
+                         const int MaxIdsArrLength, const int UnkId);
+int TextToIdsWithOffsets_wp(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
+                            int32_t* pIdsArr, int* pStartOffsets, int* pEndOffsets,
+                            const int MaxIdsArrLength, const int UnkId);
+
 /* blingfiretokdll.h:41, blingfiretokdll.cpp:610-614.  Default word breaker.  Returns -1 on
  * error, 0 for empty input, else the required output size including the trailing NUL (the
  * output is copied only if it fits).  The reference embeds wbd.bin as a byte array; this
