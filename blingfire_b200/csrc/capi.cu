@@ -32,6 +32,7 @@ using namespace bfb200;
 namespace {
 
 thread_local std::string g_last_error;
+thread_local double g_last_kernel_ms = 0.0;   // device time of the tokenization kernels of the last host batch call
 std::atomic<int64_t> g_launches{0};
 
 void set_error(const std::string& e) { g_last_error = e; }
@@ -77,6 +78,7 @@ constexpr int kAhead = 2;    // chunks enqueued behind the one whose counts the 
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t counts_ready = nullptr;   // recorded after the chunk's row offsets were copied to the host
+  cudaEvent_t k_begin = nullptr, k_end = nullptr;   // around the engine's kernels (device time of the tokenization alone)
   DevBuf<uint8_t> text;
   DevBuf<int64_t> offsets;
   DevBuf<int32_t> ids;
@@ -101,6 +103,9 @@ struct Slot {
     counter.release(); h_row_off.release(); h_offsets.release(); h_csr.release();
     if (counts_ready) cudaEventDestroy(counts_ready);
     counts_ready = nullptr;
+    if (k_begin) cudaEventDestroy(k_begin);
+    if (k_end) cudaEventDestroy(k_end);
+    k_begin = k_end = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -277,6 +282,7 @@ LexLaunch make_lex_launch(const Model*, Slot& s, int64_t first_off, int64_t b0, 
 bool ensure_stream(Slot& s) {
   if (s.stream) return true;
   if (!cuda_ok(cudaEventCreateWithFlags(&s.counts_ready, cudaEventDisableTiming), "cudaEventCreate")) return false;
+  if (!cuda_ok(cudaEventCreate(&s.k_begin), "cudaEventCreate") || !cuda_ok(cudaEventCreate(&s.k_end), "cudaEventCreate")) return false;
   return cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
 }
 
@@ -304,6 +310,7 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
   if (!cuda_ok(cudaMemcpyAsync(s.offsets.p, offsets + doc0, ((size_t)ndocs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream), "H2D offsets")) return false;
 
   WpLaunchInfo info{};
+  if (!cuda_ok(cudaEventRecord(s.k_begin, s.stream), "event record")) return false;
   if (m->engine == 3) {
     // [pos-dict] engine.  Documents whose symbols exceed the shared-memory window use a per-warp
     // arena sized for the longest document of the chunk; the grid shrinks if the arena would not fit.
@@ -356,6 +363,7 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
     L.work_counter = s.counter.p;
     if (!cuda_ok(wp_tokenize_launch(L, s.stream, &info), "tokenize launch")) return false;
   }
+  if (!cuda_ok(cudaEventRecord(s.k_end, s.stream), "event record")) return false;
   if (!cuda_ok(wp_scan_counts(s.counts.p, s.row_off.p, ndocs, s.stream), "scan")) return false;
   if (!cuda_ok(wp_compact_launch(s.ids.p, s.counts.p, s.row_off.p, ndocs, max_ids, s.csr.p, s.stream), "compact")) return false;
   g_launches += info.launches + 2;
@@ -403,6 +411,7 @@ template <typename Issue, typename Finish>
 bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, int max_ids, int unk,
                   Issue issue, Finish finish) {
   if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return false;
+  g_last_kernel_ms = 0.0;
   bool copying[kSlots] = {};
   auto settle = [&](int si) -> bool {   // wait for the ids copy of the chunk that last used slot si
     if (!copying[si]) return true;
@@ -414,6 +423,8 @@ bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t nd
   auto counts_ready = [&](int si) -> bool {   // kernels of the chunk in slot si are done
     Slot& s = m->slots[si];
     if (!cuda_ok(cudaEventSynchronize(s.counts_ready), "event sync")) return false;
+    float kms = 0.0f;
+    if (cudaEventElapsedTime(&kms, s.k_begin, s.k_end) == cudaSuccess) g_last_kernel_ms += kms;
     if (!chunk_ok(s) || !issue(s)) return false;
     copying[si] = true;
     return true;
@@ -465,6 +476,7 @@ int GetBlingFireTokVersion(void) { return 18 * 1000 + 0; }
 
 const char* BlingFireB200LastError(void) { return g_last_error.c_str(); }
 int64_t BlingFireB200KernelLaunches(void) { return g_launches.load(); }
+double BlingFireB200LastKernelMs(void) { return g_last_kernel_ms; }
 int BlingFireB200ModelEngine(void* h) { return h ? ((Model*)h)->engine : 0; }
 
 void* LoadModel(const char* path) {

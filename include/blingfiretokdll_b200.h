@@ -119,8 +119,12 @@ const char* BlingFireB200LastError(void);
 /* Number of GPU kernels this library has launched in this process (bench.py: gpu_launches). */
 int64_t BlingFireB200KernelLaunches(void);
 
+/* Device time (ms, CUDA events) the tokenization kernels of the calling thread's last host batch call
+ * took, summed over its chunks -- the kernel share of an end-to-end call. */
+double BlingFireB200LastKernelMs(void);
+
 /* Which engine serves the model: 1 = fused WordPiece kernel (FastPath lexer models),
- * 0 = none (model loaded but no GPU engine for it yet). */
+ * 2 = generic lexer engine, 3 = segmentation engine (Unigram-LM / BPE), 0 = none. */
 int BlingFireB200ModelEngine(void* ModelPtr);
 
 #ifdef __cplusplus

@@ -1,7 +1,10 @@
 #!/usr/bin/env python3
 """Side measurements for BASELINE.md's results table: the configurations other than the bench line
-(cfg 1 TextToWords, cfg 3 gpt2, cfg 4 xlm-r), through the host-pointer C ABI, next to the reference's
-CPU path on a sample.  Not the contract benchmark (that is bench.py on cfg 2)."""
+(cfg 1 TextToWords, cfg 3 gpt2, cfg 4 xlm-r; cfg 2 through the same path for comparison), through
+the host-pointer C ABI (TextToIdsBatchCsr) with PINNED host buffers, next to the reference's CPU path
+on a sample.  Reports, per configuration, the end-to-end GB/s (copies included) and the kernel-only
+GB/s (device time of the tokenization kernels, CUDA events inside the library).
+Not the contract benchmark (that is bench.py on cfg 2)."""
 import argparse
 import ctypes
 import json
@@ -24,6 +27,7 @@ def ref_cpu(model, text, offs, n, max_ids, unk, threads):
     ref = os.path.join(ROOT, "oracle", "_ref", "libblingfiretokdll.so")
     tok = ctypes.c_int64(0)
     so = np.ascontiguousarray(offs[: n + 1])
+    L.ref_time_batch(ref.encode(), model.encode(), text.ctypes.data, so.ctypes.data, min(n, 5000), max_ids, unk, threads, ctypes.byref(tok), None)
     secs = L.ref_time_batch(ref.encode(), model.encode(), text.ctypes.data, so.ctypes.data, n, max_ids, unk, threads,
                             ctypes.byref(tok), None)
     return int(so[-1]) / secs / 1e9, tok.value / secs
@@ -31,7 +35,7 @@ def ref_cpu(model, text, offs, n, max_ids, unk, threads):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--docs", type=int, default=200_000)
+    ap.add_argument("--docs", type=int, default=500_000)
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     import torch
@@ -41,11 +45,12 @@ def main():
     torch.cuda.set_device(0)
     torch.zeros(1, device="cuda")
     cores = len(os.sched_getaffinity(0))
+    L = bf.lib()
+    L.BlingFireB200LastKernelMs.restype = ctypes.c_double
     out = {"cores": cores}
 
     # cfg 1: default TextToWords on 10k short ASCII lines (per-call API)
     lines = [l for l in read_lines("test.txt") if len(l) <= 120 and all(c < 128 for c in l)][:10000]
-    L = bf.lib()
     buf = ctypes.create_string_buffer(1024)
     L.TextToWords(lines[0], len(lines[0]), buf, 1024)
     t0 = time.perf_counter()
@@ -55,25 +60,42 @@ def main():
     nb = sum(len(l) for l in lines)
     out["cfg1_TextToWords_10k_lines"] = {"MB_per_s": nb / dt / 1e6, "us_per_call": dt / len(lines) * 1e6, "bytes": nb}
 
-    for name, cfg, model, unk, max_ids, gen in [
-        ("cfg3_gpt2", 3, "gpt2.bin", 0, 4096, lambda n: corpus.gen_docs("EN", n, seed=3, fixed_len=0)),
-        ("cfg4_xlmr", 4, "xlm_roberta_base.bin", 3, 512, lambda n: corpus.gen_docs("MULTI", n, seed=4, fixed_len=512, emoji_every=16)),
-        ("cfg2_bert_host_api", 2, "bert_base_tok.bin", 100, 512, lambda n: corpus.gen_docs("EN", n, seed=2, fixed_len=512)),
+    for name, model, unk, max_ids, gen in [
+        ("cfg3_gpt2", "gpt2.bin", 0, 4096, lambda n: corpus.gen_docs("EN", n, seed=3, fixed_len=0)),
+        ("cfg4_xlmr", "xlm_roberta_base.bin", 3, 512, lambda n: corpus.gen_docs("MULTI", n, seed=4, fixed_len=512, emoji_every=16)),
+        ("cfg2_bert_same_path", "bert_base_tok.bin", 100, 512, lambda n: corpus.gen_docs("EN", n, seed=2, fixed_len=512)),
     ]:
         text, offs = gen(args.docs)
+        n, nbytes = len(offs) - 1, int(offs[-1])
+        h_text = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
+        h_text[:nbytes].copy_(torch.from_numpy(text))
+        h_offs = torch.from_numpy(offs).pin_memory()
+        cap = int(np.minimum(np.diff(offs), max_ids).sum())
+        h_ids = torch.empty(cap + 1, dtype=torch.int32, pin_memory=True)
+        h_idoffs = torch.zeros(n + 1, dtype=torch.int64, pin_memory=True)
         h = bf.load_model(model_path(model))
-        ids, idoffs = bf.text_to_ids_batch_csr(h, (text, offs), max_ids, unk)   # warm-up (allocations)
-        ts = []
+
+        def call():
+            r = L.TextToIdsBatchCsr(ctypes.c_void_p(h), h_text.data_ptr(), h_offs.data_ptr(), n, h_ids.data_ptr(), cap,
+                                    h_idoffs.data_ptr(), max_ids, unk)
+            assert r >= 0, bf.last_error()
+            return r
+
+        call()
+        best, kms, tot = 1e9, 0.0, 0
         for _ in range(args.reps):
             t0 = time.perf_counter()
-            ids, idoffs = bf.text_to_ids_batch_csr(h, (text, offs), max_ids, unk)
-            ts.append(time.perf_counter() - t0)
-        dt = min(ts)
-        ns = min(args.docs, 50000)
+            tot = call()
+            dt = time.perf_counter() - t0
+            if dt < best:
+                best, kms = dt, L.BlingFireB200LastKernelMs()
+        ns = min(n, 50000)
         cpu_gbs, cpu_tps = ref_cpu(model_path(model), text, offs, ns, max_ids, unk, cores)
-        out[name] = {"docs": args.docs, "bytes": int(offs[-1]), "tokens": int(idoffs[-1]), "e2e_GB_per_s": int(offs[-1]) / dt / 1e9,
-                     "e2e_tokens_per_s": int(idoffs[-1]) / dt, "cpu_ref_GB_per_s": cpu_gbs, "cpu_threads": cores,
-                     "note": "host pageable numpy buffers through TextToIdsBatchCsr"}
+        out[name] = {"docs": n, "bytes": nbytes, "tokens": int(tot), "e2e_GB_per_s": nbytes / best / 1e9,
+                     "e2e_ms": best * 1e3, "kernel_ms": kms, "kernel_GB_per_s": nbytes / (kms * 1e-3) / 1e9 if kms > 0 else None,
+                     "tokens_per_s_kernel": tot / (kms * 1e-3) if kms > 0 else None,
+                     "cpu_ref_GB_per_s": cpu_gbs, "cpu_ref_tokens_per_s": cpu_tps, "cpu_threads": cores, "cpu_sample_docs": ns,
+                     "api": "TextToIdsBatchCsr, pinned host buffers"}
         bf.free_model(h)
     print(json.dumps(out, indent=1))
 
