@@ -288,6 +288,35 @@ bool ensure_stream(Slot& s) {
 
 // Enqueue one chunk [doc0, doc0+ndocs) of a host CSR batch on slot s: H2D, tokenize, scan, compact,
 // D2H of the row offsets.  Offsets stay absolute; the device text pointer is biased instead.
+// [pos-dict] engine over the documents already in s.text / s.offsets (absolute bytes [b0, b1)).
+// Documents whose symbols exceed the shared-memory window use a per-warp arena sized for the longest
+// document of the launch; the grid shrinks if the arena would not fit.  With starts/ends the offsets
+// ride in the arena as well.
+bool launch_segmentation(Model* m, Slot& s, int64_t b0, int64_t b1, int64_t ndocs, int64_t max_len, int32_t* d_ids,
+                         int32_t* d_starts, int32_t* d_ends, int max_ids, int unk, int* launches) {
+  int64_t cap64 = (m->S.has_charmap ? 2 * (max_len + 1) : max_len + 1) + 2;
+  const bool is_bpe = m->S.tok_algo == kTokenizeBpe || m->S.tok_algo == kTokenizeBpeOpt || m->S.tok_algo == kTokenizeBpeOptWithMerges;
+  // Unigram keeps everything in the window when the document fits; BPE always keeps its arc
+  // scratch in the arena
+  if (cap64 <= kSpWindow && !is_bpe && !d_starts) cap64 = 16;
+  if (cap64 > (1ll << 28)) { set_error("document too large for the segmentation engine"); return false; }
+  const int cap = (int)cap64;
+  const int64_t per_warp = sp_arena_bytes_per_warp(cap, m->S.max_arc_len);
+  int warps = sp_preferred_warps();
+  const int64_t budget = 6ll << 30;
+  if (per_warp * warps > budget) warps = (int)std::max<int64_t>(8, (budget / per_warp) / 8 * 8);
+  if (per_warp * warps > (24ll << 30)) { set_error("document too large for the segmentation engine arena"); return false; }
+  if (!s.sp_arena.reserve((size_t)(per_warp * warps)) || !s.counter.reserve(2)) return false;
+  const int64_t ovf_entries = is_bpe ? sp_overflow_entries(cap, m->S.max_arc_len) : 1;
+  if (!s.sp_overflow.reserve((size_t)ovf_entries * 16)) return false;
+  SpLaunch X{};
+  X.overflow = s.sp_overflow.p; X.overflow_cap = ovf_entries;
+  X.text = s.text.p - b0; X.offsets = s.offsets.p; X.ndocs = ndocs; X.text_bytes = b1;
+  X.ids = d_ids; X.counts = s.counts.p; X.starts = d_starts; X.ends = d_ends; X.max_ids = max_ids; X.unk_id = unk;
+  X.work_counter = s.counter.p; X.arena = s.sp_arena.p; X.arena_stride = per_warp; X.arena_cap = cap; X.grid_warps = warps;
+  return cuda_ok(sp_tokenize_launch(X, make_sp_model(m), s.stream, launches), "segmentation launch");
+}
+
 bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, int64_t doc0, int64_t ndocs,
                    int max_ids, int unk) {
   if (!ensure_stream(s)) return false;
@@ -312,32 +341,10 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
   WpLaunchInfo info{};
   if (!cuda_ok(cudaEventRecord(s.k_begin, s.stream), "event record")) return false;
   if (m->engine == 3) {
-    // [pos-dict] engine.  Documents whose symbols exceed the shared-memory window use a per-warp
-    // arena sized for the longest document of the chunk; the grid shrinks if the arena would not fit.
     int64_t max_len = 0;
     for (int64_t d = doc0; d < doc0 + ndocs; ++d) max_len = std::max(max_len, offsets[d + 1] - offsets[d]);
-    int64_t cap64 = (m->S.has_charmap ? 2 * (max_len + 1) : max_len + 1) + 2;
-    const bool is_bpe = m->S.tok_algo == kTokenizeBpe || m->S.tok_algo == kTokenizeBpeOpt || m->S.tok_algo == kTokenizeBpeOptWithMerges;
-    // Unigram keeps everything in the window when the document fits; BPE always keeps its arc
-    // scratch (32 arcs per symbol of capacity) in the arena
-    if (cap64 <= kSpWindow && !is_bpe) cap64 = 16;
-    if (cap64 > (1ll << 28)) { set_error("document too large for the segmentation engine"); return false; }
-    const int cap = (int)cap64;
-    const int64_t per_warp = sp_arena_bytes_per_warp(cap, m->S.max_arc_len);
-    int warps = sp_preferred_warps();
-    const int64_t budget = 6ll << 30;
-    if (per_warp * warps > budget) warps = (int)std::max<int64_t>(8, (budget / per_warp) / 8 * 8);
-    if (per_warp * warps > (24ll << 30)) { set_error("document too large for the segmentation engine arena"); return false; }
-    if (!s.sp_arena.reserve((size_t)(per_warp * warps)) || !s.counter.reserve(2)) return false;
-    const int64_t ovf_entries = is_bpe ? sp_overflow_entries(cap, m->S.max_arc_len) : 1;
-    if (!s.sp_overflow.reserve((size_t)ovf_entries * 16)) return false;
-    SpLaunch X{};
-    X.overflow = s.sp_overflow.p; X.overflow_cap = ovf_entries;
-    X.text = s.text.p - b0; X.offsets = s.offsets.p; X.ndocs = ndocs; X.text_bytes = b1;
-    X.ids = s.ids.p; X.counts = s.counts.p; X.max_ids = max_ids; X.unk_id = unk;
-    X.work_counter = s.counter.p; X.arena = s.sp_arena.p; X.arena_stride = per_warp; X.arena_cap = cap; X.grid_warps = warps;
     int nl = 0;
-    if (!cuda_ok(sp_tokenize_launch(X, make_sp_model(m), s.stream, &nl), "segmentation launch")) return false;
+    if (!launch_segmentation(m, s, b0, b1, ndocs, max_len, s.ids.p, nullptr, nullptr, max_ids, unk, &nl)) return false;
     info.launches = nl;
   } else if (m->engine == 2) {
     // generic lexer: decode/classify -> Process_int triples -> wp post-pass
@@ -599,14 +606,43 @@ int TextToIdsWithOffsets(void* h, const char* s, int n, int32_t* ids, int* start
     if (!starts || !ends) return TextToIds(h, s, n, ids, max_ids, unk);
     Model* m = (Model*)h;
     g_last_error.clear();
-    if (m->has_seg) { set_error("TextToIdsWithOffsets is not served for [pos-dict] models yet"); return 0; }
-    if (!m->has_wbd || !m->lex_ok || !m->d_cls) { set_error("model has no lexer engine with a 1->1 charmap"); return 0; }
+    if (m->engine == 0) { set_error("no GPU engine for this model type yet"); return 0; }
+    if (m->engine != 3 && (!m->has_wbd || !m->lex_ok || !m->d_cls)) { set_error("model has no lexer engine with a 1->1 charmap"); return 0; }
     if (max_ids <= 0 || !ids) return 0;
     std::lock_guard<std::mutex> lock(m->mu);
     if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return 0;
     Slot& sl = m->slots[0];
     if (!ensure_stream(sl)) return 0;
     const size_t nb = (size_t)n;
+    if (m->engine == 3) {
+      // TextToIdsWithOffsets_sp (:1349-1535): the segmentation kernel with the byte offsets of every
+      // symbol carried through normalisation and whitespace collapsing
+      if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve(2) || !sl.ids.reserve(3 * (size_t)max_ids) || !sl.counts.reserve(2) ||
+          !m->h_words.reserve(3 * (size_t)max_ids + 16))
+        return 0;
+      const int64_t offs[2] = {0, n};
+      if (!cuda_ok(cudaMemcpyAsync(sl.text.p, s, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return 0;
+      if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return 0;
+      int32_t* d_ids = sl.ids.p;
+      int nl = 0;
+      if (!launch_segmentation(m, sl, 0, n, 1, n, d_ids, d_ids + max_ids, d_ids + 2 * (size_t)max_ids, max_ids, unk, &nl)) return 0;
+      g_launches += nl;
+      int32_t* hw = m->h_words.p;
+      if (!cuda_ok(cudaMemcpyAsync(hw, sl.counts.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return 0;
+      if (!cuda_ok(cudaMemcpyAsync(hw + 2, sl.counter.p + 1, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H flag")) return 0;
+      if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return 0;
+      if (hw[2] != 0) { set_error("segmentation engine: scratch exhausted (code " + std::to_string(hw[2]) + ")"); return 0; }
+      const int count = hw[0];
+      if (count <= 0 || count > max_ids) return 0;
+      for (int k = 0; k < 3; ++k)
+        if (!cuda_ok(cudaMemcpyAsync(hw + 4 + (size_t)k * max_ids, d_ids + (size_t)k * max_ids, (size_t)count * 4, cudaMemcpyDeviceToHost, sl.stream), "D2H rows"))
+          return 0;
+      if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return 0;
+      std::memcpy(ids, hw + 4, (size_t)count * 4);                   // the rest of the arrays stays untouched
+      std::memcpy(starts, hw + 4 + (size_t)max_ids, (size_t)count * 4);
+      std::memcpy(ends, hw + 4 + 2 * (size_t)max_ids, (size_t)count * 4);
+      return count;
+    }
     if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve(2) || !sl.lex_cls.reserve(nb + 8) || !sl.lex_ncps.reserve(1) ||
         !sl.lex_tri_count.reserve(1) || !sl.lex_tri.reserve(6 * nb + 8) || !sl.lex_boff.reserve(nb + 8) ||
         !sl.ids.reserve(3 * (size_t)max_ids) || !sl.counts.reserve(2) || !m->h_words.reserve(3 * (size_t)max_ids + 16))
@@ -642,6 +678,12 @@ int TextToIdsWithOffsets(void* h, const char* s, int n, int32_t* ids, int* start
 int TextToIdsWithOffsets_wp(void* h, const char* s, int n, int32_t* ids, int* starts, int* ends, const int max_ids, const int unk) {
   Model* m = (Model*)h;
   if (!m || !m->has_wbd || m->has_seg) return 0;
+  return TextToIdsWithOffsets(h, s, n, ids, starts, ends, max_ids, unk);
+}
+
+int TextToIdsWithOffsets_sp(void* h, const char* s, int n, int32_t* ids, int* starts, int* ends, const int max_ids, const int unk) {
+  Model* m = (Model*)h;
+  if (!m || !m->has_seg) return 0;
   return TextToIdsWithOffsets(h, s, n, ids, starts, ends, max_ids, unk);
 }
 

@@ -42,6 +42,8 @@ struct Work {
   int32_t* bid;        // [cap]   Unigram best id; BPE: first-arc index, then tos[]
   uint8_t* flag;       // [cap+4] token-start marks / BPE intermediate[]
   int2* tile;          // [kTileArcs] Unigram arc tile {end, key}
+  int32_t* boff_a;     // [cap+2] byte offset of every symbol (offsets requested; arena only)
+  int32_t* boff_b;     // [cap+2] its staging twin; later the end position of the token that starts here
   int cap;
 };
 
@@ -49,14 +51,18 @@ __host__ __device__ inline int64_t align16(int64_t v) { return (v + 15) & ~(int6
 __host__ __device__ inline int64_t work_bytes(int cap) {
   return align16(4ll * (cap + 2)) * 2 + align16(8ll * cap) + align16(4ll * cap) + align16(cap + 4) + align16(8ll * kTileArcs);
 }
-__device__ inline Work make_work(uint8_t* base, int cap) {
+// the arena variant also carries the two offset arrays
+__host__ __device__ inline int64_t work_bytes_arena(int cap) { return work_bytes(cap) + 2 * align16(4ll * (cap + 2)); }
+__device__ inline Work make_work(uint8_t* base, int cap, bool with_offsets) {
   Work w; int64_t o = 0;
   w.sym = (int32_t*)(base + o); o += align16(4ll * (cap + 2));
   w.tmp = (int32_t*)(base + o); o += align16(4ll * (cap + 2));
   w.score = (double*)(base + o); o += align16(8ll * cap);
   w.bid = (int32_t*)(base + o); o += align16(4ll * cap);
   w.flag = base + o; o += align16(cap + 4);
-  w.tile = (int2*)(base + o);
+  w.tile = (int2*)(base + o); o += align16(8ll * kTileArcs);
+  w.boff_a = with_offsets ? (int32_t*)(base + o) : nullptr; o += align16(4ll * (cap + 2));
+  w.boff_b = with_offsets ? (int32_t*)(base + o) : nullptr;
   w.cap = cap;
   return w;
 }
@@ -99,17 +105,17 @@ __device__ __forceinline__ void sp_info(const SpModelDev& m, int key, int unk, i
 // Returns the number of raw symbols incl. the dummy prefix, or -1 on invalid UTF-8 / no symbols.
 // blingfiretokdll.cpp:1372-1412
 __device__ int sp_raw_symbols(const SpModelDev& m, const uint8_t* text, int64_t lo0, int64_t hi, int64_t padded_bytes,
-                              int32_t* out, bool store, int lane) {
+                              int32_t* out, int32_t* boff, bool store, int lane) {
   int64_t lo = lo0;
   if (hi - lo >= 3) {
     const uint32_t b0 = __ldg(text + lo), b1 = __ldg(text + lo + 1), b2 = __ldg(text + lo + 2);
     if (b0 == 0xEF && b1 == 0xBB && b2 == 0xBF) lo += 3;   // both decoders skip the BOM
   }
   const int off = m.no_dummy_prefix ? 0 : 1;
-  if (store && off && lane == 0) out[0] = kSpDelim;
+  if (store && off && lane == 0) { out[0] = kSpDelim; if (boff) boff[0] = -1; }   // :1372,:1387
   int cnt = 0;
   if (m.use_raw_bytes) {                                    // FAStrUtf8AsBytesToArray
-    if (store) for (int64_t p = lo + lane; p < hi; p += 32) out[off + (p - lo)] = (int)__ldg(text + p);
+    if (store) for (int64_t p = lo + lane; p < hi; p += 32) { out[off + (p - lo)] = (int)__ldg(text + p); if (boff) boff[off + (p - lo)] = (int)(p - lo0); }
     cnt = (int)(hi - lo);
   } else {                                                  // FAStrUtf8ToArray
     const uint32_t* text32 = reinterpret_cast<const uint32_t*>(text);
@@ -126,7 +132,7 @@ __device__ int sp_raw_symbols(const SpModelDev& m, const uint8_t* text, int64_t 
       if (store) {
         int idx = off + cnt + incl - c;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (d.start_mask & (1u << k)) out[idx++] = (int)d.cp[k];
+        for (int k = 0; k < 4; ++k) if (d.start_mask & (1u << k)) { if (boff) boff[idx] = (int)(pos0 + k - lo0); out[idx++] = (int)d.cp[k]; }
       }
       cnt += __shfl_sync(0xffffffffu, incl, 31);
       bpos = bs + 128;
@@ -140,7 +146,8 @@ __device__ int sp_raw_symbols(const SpModelDev& m, const uint8_t* text, int64_t 
 }
 
 // FANormalize over src[0..n) (FAUtils_cl.h:311-369): returns the normalized length; writes dst when given.
-__device__ int sp_normalize(const SpModelDev& m, const int32_t* src, int n, int32_t* dst, int lane) {
+__device__ int sp_normalize(const SpModelDev& m, const int32_t* src, int n, int32_t* dst, int lane,
+                            const int32_t* boff_src = nullptr, int32_t* boff_dst = nullptr) {
   int total = 0;
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
@@ -155,6 +162,7 @@ __device__ int sp_normalize(const SpModelDev& m, const int32_t* src, int n, int3
       const int o = total + incl - c;
       if (nc == 0xFF) dst[o] = cp;
       else { const uint32_t f = __ldg(m.norm_first + cp); for (int k = 0; k < c; ++k) dst[o + k] = __ldg(m.norm_values + f + k); }
+      if (boff_dst) for (int k = 0; k < c; ++k) boff_dst[o + k] = boff_src[i];   // pNormOffsets composed with pOffsets
     }
     total += __shfl_sync(0xffffffffu, incl, 31);
   }
@@ -164,7 +172,8 @@ __device__ int sp_normalize(const SpModelDev& m, const int32_t* src, int n, int3
 // whitespace runs -> one U+2581, one trailing U+2581 dropped (blingfiretokdll.cpp:1462-1496).
 // A white symbol is kept iff the previous OUTPUT symbol is not U+2581, which is equivalent to
 //   i == 0  ||  (src[i-1] is not white && src[i-1] != U+2581).
-__device__ int sp_collapse(const int32_t* src, int n, int32_t* dst, int lane) {
+__device__ int sp_collapse(const int32_t* src, int n, int32_t* dst, int lane, const int32_t* boff_src = nullptr,
+                           int32_t* boff_dst = nullptr) {
   int total = 0;
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
@@ -177,7 +186,7 @@ __device__ int sp_collapse(const int32_t* src, int n, int32_t* dst, int lane) {
       if (w) c = kSpDelim;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (keep) dst[total + __popc(bal & bf_lanemask_lt())] = c;
+    if (keep) { const int o = total + __popc(bal & bf_lanemask_lt()); dst[o] = c; if (boff_dst) boff_dst[o] = boff_src[i]; }
     total += __popc(bal);
   }
   __syncwarp();
@@ -185,9 +194,27 @@ __device__ int sp_collapse(const int32_t* src, int n, int32_t* dst, int lane) {
   return total;
 }
 
-// ordered emission of the tokens marked in w.flag (bit 1) with ids taken from idsrc[]
+// FAUtf8Size of a lead byte (FAUtf8Utils.cpp:23-42)
+__device__ __forceinline__ int sp_utf8_size_of_lead(unsigned ch) {
+  if ((ch & 0x80) == 0) return 1;
+  if ((ch & 0xE0) == 0xC0) return 2;
+  if ((ch & 0xF0) == 0xE0) return 3;
+  if ((ch & 0xF8) == 0xF0) return 4;
+  return 0;
+}
+
+// where the offsets of one document go (blingfiretokdll.cpp:1519-1529); boff == nullptr: ids only
+struct OffsetsOut {
+  const int32_t* boff;   // byte offset (from the document start) of every final symbol, -1 = dummy prefix
+  const uint8_t* doc;    // first byte of the document
+  int32_t* starts;       // rows parallel to the ids row
+  int32_t* ends;
+};
+
+// ordered emission of the tokens marked in w.flag (bit 1) with ids taken from idsrc[]; with offsets,
+// the token that starts at q ends at symbol w.bid[q]
 __device__ int sp_emit(const Work& w, const int32_t* idsrc, int N, int32_t* row, int max_ids, int unk, int id_offset,
-                       bool map_unknown, int lane) {
+                       bool map_unknown, int lane, const OffsetsOut& oo) {
   int out = 0;
   for (int p0 = 0; p0 < N; p0 += 32) {
     const int q = p0 + lane;
@@ -198,6 +225,14 @@ __device__ int sp_emit(const Work& w, const int32_t* idsrc, int N, int32_t* row,
       int id = idsrc[q];
       if (map_unknown && id == -1) id = unk;
       row[rank] = id + id_offset;                           // ids[k] = id + IdOffset, UNK included (:1516)
+      if (oo.boff) {
+        oo.starts[rank] = oo.boff[q];
+        const int to_off = oo.boff[w.bid[q]];
+        // a token that is only the dummy prefix has to_off == -1: the reference then sizes the byte
+        // BEFORE the input (:1527, out of bounds); pinned to size 0 like the oracle does
+        const int cs = to_off < 0 ? 0 : sp_utf8_size_of_lead(oo.doc[to_off]);
+        oo.ends[rank] = to_off + (cs > 0 ? cs - 1 : 0);
+      }
     }
     out += __popc(bal);
   }
@@ -207,7 +242,8 @@ __device__ int sp_emit(const Work& w, const int32_t* idsrc, int N, int32_t* row,
 // =====================================================================================
 // Unigram-LM best path (FATokenSegmentationTools_1best_t.h:174-279)
 // =====================================================================================
-__device__ int sp_unigram(const SpModelDev& m, Work& w, int N, int32_t* row, int max_ids, int unk, int lane) {
+__device__ int sp_unigram(const SpModelDev& m, Work& w, int N, int32_t* row, int max_ids, int unk, int lane,
+                          const OffsetsOut& oo) {
   int32_t* begin = w.tmp;
   for (int i = lane; i < N; i += 32) { w.score[i] = -(double)FLT_MAX; w.bid[i] = -1; begin[i] = -1; w.flag[i] = 0; }
   __syncwarp();
@@ -259,14 +295,15 @@ __device__ int sp_unigram(const SpModelDev& m, Work& w, int N, int32_t* row, int
     while (end >= 0) {
       const int b = begin[end];
       const int id = w.bid[end];
-      if (b < 0) { w.flag[0] |= 2; w.sym[0] = id; break; }   // never-set arc: the reference emits it first and stops
+      if (b < 0) { w.flag[0] |= 2; w.sym[0] = id; w.bid[0] = end; break; }   // never-set arc: the reference emits it first and stops
       w.flag[b] |= 2;
       w.sym[b] = id;                                         // symbols before `end` are not read again
+      w.bid[b] = end;                                        // ... nor are the ids at or before b: keep the token's end
       end = b - 1;
     }
   }
   __syncwarp();
-  return sp_emit(w, w.sym, N, row, max_ids, unk, m.id_offset, true, lane);
+  return sp_emit(w, w.sym, N, row, max_ids, unk, m.id_offset, true, lane, oo);
 }
 
 // =====================================================================================
@@ -406,7 +443,7 @@ __device__ bool bpe_segment(const SpModelDev& m, Work& w, int N, int a, int b, i
 }
 
 __device__ int sp_bpe(const SpModelDev& m, Work& w, int N, int32_t* row, int max_ids, int unk, const ArcScratch& scratch,
-                      int lane, bool* overflow) {
+                      int lane, bool* overflow, const OffsetsOut& oo) {
   const bool merges = m.tok_algo == kTokenizeBpeOptWithMerges;
   const bool fast = merges || m.tok_algo == kTokenizeBpeOpt;
   int32_t* ids_at = w.tmp;
@@ -442,7 +479,7 @@ __device__ int sp_bpe(const SpModelDev& m, Work& w, int N, int32_t* row, int max
       if (whole && ((fast && tok_start) || b - a == 1)) {
         int id; float r;
         sp_info(m, whole_key, unk, id, r);
-        ids_at[a] = id; w.flag[a] = 2;
+        ids_at[a] = id; w.flag[a] = 2; w.bid[a] = b - 1;     // tos[a]
       } else hard = true;
     }
     // ---- the other segments of this round, one at a time, warp-cooperatively ----
@@ -454,7 +491,7 @@ __device__ int sp_bpe(const SpModelDev& m, Work& w, int N, int32_t* row, int max
     }
   }
   __syncwarp();
-  return sp_emit(w, ids_at, N, row, max_ids, unk, m.id_offset, false, lane);
+  return sp_emit(w, ids_at, N, row, max_ids, unk, m.id_offset, false, lane, oo);
 }
 
 template <bool kBpe>
@@ -462,11 +499,12 @@ __global__ void __launch_bounds__(kSpThreads, 1) sp_tokenize_kernel(const SpLaun
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * kSpWarps + warp;
-  Work ws = make_work(smem + (size_t)warp * work_bytes(kSpWin), kSpWin);
+  const bool want_offsets = p.starts != nullptr;              // offsets ride in the arena workspace only
+  Work ws = make_work(smem + (size_t)warp * work_bytes(kSpWin), kSpWin, false);
   uint8_t* my_arena = p.arena + (size_t)gwarp * p.arena_stride;
-  Work wa = make_work(my_arena, p.arena_cap);
+  Work wa = make_work(my_arena, p.arena_cap, want_offsets);
   ArcScratch scratch;
-  scratch.priv = reinterpret_cast<Arc3*>(my_arena + work_bytes(p.arena_cap));
+  scratch.priv = reinterpret_cast<Arc3*>(my_arena + work_bytes_arena(p.arena_cap));
   scratch.priv_cap = (int64_t)p.arena_cap * kArcsPerSym + 4096;
   scratch.ovf = reinterpret_cast<Arc3*>(p.overflow);
   scratch.ovf_cap = p.overflow_cap;
@@ -483,34 +521,46 @@ __global__ void __launch_bounds__(kSpThreads, 1) sp_tokenize_kernel(const SpLaun
     const int64_t n = hi - lo;
     int result = 0;
     if (n > 0 && n <= 1000000000) {                                      // :1362
-      const int nraw = sp_raw_symbols(m, p.text, lo, hi, padded_bytes, nullptr, false, lane);
+      const int nraw = sp_raw_symbols(m, p.text, lo, hi, padded_bytes, nullptr, nullptr, false, lane);
       bool ok = nraw > 0;
       const int64_t need = (m.norm_count ? 2 * (n + 1) : (int64_t)nraw) + 2;   // staging bound (:1423)
-      const bool fits_smem = need <= kSpWin;
+      const bool fits_smem = !want_offsets && need <= kSpWin;
       if (ok && !fits_smem && need > (int64_t)p.arena_cap) { ok = false; if (lane == 0) atomicExch(error_flag, 2); }
       if (ok) {
         Work& w = fits_smem ? ws : wa;
-        sp_raw_symbols(m, p.text, lo, hi, padded_bytes, w.sym, true, lane);
+        int32_t* boff = w.boff_a; int32_t* boff_other = w.boff_b;           // nullptr unless offsets are wanted
+        sp_raw_symbols(m, p.text, lo, hi, padded_bytes, w.sym, boff, true, lane);
         __syncwarp();
         int N = nraw;
         int32_t* cur = w.sym; int32_t* other = w.tmp;
         if (m.norm_count) {
           const int nn = sp_normalize(m, cur, N, nullptr, lane);
           if (nn <= 0 || (int64_t)nn > 2 * (n + 1)) ok = false;          // :1442-1446
-          else { sp_normalize(m, cur, N, other, lane); __syncwarp(); N = nn; int32_t* t = cur; cur = other; other = t; }
+          else {
+            sp_normalize(m, cur, N, other, lane, boff, boff_other);
+            __syncwarp();
+            N = nn;
+            int32_t* t = cur; cur = other; other = t;
+            t = boff; boff = boff_other; boff_other = t;
+          }
         }
         if (ok) {
-          N = sp_collapse(cur, N, other, lane);
+          N = sp_collapse(cur, N, other, lane, boff, boff_other);
           __syncwarp();
           if (other != w.sym) { for (int i = lane; i < N; i += 32) w.sym[i] = other[i]; __syncwarp(); }
           if (N > 0) {
             int32_t* row = p.ids + doc * (int64_t)p.max_ids;
+            OffsetsOut oo;
+            oo.boff = want_offsets ? boff_other : nullptr;                 // sp_collapse wrote the final offsets there
+            oo.doc = p.text + lo;
+            oo.starts = want_offsets ? p.starts + doc * (int64_t)p.max_ids : nullptr;
+            oo.ends = want_offsets ? p.ends + doc * (int64_t)p.max_ids : nullptr;
             if (kBpe) {
               bool overflow = false;
-              result = sp_bpe(m, w, N, row, p.max_ids, p.unk_id, scratch, lane, &overflow);
+              result = sp_bpe(m, w, N, row, p.max_ids, p.unk_id, scratch, lane, &overflow, oo);
               if (overflow) { result = 0; if (lane == 0) atomicExch(error_flag, 3); }
             } else {
-              result = sp_unigram(m, w, N, row, p.max_ids, p.unk_id, lane);
+              result = sp_unigram(m, w, N, row, p.max_ids, p.unk_id, lane, oo);
             }
           }
         }
@@ -524,7 +574,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sp_tokenize_kernel(const SpLaun
 }  // namespace
 
 int64_t sp_arena_bytes_per_warp(int cap, int) {
-  return align16(work_bytes(cap) + 16ll * ((int64_t)cap * kArcsPerSym + 4096) + 256);
+  return align16(work_bytes_arena(cap) + 16ll * ((int64_t)cap * kArcsPerSym + 4096) + 256);
 }
 
 int64_t sp_overflow_entries(int cap, int max_arc_len) {

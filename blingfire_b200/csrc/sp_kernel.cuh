@@ -34,6 +34,11 @@ struct SpLaunch {
   int64_t text_bytes;
   int32_t* ids;                  // [ndocs][max_ids]
   int32_t* counts;               // [ndocs]
+  // optional (both or neither): byte offsets of the first byte of every token's first character and
+  // of the last byte of its last character, relative to the document start, [ndocs][max_ids].
+  // Offsets ride in the arena workspace: arena_cap must then cover every document of the launch.
+  int32_t* starts;
+  int32_t* ends;
   int max_ids, unk_id;
   unsigned long long* work_counter;
   // per-warp global scratch for documents that do not fit the shared-memory window

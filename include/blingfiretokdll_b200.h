@@ -62,15 +62,19 @@ int TextToIds_wp(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
 int TextToIds_sp(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
                        int32_t* pIdsArr, const int MaxIdsArrLength, const int UnkId);
 
-/* blingfiretokdll.h:83-92 / :49-58, blingfiretokdll.cpp:1563-1609 / :1108-1314.  Same as TextToIds
- * plus, for every id, the byte offsets of the first byte of its first character and of the LAST
- * byte of its last character in the input (UnkId tokens take the offsets of their word).  Entries
- * beyond the returned count stay untouched in all three arrays.  Served for lexer ([wbd]) models;
- * [pos-dict] models return 0 here for now (use TextToIds). */
+/* blingfiretokdll.h:83-92 / :49-58 / :65-74, blingfiretokdll.cpp:1563-1609 / :1108-1314 / :1349-1535.
+ * Same as TextToIds plus, for every id, the byte offsets of the first byte of its first character and
+ * of the LAST byte of its last character in the input (UnkId tokens take the offsets of their word).
+ * Entries beyond the returned count stay untouched in all three arrays.  For [pos-dict] models a token
+ * that consists of the dummy prefix alone has start -1; its end is pinned to -1 (the reference reads
+ * the byte before the input there, blingfiretokdll.cpp:1527). */
 int TextToIdsWithOffsets(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
                          int32_t* pIdsArr, int* pStartOffsets, int* pEndOffsets,
                          const int MaxIdsArrLength, const int UnkId);
 int TextToIdsWithOffsets_wp(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
+                            int32_t* pIdsArr, int* pStartOffsets, int* pEndOffsets,
+                            const int MaxIdsArrLength, const int UnkId);
+int TextToIdsWithOffsets_sp(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
                             int32_t* pIdsArr, int* pStartOffsets, int* pEndOffsets,
                             const int MaxIdsArrLength, const int UnkId);
 

@@ -1,8 +1,11 @@
-"""TextToIdsWithOffsets for lexer models through the C ABI: ids, start offsets and end
-offsets against the golden fixtures (the reference itself) and the oracle."""
+"""TextToIdsWithOffsets through the C ABI, for lexer models (the _wp branch) and
+[pos-dict] models (the _sp branch): ids, start offsets and end offsets against the golden fixtures
+(the reference itself) and the oracle."""
 import base64
+import ctypes
 import json
 import os
+import random
 
 import numpy as np
 import pytest
@@ -22,18 +25,23 @@ def bf():
     return blingfire_b200
 
 
-def test_offsets_vs_golden(bf):
+@pytest.mark.parametrize("name", ["bert_base_tok.bin", "xlm_roberta_base.bin", "gpt2.bin"])
+def test_offsets_vs_golden(bf, name):
     with open(os.path.join(GOLDEN, "golden.json")) as f:
         golden = json.load(f)
-    h = bf.load_model(model_path("bert_base_tok.bin"))
+    h = bf.load_model(model_path(name))
     n_checked = 0
     for c in golden["ids_with_offsets"]:
-        if c["model"] != "bert_base_tok.bin":
+        if c["model"] != name:
             continue
         data = base64.b64decode(c["input"])
         ids, st, en = bf.utf8text_to_ids_with_offsets(h, data, 256, c["unk"], no_padding=True)
         assert len(ids) == c["count"], data[:40]
-        assert ids.astype(np.int64).tolist() == c["ids"] and st.tolist() == c["starts"] and en.tolist() == c["ends"], data[:40]
+        assert ids.astype(np.int64).tolist() == c["ids"] and st.tolist() == c["starts"], data[:40]
+        # a token that is only the dummy prefix has start -1; its end offset is an out-of-bounds read
+        # in the reference (blingfiretokdll.cpp:1527) and is excluded from the comparison
+        keep = [k for k in range(len(ids)) if c["starts"][k] >= 0 or c["ends"][k] == -1]
+        assert [int(en[k]) for k in keep] == [c["ends"][k] for k in keep], data[:40]
         n_checked += 1
     assert n_checked > 30
     bf.free_model(h)
@@ -53,9 +61,52 @@ def test_offsets_vs_oracle(bf, name):
             assert len(ids) == n, d[:40]
             assert (ids.astype(np.int32) == oi[:n]).all() and (st == os_[:n]).all() and (en == oe[:n]).all(), d[:40]
     # untouched tails
-    import ctypes
     L = bf.lib()
     a = np.full(64, -7, np.int32); b = np.full(64, -7, np.int32); c = np.full(64, -7, np.int32)
     n = L.TextToIdsWithOffsets(ctypes.c_void_p(h), b"hello world", 11, a.ctypes.data, b.ctypes.data, c.ctypes.data, 64, 100)
     assert n >= 1 and (a[n:] == -7).all() and (b[n:] == -7).all() and (c[n:] == -7).all()
+    bf.free_model(h)
+
+
+def _sp_docs(seed):
+    rng = random.Random(seed)
+    lines = read_lines("test.multi.txt")[:1500] + read_lines("test.txt")[:1500]
+    docs = rng.sample(lines, 250)
+    docs += [b" ".join(rng.choice(lines) for _ in range(6)) for _ in range(20)]          # beyond the smem window
+    docs += [b"\xef\xbb\xbfbom first", b"abc \xff def", b"a" * 700, b"." * 300, b" ", b"x", b"  lead and trail  ",
+             "ﬁne ＡＢＣ ½ ™ ｶﾞ".encode(), "a b c　d".encode(), "🙂🙂 emoji 👩‍👩‍👧".encode(),
+             b"tab\tnew\nline\r\n", "é combining".encode()]
+    return docs
+
+
+# one model of every [pos-dict] kind: Unigram + charmap, BPE-opt raw bytes, Unigram w/o normalisation,
+# BPE with merges ranks, plain BPE, Unigram 100k
+@pytest.mark.parametrize("name,unk", [("xlm_roberta_base.bin", 3), ("gpt2.bin", 0), ("xlnet_nonorm.bin", 0), ("roberta.bin", 3),
+                                      ("bpe_example.bin", 1), ("laser100k.bin", 1), ("xlnet.bin", 0)])
+def test_sp_offsets_vs_oracle(bf, name, unk):
+    h = bf.load_model(model_path(name))
+    assert bf.lib().BlingFireB200ModelEngine(ctypes.c_void_p(h)) == 3
+    o = Oracle()
+    ho = o.load(model_path(name))
+    for d in _sp_docs(11):
+        for max_ids in (1024, 5):
+            n, oi, os_, oe = o.text_to_ids_with_offsets(ho, d, max_ids, unk)
+            ids, st, en = bf.utf8text_to_ids_with_offsets(h, d, max_ids, unk, no_padding=True)
+            assert len(ids) == n, d[:40]
+            assert (ids.astype(np.int32) == oi[:n]).all(), d[:40]
+            assert (st == os_[:n]).all() and (en == oe[:n]).all(), d[:40]
+            # the ids agree with the offset-less entry point
+            plain = bf.text_to_ids(h, d, max_ids, unk, no_padding=True)
+            assert (plain == ids).all(), d[:40]
+    L = bf.lib()
+    L.TextToIdsWithOffsets_sp.restype = ctypes.c_int
+    L.TextToIdsWithOffsets_sp.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    a = np.full(64, -7, np.int32); b = np.full(64, -7, np.int32); c = np.full(64, -7, np.int32)
+    n = L.TextToIdsWithOffsets_sp(ctypes.c_void_p(h), b"hello world", 11, a.ctypes.data, b.ctypes.data, c.ctypes.data, 64, unk)
+    assert n >= 1 and (a[n:] == -7).all() and (b[n:] == -7).all() and (c[n:] == -7).all()
+    # the _wp spelling refuses a [pos-dict] model, like the reference's dispatch would never route it there
+    L.TextToIdsWithOffsets_wp.restype = ctypes.c_int
+    L.TextToIdsWithOffsets_wp.argtypes = L.TextToIdsWithOffsets_sp.argtypes
+    assert L.TextToIdsWithOffsets_wp(ctypes.c_void_p(h), b"hello world", 11, a.ctypes.data, b.ctypes.data, c.ctypes.data, 64, unk) == 0
     bf.free_model(h)
