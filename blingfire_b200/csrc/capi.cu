@@ -296,13 +296,13 @@ bool launch_segmentation(Model* m, Slot& s, int64_t b0, int64_t b1, int64_t ndoc
                          int32_t* d_starts, int32_t* d_ends, int max_ids, int unk, int* launches) {
   int64_t cap64 = (m->S.has_charmap ? 2 * (max_len + 1) : max_len + 1) + 2;
   const bool is_bpe = m->S.tok_algo == kTokenizeBpe || m->S.tok_algo == kTokenizeBpeOpt || m->S.tok_algo == kTokenizeBpeOptWithMerges;
-  // Unigram keeps everything in the window when the document fits; BPE always keeps its arc
-  // scratch in the arena
-  if (cap64 <= kSpWindow && !is_bpe && !d_starts) cap64 = 16;
+  // the Unigram fast path keeps everything in shared memory when even the worst-case staging fits;
+  // BPE always keeps its arc scratch in the arena
+  if (cap64 <= sp_fast_cap(m->S.tok_algo, m->S.max_arc_len, m->S.use_raw_bytes) && !d_starts) cap64 = 16;
   if (cap64 > (1ll << 28)) { set_error("document too large for the segmentation engine"); return false; }
   const int cap = (int)cap64;
   const int64_t per_warp = sp_arena_bytes_per_warp(cap, m->S.max_arc_len);
-  int warps = sp_preferred_warps();
+  int warps = sp_preferred_warps(m->S.tok_algo);
   const int64_t budget = 6ll << 30;
   if (per_warp * warps > budget) warps = (int)std::max<int64_t>(8, (budget / per_warp) / 8 * 8);
   if (per_warp * warps > (24ll << 30)) { set_error("document too large for the segmentation engine arena"); return false; }

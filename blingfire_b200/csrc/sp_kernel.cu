@@ -494,40 +494,23 @@ __device__ int sp_bpe(const SpModelDev& m, Work& w, int N, int32_t* row, int max
   return sp_emit(w, ids_at, N, row, max_ids, unk, m.id_offset, false, lane, oo);
 }
 
+// One document through the general path: any length (arena), any token length, offsets if wanted.
+// `ws` is the warp's shared-memory workspace (nullptr: none, everything goes to the arena `wa`).
 template <bool kBpe>
-__global__ void __launch_bounds__(kSpThreads, 1) sp_tokenize_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gwarp = blockIdx.x * kSpWarps + warp;
+__device__ int sp_doc_generic(const SpLaunch& p, const SpModelDev& m, Work* ws, Work& wa, const ArcScratch& scratch, int64_t doc,
+                              int64_t lo, int64_t hi, int64_t padded_bytes, int lane, int* error_flag) {
   const bool want_offsets = p.starts != nullptr;              // offsets ride in the arena workspace only
-  Work ws = make_work(smem + (size_t)warp * work_bytes(kSpWin), kSpWin, false);
-  uint8_t* my_arena = p.arena + (size_t)gwarp * p.arena_stride;
-  Work wa = make_work(my_arena, p.arena_cap, want_offsets);
-  ArcScratch scratch;
-  scratch.priv = reinterpret_cast<Arc3*>(my_arena + work_bytes_arena(p.arena_cap));
-  scratch.priv_cap = (int64_t)p.arena_cap * kArcsPerSym + 4096;
-  scratch.ovf = reinterpret_cast<Arc3*>(p.overflow);
-  scratch.ovf_cap = p.overflow_cap;
-  scratch.lock = error_flag + 1;
-  const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
-
-  for (;;) {
-    unsigned long long d64 = 0;
-    if (lane == 0) d64 = atomicAdd(p.work_counter, 1ull);
-    d64 = __shfl_sync(0xffffffffu, d64, 0);
-    if ((int64_t)d64 >= p.ndocs) break;
-    const int64_t doc = (int64_t)d64;
-    const int64_t lo = __ldg(p.offsets + doc), hi = __ldg(p.offsets + doc + 1);
-    const int64_t n = hi - lo;
-    int result = 0;
-    if (n > 0 && n <= 1000000000) {                                      // :1362
+  const int64_t n = hi - lo;
+  int result = 0;
+  {
+    {
       const int nraw = sp_raw_symbols(m, p.text, lo, hi, padded_bytes, nullptr, nullptr, false, lane);
       bool ok = nraw > 0;
       const int64_t need = (m.norm_count ? 2 * (n + 1) : (int64_t)nraw) + 2;   // staging bound (:1423)
-      const bool fits_smem = !want_offsets && need <= kSpWin;
+      const bool fits_smem = ws != nullptr && !want_offsets && need <= kSpWin;
       if (ok && !fits_smem && need > (int64_t)p.arena_cap) { ok = false; if (lane == 0) atomicExch(error_flag, 2); }
       if (ok) {
-        Work& w = fits_smem ? ws : wa;
+        Work& w = fits_smem ? *ws : wa;
         int32_t* boff = w.boff_a; int32_t* boff_other = w.boff_b;           // nullptr unless offsets are wanted
         sp_raw_symbols(m, p.text, lo, hi, padded_bytes, w.sym, boff, true, lane);
         __syncwarp();
@@ -566,6 +549,309 @@ __global__ void __launch_bounds__(kSpThreads, 1) sp_tokenize_kernel(const SpLaun
         }
       }
     }
+  }
+  return result;
+}
+
+__device__ __forceinline__ ArcScratch make_scratch(const SpLaunch& p, uint8_t* my_arena, int* error_flag) {
+  ArcScratch scratch;
+  scratch.priv = reinterpret_cast<Arc3*>(my_arena + work_bytes_arena(p.arena_cap));
+  scratch.priv_cap = (int64_t)p.arena_cap * kArcsPerSym + 4096;
+  scratch.ovf = reinterpret_cast<Arc3*>(p.overflow);
+  scratch.ovf_cap = p.overflow_cap;
+  scratch.lock = error_flag + 1;
+  return scratch;
+}
+
+// BPE family: one document per warp
+__global__ void __launch_bounds__(kSpThreads, 1) sp_bpe_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * kSpWarps + warp;
+  Work ws = make_work(smem + (size_t)warp * work_bytes(kSpWin), kSpWin, false);
+  uint8_t* my_arena = p.arena + (size_t)gwarp * p.arena_stride;
+  Work wa = make_work(my_arena, p.arena_cap, p.starts != nullptr);
+  const ArcScratch scratch = make_scratch(p, my_arena, error_flag);
+  const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
+  for (;;) {
+    unsigned long long d64 = 0;
+    if (lane == 0) d64 = atomicAdd(p.work_counter, 1ull);
+    d64 = __shfl_sync(0xffffffffu, d64, 0);
+    if ((int64_t)d64 >= p.ndocs) break;
+    const int64_t doc = (int64_t)d64;
+    const int64_t lo = __ldg(p.offsets + doc), hi = __ldg(p.offsets + doc + 1);
+    const int64_t n = hi - lo;
+    int result = 0;
+    if (n > 0 && n <= 1000000000)                                         // :1362
+      result = sp_doc_generic<true>(p, m, &ws, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
+    if (lane == 0) p.counts[doc] = result;
+    __syncwarp();
+  }
+}
+
+// =====================================================================================
+// Unigram-LM fast path: documents of up to kUCap symbols with tokens of up to kUMaxLen symbols,
+// entirely in ~8 KB of shared memory per warp (24 warps per SM).  Same arithmetic and the same
+// visiting order as sp_unigram; what changes is where things live:
+//   * one fused pass decodes UTF-8 and applies the charmap, one pass collapses whitespace and
+//     maps code points to alphabet indices (so a walk step is ONE 16-byte gather);
+//   * lanes walk 32 consecutive starts at a time and fetch {id, score} of every arc they find
+//     right there (the I2Info gather overlaps the next step's gather), so the serial relaxation
+//     touches shared memory only;
+//   * a token spans <= 16 symbols, so the best scores live in a 64-entry ring.
+// Anything that does not fit (long documents, more normalised symbols than kUCap, offsets, raw
+// bytes, longer tokens) takes sp_doc_generic in the warp's arena.
+// =====================================================================================
+constexpr int kUWarps = 8;                 // per CTA
+constexpr int kUCtasPerSm = 3;
+constexpr int kUCap = kSpUnigramFastCap;   // symbols
+constexpr int kUMaxLen = 16;               // longest token (symbols) the ring arithmetic covers
+constexpr int kUArcs = 8;                  // arcs per start kept in the tile; more: that start walks again, serially
+constexpr int kUNoBegin = 0xFFFF;
+
+struct UWork {
+  double* ring;        // [64]  best score of position p at ring[p & 63], for the positions in flight
+  int2* arc;           // [32*kUArcs] {id, score bits} of the arcs of the tile's starts
+  int32_t* stage;      // [kUCap] normalised code points; then bid[]: id of the best arc ending at p
+  uint32_t* mark;      // [kUCap/32] bit p: a token starts at p
+  uint16_t* sym;       // [kUCap] alphabet indices after whitespace collapsing
+  uint16_t* begin;     // [kUCap] start of the best arc ending at p
+  uint8_t* arc_len;    // [32*kUArcs] end - start
+};
+constexpr int kUWorkBytes = 8 * 64 + 8 * 32 * kUArcs + 4 * kUCap + 4 * (kUCap / 32) + 2 * kUCap + 2 * kUCap + 32 * kUArcs;
+static_assert(kUWorkBytes % 16 == 0 && kUCap % 32 == 0 && kUCap < kUNoBegin, "workspace layout");
+
+__device__ inline UWork make_uwork(uint8_t* b) {
+  UWork w;
+  w.ring = (double*)b; b += 8 * 64;
+  w.arc = (int2*)b; b += 8 * 32 * kUArcs;
+  w.stage = (int32_t*)b; b += 4 * kUCap;
+  w.mark = (uint32_t*)b; b += 4 * (kUCap / 32);
+  w.sym = (uint16_t*)b; b += 2 * kUCap;
+  w.begin = (uint16_t*)b; b += 2 * kUCap;
+  w.arc_len = b;
+  return w;
+}
+
+constexpr int kUFallback = -2;   // the document does not fit the fast path
+
+__device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
+                               int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane) {
+  const unsigned full = 0xffffffffu;
+  int64_t lo = lo0;
+  if (hi - lo >= 3) {
+    const uint32_t b0 = __ldg(text + lo), b1 = __ldg(text + lo + 1), b2 = __ldg(text + lo + 2);
+    if (b0 == 0xEF && b1 == 0xBB && b2 == 0xBF) lo += 3;      // FAStrUtf8ToArray skips the BOM
+  }
+  if (hi <= lo) return 0;                                      // no symbols (:1409)
+  const int64_t n = hi - lo0;
+  const bool cm = m.norm_count != nullptr;
+  // ---- pass 1: decode + charmap (FANormalize, FAUtils_cl.h:311-369), dummy prefix included (:1372,:1432) ----
+  int total = 0;
+  if (!m.no_dummy_prefix) {
+    const unsigned nc = cm ? (unsigned)__ldg(m.norm_count + kSpDelim) : 0xFFu;
+    if (nc == 0xFFu) { if (lane == 0) w.stage[0] = kSpDelim; total = 1; }
+    else {
+      const uint32_t f = __ldg(m.norm_first + kSpDelim);
+      if (lane == 0) for (unsigned k = 0; k < nc; ++k) w.stage[k] = __ldg(m.norm_values + f + k);
+      total = (int)nc;
+    }
+  }
+  {
+    const uint32_t* text32 = reinterpret_cast<const uint32_t*>(text);
+    unsigned bad = 0, sumlen = 0;
+    for (int64_t bpos = lo; bpos < hi;) {
+      const int64_t bs = bpos & ~(int64_t)3;
+      const int64_t pos0 = bs + lane * 4;
+      uint32_t w0, w1;
+      utf8_load_words(text32, pos0, padded_bytes, &w0, &w1);
+      const Utf8Lane d = utf8_decode_lane(w0, w1, pos0, bpos, hi);
+      bad |= d.bad; sumlen += d.sumlen;
+      unsigned nck[4]; int c = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        nck[k] = 0xFFu;
+        if (d.start_mask & (1u << k)) {
+          if (cm) nck[k] = (unsigned)__ldg(m.norm_count + d.cp[k]);
+          c += nck[k] == 0xFFu ? 1 : (int)nck[k];
+        }
+      }
+      const int incl = warp_incl_scan(c, lane);
+      const int wt = __shfl_sync(full, incl, 31);
+      if (total + wt > kUCap) return kUFallback;
+      int o = total + incl - c;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (d.start_mask & (1u << k)) {
+          if (nck[k] == 0xFFu) w.stage[o++] = (int)d.cp[k];
+          else {
+            const uint32_t f = __ldg(m.norm_first + d.cp[k]);
+            for (unsigned j = 0; j < nck[k]; ++j) w.stage[o++] = __ldg(m.norm_values + f + j);
+          }
+        }
+      }
+      total += wt;
+      bpos = bs + 128;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sumlen += __shfl_xor_sync(full, sumlen, o);
+    if (__any_sync(full, bad != 0) || (int64_t)sumlen != hi - lo) return 0;
+  }
+  if (cm && (total <= 0 || (int64_t)total > 2 * (n + 1))) return 0;      // :1442-1446
+  __syncwarp();
+  // ---- pass 2: whitespace runs -> one U+2581, trailing one dropped (:1462-1496); alphabet indices ----
+  int N = 0, last_c = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int i = base + lane;
+    bool keep = false; int c = 0;
+    if (i < total) {
+      c = w.stage[i];
+      const bool white = sp_is_white(c);
+      if (!white || i == 0) keep = true;
+      else { const int q = w.stage[i - 1]; keep = !sp_is_white(q) && q != kSpDelim; }
+      if (white) c = kSpDelim;
+    }
+    const unsigned bal = __ballot_sync(full, keep);
+    if (keep) w.sym[N + __popc(bal & bf_lanemask_lt())] = (unsigned)c <= 0x10FFFFu ? __ldg(m.sym_of_cp + c) : kNoSym;
+    if (bal) last_c = __shfl_sync(full, c, 31 - __clz(bal));
+    N += __popc(bal);
+  }
+  if (N > 1 && last_c == kSpDelim) --N;
+  if (N <= 0) return 0;
+  __syncwarp();
+  // ---- best path (FATokenSegmentationTools_1best_t.h:174-279) ----
+  int32_t* bid = w.stage;
+  for (int i = lane; i < N; i += 32) { w.begin[i] = kUNoBegin; bid[i] = -1; }
+  for (int i = lane; i < kUCap / 32; i += 32) w.mark[i] = 0;
+  w.ring[lane] = -(double)FLT_MAX; w.ring[lane + 32] = -(double)FLT_MAX;
+  const uint4* da = reinterpret_cast<const uint4*>(m.da);
+  for (int t0 = 0; t0 < N; t0 += 32) {
+    __syncwarp();
+    w.ring[(t0 + kUMaxLen - 1 + lane) & 63] = -(double)FLT_MAX;           // the positions this tile reaches first
+    // phase A: lane l finds the arcs of start t0 + l (:196-224)
+    const int start = t0 + lane;
+    int narc = 0;
+    if (start < N) {
+      uint32_t q = m.root; int sum = 0;
+      const int lim = min(kUMaxLen, N - start);
+      for (int k = 0; k < lim; ++k) {
+        const uint16_t s = w.sym[start + k];
+        if (s == kNoSym) break;
+        const uint4 e = __ldg(da + ((size_t)q + s));
+        if (e.x != q) break;
+        sum += (int)e.z;
+        q = e.y & ~kDaFinalBit;
+        if (e.y & kDaFinalBit) {
+          if (narc < kUArcs) {
+            int id; float sc;
+            sp_info(m, sum, -1, id, sc);
+            w.arc[lane * kUArcs + narc] = make_int2(id, __float_as_int(sc));
+            w.arc_len[lane * kUArcs + narc] = (uint8_t)k;
+          }
+          ++narc;
+        }
+        if (q == 0) break;                                     // a leaf: every further step fails
+      }
+    }
+    __syncwarp();
+    // phase B: relax in start order (ties keep the earlier start); the arcs of one start end at distinct positions
+    const int ns = min(32, N - t0);
+    for (int l = 0; l < ns; ++l) {
+      const int st = t0 + l;
+      const int cnt = __shfl_sync(full, narc, l);
+      const double prev = st > 0 ? w.ring[(st - 1) & 63] : 0.0;
+      if (cnt > kUArcs) {
+        // more arcs than the tile keeps: walk again, relaxing as the reference does (AddArc :118-142)
+        if (lane == 0) {
+          uint32_t q = m.root; int sum = 0;
+          const int lim = min(kUMaxLen, N - st);
+          for (int k = 0; k < lim; ++k) {
+            const uint16_t s = w.sym[st + k];
+            if (s == kNoSym) break;
+            const uint4 e = __ldg(da + ((size_t)q + s));
+            if (e.x != q) break;
+            sum += (int)e.z;
+            q = e.y & ~kDaFinalBit;
+            if (e.y & kDaFinalBit) {
+              int id; float sc;
+              sp_info(m, sum, -1, id, sc);
+              const double cand = (double)sc + prev;
+              const int en = st + k;
+              if (w.ring[en & 63] < cand) { w.ring[en & 63] = cand; w.begin[en] = (uint16_t)st; bid[en] = id; }
+            }
+            if (q == 0) break;
+          }
+        }
+      } else if (cnt > 0) {
+        if (lane < cnt) {                                      // AddArc (:118-142)
+          const int2 a = w.arc[l * kUArcs + lane];
+          const int en = st + w.arc_len[l * kUArcs + lane];
+          const double cand = (double)__int_as_float(a.y) + prev;
+          if (w.ring[en & 63] < cand) { w.ring[en & 63] = cand; w.begin[en] = (uint16_t)st; bid[en] = a.x; }
+        }
+      } else if (lane == 0) {                                  // AddUnknownArc (:145-171)
+        const double cand = (double)(-100000.0f) + prev;
+        if (w.ring[st & 63] < cand) {
+          w.ring[st & 63] = cand; bid[st] = -1;
+          w.begin[st] = (st > 0 && bid[st - 1] == -1) ? w.begin[st - 1] : (uint16_t)st;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // ---- back-trace (:227-257): mark token starts, move each token's id to its start slot ----
+  if (lane == 0) {
+    int end = N - 1;
+    while (end >= 0) {
+      const int b = w.begin[end];
+      const int id = bid[end];
+      if (b == kUNoBegin) { w.mark[0] |= 1u; bid[0] = id; break; }   // never-set arc: the reference emits it first and stops
+      w.mark[b >> 5] |= 1u << (b & 31);
+      bid[b] = id;                                             // positions at or before b are not read again as ends
+      end = b - 1;
+    }
+  }
+  __syncwarp();
+  int out = 0;
+  for (int p0 = 0; p0 < N && out < max_ids; p0 += 32) {
+    const uint32_t word = w.mark[p0 >> 5];
+    const int rank = out + __popc(word & bf_lanemask_lt());
+    if (((word >> lane) & 1u) && rank < max_ids) {
+      int id = bid[p0 + lane];
+      if (id == -1) id = unk;
+      row[rank] = id + m.id_offset;                            // ids[k] = id + IdOffset, UNK included (:1516)
+    }
+    out += __popc(word);
+  }
+  return out < max_ids ? out : max_ids;
+}
+
+__global__ void __launch_bounds__(kUWarps * 32, kUCtasPerSm) sp_unigram_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * kUWarps + warp;
+  const UWork w = make_uwork(smem + (size_t)warp * kUWorkBytes);
+  uint8_t* my_arena = p.arena + (size_t)gwarp * p.arena_stride;
+  Work wa = make_work(my_arena, p.arena_cap, p.starts != nullptr);
+  const ArcScratch scratch = make_scratch(p, my_arena, error_flag);
+  const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
+  const bool fast_model = p.starts == nullptr && !m.use_raw_bytes && m.max_arc_len <= kUMaxLen;
+  for (;;) {
+    unsigned long long d64 = 0;
+    if (lane == 0) d64 = atomicAdd(p.work_counter, 1ull);
+    d64 = __shfl_sync(0xffffffffu, d64, 0);
+    if ((int64_t)d64 >= p.ndocs) break;
+    const int64_t doc = (int64_t)d64;
+    const int64_t lo = __ldg(p.offsets + doc), hi = __ldg(p.offsets + doc + 1);
+    const int64_t n = hi - lo;
+    int result = 0;
+    if (n > 0 && n <= 1000000000) {                                       // :1362
+      result = kUFallback;
+      if (fast_model && n <= 4ll * kUCap)                                 // a code point takes at most 4 bytes
+        result = sp_unigram_fast(m, w, p.text, lo, hi, padded_bytes, p.ids + doc * (int64_t)p.max_ids, p.max_ids, p.unk_id, lane);
+      if (result == kUFallback)
+        result = sp_doc_generic<false>(p, m, nullptr, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
+    }
     if (lane == 0) p.counts[doc] = result;
     __syncwarp();
   }
@@ -586,28 +872,37 @@ int64_t sp_overflow_entries(int cap, int max_arc_len) {
   return need < limit ? need : limit;
 }
 
-int sp_preferred_warps() {
+static bool is_bpe_algo(int tok_algo) {
+  return tok_algo == kTokenizeBpe || tok_algo == kTokenizeBpeOpt || tok_algo == kTokenizeBpeOptWithMerges;
+}
+
+int sp_preferred_warps(int tok_algo) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms * kSpWarps;
+  return is_bpe_algo(tok_algo) ? sms * kSpWarps : sms * kUWarps * kUCtasPerSm;
+}
+
+int sp_fast_cap(int tok_algo, int max_arc_len, bool use_raw_bytes) {
+  return (!is_bpe_algo(tok_algo) && !use_raw_bytes && max_arc_len <= kUMaxLen) ? kUCap : 0;
 }
 
 cudaError_t sp_tokenize_launch(const SpLaunch& p, const SpModelDev& m, cudaStream_t stream, int* launches) {
   if (p.ndocs <= 0) return cudaSuccess;
-  const bool bpe = m.tok_algo == kTokenizeBpe || m.tok_algo == kTokenizeBpeOpt || m.tok_algo == kTokenizeBpeOptWithMerges;
-  const size_t smem = (size_t)kSpWarps * work_bytes(kSpWin);
-  auto kern = bpe ? sp_tokenize_kernel<true> : sp_tokenize_kernel<false>;
+  const bool bpe = is_bpe_algo(m.tok_algo);
+  const int cta_warps = bpe ? kSpWarps : kUWarps;
+  const size_t smem = bpe ? (size_t)kSpWarps * work_bytes(kSpWin) : (size_t)kUWarps * kUWorkBytes;
+  auto kern = bpe ? sp_bpe_kernel : sp_unigram_kernel;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  int grid = p.grid_warps / kSpWarps;
+  int grid = p.grid_warps / cta_warps;
   if (grid < 1) return cudaErrorInvalidValue;
-  const int64_t needed = (p.ndocs + kSpWarps - 1) / kSpWarps;
+  const int64_t needed = (p.ndocs + cta_warps - 1) / cta_warps;
   if (needed < grid) grid = (int)needed;
   e = cudaMemsetAsync(p.work_counter, 0, 16, stream);   // counter (8 B) + error flag (4 B)
   if (e != cudaSuccess) return e;
   int* err = reinterpret_cast<int*>(p.work_counter + 1);
-  kern<<<grid, kSpThreads, smem, stream>>>(p, m, err);
+  kern<<<grid, cta_warps * 32, smem, stream>>>(p, m, err);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
