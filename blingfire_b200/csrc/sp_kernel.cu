@@ -598,38 +598,37 @@ __global__ void __launch_bounds__(kSpThreads, 1) sp_bpe_kernel(const SpLaunch p,
 //   * lanes walk 32 consecutive starts at a time and fetch {id, score} of every arc they find
 //     right there (the I2Info gather overlaps the next step's gather), so the serial relaxation
 //     touches shared memory only;
-//   * a token spans <= 16 symbols, so the best scores live in a 64-entry ring.
+//   * a token spans <= 16 symbols, so the relaxation keeps the scores in REGISTERS: during a
+//     half-tile of 16 starts lane j owns position t0-1+j (lane 0: the finished position before the
+//     half-tile, lanes 1..31: everything its starts can reach).  Start st's turn: every lane takes
+//     score[st-1] by shuffle, the lane whose position is st+k looks up arc (st, k) in the tile and
+//     relaxes its own registers.  No shared-memory traffic but the arc fetch, no barriers.
 // Anything that does not fit (long documents, more normalised symbols than kUCap, offsets, raw
 // bytes, longer tokens) takes sp_doc_generic in the warp's arena.
 // =====================================================================================
 constexpr int kUWarps = 8;                 // per CTA
 constexpr int kUCtasPerSm = 3;
 constexpr int kUCap = kSpUnigramFastCap;   // symbols
-constexpr int kUMaxLen = 16;               // longest token (symbols) the ring arithmetic covers
-constexpr int kUArcs = 8;                  // arcs per start kept in the tile; more: that start walks again, serially
+constexpr int kUMaxLen = 16;               // longest token (symbols): lanes 1..31 cover 16 starts + 15 more positions
 constexpr int kUNoBegin = 0xFFFF;
 
 struct UWork {
-  double* ring;        // [64]  best score of position p at ring[p & 63], for the positions in flight
-  int2* arc;           // [32*kUArcs] {id, score bits} of the arcs of the tile's starts
+  int2* arc;           // [32][kUMaxLen] {id, score bits} of arc (start, length-1) for the tile's 32 starts
   int32_t* stage;      // [kUCap] normalised code points; then bid[]: id of the best arc ending at p
   uint32_t* mark;      // [kUCap/32] bit p: a token starts at p
   uint16_t* sym;       // [kUCap] alphabet indices after whitespace collapsing
   uint16_t* begin;     // [kUCap] start of the best arc ending at p
-  uint8_t* arc_len;    // [32*kUArcs] end - start
 };
-constexpr int kUWorkBytes = 8 * 64 + 8 * 32 * kUArcs + 4 * kUCap + 4 * (kUCap / 32) + 2 * kUCap + 2 * kUCap + 32 * kUArcs;
-static_assert(kUWorkBytes % 16 == 0 && kUCap % 32 == 0 && kUCap < kUNoBegin, "workspace layout");
+constexpr int kUWorkBytes = 8 * 32 * kUMaxLen + 4 * kUCap + 4 * (kUCap / 32) + 2 * kUCap + 2 * kUCap;
+static_assert(kUWorkBytes % 8 == 0 && kUCap % 32 == 0 && kUCap < kUNoBegin, "workspace layout");
 
 __device__ inline UWork make_uwork(uint8_t* b) {
   UWork w;
-  w.ring = (double*)b; b += 8 * 64;
-  w.arc = (int2*)b; b += 8 * 32 * kUArcs;
+  w.arc = (int2*)b; b += 8 * 32 * kUMaxLen;
   w.stage = (int32_t*)b; b += 4 * kUCap;
   w.mark = (uint32_t*)b; b += 4 * (kUCap / 32);
   w.sym = (uint16_t*)b; b += 2 * kUCap;
-  w.begin = (uint16_t*)b; b += 2 * kUCap;
-  w.arc_len = b;
+  w.begin = (uint16_t*)b;
   return w;
 }
 
@@ -721,16 +720,16 @@ __device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_
   __syncwarp();
   // ---- best path (FATokenSegmentationTools_1best_t.h:174-279) ----
   int32_t* bid = w.stage;
-  for (int i = lane; i < N; i += 32) { w.begin[i] = kUNoBegin; bid[i] = -1; }
   for (int i = lane; i < kUCap / 32; i += 32) w.mark[i] = 0;
-  w.ring[lane] = -(double)FLT_MAX; w.ring[lane + 32] = -(double)FLT_MAX;
   const uint4* da = reinterpret_cast<const uint4*>(m.da);
-  for (int t0 = 0; t0 < N; t0 += 32) {
-    __syncwarp();
-    w.ring[(t0 + kUMaxLen - 1 + lane) & 63] = -(double)FLT_MAX;           // the positions this tile reaches first
-    // phase A: lane l finds the arcs of start t0 + l (:196-224)
-    const int start = t0 + lane;
-    int narc = 0;
+  // lane j owns position t0-1+j: best score, start and id of the best arc ending there
+  double sc = lane == 0 ? 0.0 : -(double)FLT_MAX;            // "position -1": the empty prefix
+  int bg = kUNoBegin, bi = lane == 0 ? 0 : -1;
+  for (int tA = 0; tA < N; tA += 32) {
+    __syncwarp();                                              // the previous tile's arcs have been consumed
+    // phase A: lane l finds the arcs of start tA + l (:196-224): bit k of amask = an arc of k+1 symbols
+    const int start = tA + lane;
+    unsigned amask = 0;
     if (start < N) {
       uint32_t q = m.root; int sum = 0;
       const int lim = min(kUMaxLen, N - start);
@@ -742,63 +741,48 @@ __device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_
         sum += (int)e.z;
         q = e.y & ~kDaFinalBit;
         if (e.y & kDaFinalBit) {
-          if (narc < kUArcs) {
-            int id; float sc;
-            sp_info(m, sum, -1, id, sc);
-            w.arc[lane * kUArcs + narc] = make_int2(id, __float_as_int(sc));
-            w.arc_len[lane * kUArcs + narc] = (uint8_t)k;
-          }
-          ++narc;
+          int id; float score;
+          sp_info(m, sum, -1, id, score);
+          w.arc[lane * kUMaxLen + k] = make_int2(id, __float_as_int(score));
+          amask |= 1u << k;
         }
         if (q == 0) break;                                     // a leaf: every further step fails
       }
     }
     __syncwarp();
-    // phase B: relax in start order (ties keep the earlier start); the arcs of one start end at distinct positions
-    const int ns = min(32, N - t0);
-    for (int l = 0; l < ns; ++l) {
-      const int st = t0 + l;
-      const int cnt = __shfl_sync(full, narc, l);
-      const double prev = st > 0 ? w.ring[(st - 1) & 63] : 0.0;
-      if (cnt > kUArcs) {
-        // more arcs than the tile keeps: walk again, relaxing as the reference does (AddArc :118-142)
-        if (lane == 0) {
-          uint32_t q = m.root; int sum = 0;
-          const int lim = min(kUMaxLen, N - st);
-          for (int k = 0; k < lim; ++k) {
-            const uint16_t s = w.sym[st + k];
-            if (s == kNoSym) break;
-            const uint4 e = __ldg(da + ((size_t)q + s));
-            if (e.x != q) break;
-            sum += (int)e.z;
-            q = e.y & ~kDaFinalBit;
-            if (e.y & kDaFinalBit) {
-              int id; float sc;
-              sp_info(m, sum, -1, id, sc);
-              const double cand = (double)sc + prev;
-              const int en = st + k;
-              if (w.ring[en & 63] < cand) { w.ring[en & 63] = cand; w.begin[en] = (uint16_t)st; bid[en] = id; }
-            }
-            if (q == 0) break;
+    // phase B: relax in start order (ties keep the earlier start), 16 starts per register window
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int t0 = tA + 16 * h;
+      if (t0 >= N) break;
+#pragma unroll
+      for (int l = 0; l < 16; ++l) {
+        const int st = t0 + l;
+        if (st >= N) break;
+        const unsigned M = __shfl_sync(full, amask, 16 * h + l);
+        const double prev = __shfl_sync(full, sc, l);          // score[st-1], final by now
+        if (M != 0) {                                          // AddArc (:118-142)
+          const int k = lane - 1 - l;
+          if ((unsigned)k < (unsigned)kUMaxLen && ((M >> k) & 1u)) {
+            const int2 a = w.arc[(16 * h + l) * kUMaxLen + k];
+            const double cand = (double)__int_as_float(a.y) + prev;
+            if (sc < cand) { sc = cand; bg = st; bi = a.x; }
+          }
+        } else {                                               // AddUnknownArc (:145-171)
+          const int pid = __shfl_sync(full, bi, l), pbg = __shfl_sync(full, bg, l);
+          if (lane == l + 1) {
+            const double cand = (double)(-100000.0f) + prev;
+            if (sc < cand) { sc = cand; bi = -1; bg = (st > 0 && pid == -1) ? pbg : st; }
           }
         }
-      } else if (cnt > 0) {
-        if (lane < cnt) {                                      // AddArc (:118-142)
-          const int2 a = w.arc[l * kUArcs + lane];
-          const int en = st + w.arc_len[l * kUArcs + lane];
-          const double cand = (double)__int_as_float(a.y) + prev;
-          if (w.ring[en & 63] < cand) { w.ring[en & 63] = cand; w.begin[en] = (uint16_t)st; bid[en] = a.x; }
-        }
-      } else if (lane == 0) {                                  // AddUnknownArc (:145-171)
-        const double cand = (double)(-100000.0f) + prev;
-        if (w.ring[st & 63] < cand) {
-          w.ring[st & 63] = cand; bid[st] = -1;
-          w.begin[st] = (st > 0 && bid[st - 1] == -1) ? w.begin[st - 1] : (uint16_t)st;
-        }
       }
-      __syncwarp();
+      // positions t0 .. t0+15 (lanes 1..16) are final: park them for the back-trace, slide the window
+      if (lane >= 1 && lane <= 16 && t0 - 1 + lane < N) { w.begin[t0 - 1 + lane] = (uint16_t)bg; bid[t0 - 1 + lane] = bi; }
+      sc = __shfl_down_sync(full, sc, 16); bg = __shfl_down_sync(full, bg, 16); bi = __shfl_down_sync(full, bi, 16);
+      if (lane >= 16) { sc = -(double)FLT_MAX; bg = kUNoBegin; bi = -1; }
     }
   }
+  __syncwarp();
   // ---- back-trace (:227-257): mark token starts, move each token's id to its start slot ----
   if (lane == 0) {
     int end = N - 1;

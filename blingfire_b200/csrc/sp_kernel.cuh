@@ -61,7 +61,7 @@ int64_t sp_arena_bytes_per_warp(int cap, int max_arc_len);
 int sp_preferred_warps(int tok_algo);
 // symbols (after the charmap) a document may have and still be served without the arena: the
 // Unigram fast path's shared-memory capacity; 0 for the models that always use the arena
-constexpr int kSpUnigramFastCap = 640;
+constexpr int kSpUnigramFastCap = 576;
 int sp_fast_cap(int tok_algo, int max_arc_len, bool use_raw_bytes);
 
 cudaError_t sp_tokenize_launch(const SpLaunch& p, const SpModelDev& m, cudaStream_t stream, int* launches);

@@ -37,7 +37,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--docs", type=int, default=500_000)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--only", default="", help="comma-separated configuration names (default: all)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the reference CPU timing")
     args = ap.parse_args()
+    only = set(x for x in args.only.split(",") if x)
     import torch
     import blingfire_b200 as bf
     import corpus
@@ -50,21 +53,24 @@ def main():
     out = {"cores": cores}
 
     # cfg 1: default TextToWords on 10k short ASCII lines (per-call API)
-    lines = [l for l in read_lines("test.txt") if len(l) <= 120 and all(c < 128 for c in l)][:10000]
-    buf = ctypes.create_string_buffer(1024)
-    L.TextToWords(lines[0], len(lines[0]), buf, 1024)
-    t0 = time.perf_counter()
-    for l in lines:
-        L.TextToWords(l, len(l), buf, 1024)
-    dt = time.perf_counter() - t0
-    nb = sum(len(l) for l in lines)
-    out["cfg1_TextToWords_10k_lines"] = {"MB_per_s": nb / dt / 1e6, "us_per_call": dt / len(lines) * 1e6, "bytes": nb}
+    if not only or "cfg1" in only:
+        lines = [l for l in read_lines("test.txt") if len(l) <= 120 and all(c < 128 for c in l)][:10000]
+        buf = ctypes.create_string_buffer(1024)
+        L.TextToWords(lines[0], len(lines[0]), buf, 1024)
+        t0 = time.perf_counter()
+        for l in lines:
+            L.TextToWords(l, len(l), buf, 1024)
+        dt = time.perf_counter() - t0
+        nb = sum(len(l) for l in lines)
+        out["cfg1_TextToWords_10k_lines"] = {"MB_per_s": nb / dt / 1e6, "us_per_call": dt / len(lines) * 1e6, "bytes": nb}
 
     for name, model, unk, max_ids, gen in [
         ("cfg3_gpt2", "gpt2.bin", 0, 4096, lambda n: corpus.gen_docs("EN", n, seed=3, fixed_len=0)),
         ("cfg4_xlmr", "xlm_roberta_base.bin", 3, 512, lambda n: corpus.gen_docs("MULTI", n, seed=4, fixed_len=512, emoji_every=16)),
         ("cfg2_bert_same_path", "bert_base_tok.bin", 100, 512, lambda n: corpus.gen_docs("EN", n, seed=2, fixed_len=512)),
     ]:
+        if only and name not in only:
+            continue
         text, offs = gen(args.docs)
         n, nbytes = len(offs) - 1, int(offs[-1])
         h_text = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True)
@@ -90,7 +96,7 @@ def main():
             if dt < best:
                 best, kms = dt, L.BlingFireB200LastKernelMs()
         ns = min(n, 50000)
-        cpu_gbs, cpu_tps = ref_cpu(model_path(model), text, offs, ns, max_ids, unk, cores)
+        cpu_gbs, cpu_tps = (None, None) if args.no_cpu else ref_cpu(model_path(model), text, offs, ns, max_ids, unk, cores)
         out[name] = {"docs": n, "bytes": nbytes, "tokens": int(tot), "e2e_GB_per_s": nbytes / best / 1e9,
                      "e2e_ms": best * 1e3, "kernel_ms": kms, "kernel_GB_per_s": nbytes / (kms * 1e-3) / 1e9 if kms > 0 else None,
                      "tokens_per_s_kernel": tot / (kms * 1e-3) if kms > 0 else None,
