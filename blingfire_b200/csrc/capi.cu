@@ -138,6 +138,8 @@ struct Model {
   uint8_t* d_norm_count = nullptr;
   uint32_t* d_norm_first = nullptr;
   int32_t* d_norm_values = nullptr;
+  int32_t* d_bpe_ord = nullptr;
+  int32_t* d_bpe_id_of_ord = nullptr;
   std::mutex mu;               // serialises the host-pointer entry points of this handle
   Slot slots[kSlots];
   DevBuf<unsigned long long> dev_counter;   // for the device-pointer entry point
@@ -161,6 +163,8 @@ struct Model {
     if (d_norm_count) cudaFree(d_norm_count);
     if (d_norm_first) cudaFree(d_norm_first);
     if (d_norm_values) cudaFree(d_norm_values);
+    if (d_bpe_ord) cudaFree(d_bpe_ord);
+    if (d_bpe_id_of_ord) cudaFree(d_bpe_id_of_ord);
     h_words.release();
   }
 };
@@ -220,6 +224,10 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
       if (!upload(&m->d_norm_first, S.norm_first.data(), S.norm_first.size())) return nullptr;
       if (!upload(&m->d_norm_values, S.norm_values.data(), S.norm_values.size(), 16)) return nullptr;
     }
+    if (S.bpe_ord_ok) {
+      if (!upload(&m->d_bpe_ord, S.bpe_ord.data(), S.bpe_ord.size(), 1)) return nullptr;
+      if (!upload(&m->d_bpe_id_of_ord, S.bpe_id_of_ord.data(), S.bpe_id_of_ord.size(), 1)) return nullptr;
+    }
     m->engine = 3;
   }
   return m.release();
@@ -232,6 +240,7 @@ SpModelDev make_sp_model(const Model* m) {
   d.norm_count = S.has_charmap ? m->d_norm_count : nullptr; d.norm_first = m->d_norm_first; d.norm_values = m->d_norm_values;
   d.tok_algo = S.tok_algo; d.id_offset = S.id_offset; d.use_raw_bytes = S.use_raw_bytes; d.no_dummy_prefix = S.no_dummy_prefix;
   d.delim_inside_tokens = S.delim_inside_tokens; d.max_arc_len = S.max_arc_len;
+  d.bpe_ord = S.bpe_ord_ok ? m->d_bpe_ord : nullptr; d.bpe_id_of_ord = m->d_bpe_id_of_ord;
   return d;
 }
 

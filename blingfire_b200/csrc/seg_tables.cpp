@@ -194,6 +194,38 @@ bool build_seg_tables(const LdbImage& ldb, SegTables* T, std::string* err) {
     if (!LdbImage::parse_fixedmap(ldb.dump(charmap_dump), &cm, err)) return false;
     flatten_charmap(cm, &T->norm_count, &T->norm_first, &T->norm_values);
   }
+
+  // ---- BPE: the arc order as one integer ----
+  // The BPE family sorts a segment's arcs by (rank descending -- with-merges only), id, start
+  // (FATokenSegmentationTools_1best_bpe_t.h:238-255, ..._with_merges_t.h:242-262).  rank is a function
+  // of the key, so (rank, id) collapses into a dense per-key ordinal and a sort key is one integer.
+  T->bpe_ord.clear(); T->bpe_id_of_ord.clear(); T->bpe_ord_ok = false;
+  const bool bpe = T->tok_algo == kTokenizeBpe || T->tok_algo == kTokenizeBpeOpt || T->tok_algo == kTokenizeBpeOptWithMerges;
+  if (bpe && !T->info.empty()) {
+    const bool merges = T->tok_algo == kTokenizeBpeOptWithMerges;
+    const size_t n = T->info.size();
+    std::vector<int> order; order.reserve(n);
+    bool ok = true;
+    for (size_t k = 0; k < n; ++k) {
+      if (T->info[k].id == INT32_MIN) continue;              // unusable row: never an arc of a valid model
+      if (T->info[k].score != T->info[k].score) ok = false;  // a NaN rank has no place in an order
+      order.push_back((int)k);
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+      const SegInfo& x = T->info[a]; const SegInfo& y = T->info[b];
+      if (merges) { if (x.score > y.score) return true; if (x.score < y.score) return false; }
+      return x.id < y.id;
+    });
+    T->bpe_ord.assign(n, -1);
+    int ord = -1;
+    for (size_t i = 0; i < order.size(); ++i) {
+      const SegInfo& x = T->info[order[i]];
+      const bool same = i > 0 && T->info[order[i - 1]].id == x.id && (!merges || T->info[order[i - 1]].score == x.score);
+      if (!same) { ++ord; T->bpe_id_of_ord.push_back(x.id); }
+      T->bpe_ord[order[i]] = ord;
+    }
+    T->bpe_ord_ok = ok && ord < (1 << 20) - 1;               // 20 bits in a sort key, all-ones reserved
+  }
   return true;
 }
 

@@ -54,6 +54,12 @@ struct SegTables {
   int max_arc_len = 0;                  // longest path from the root (symbols)
   bool delim_inside_tokens = false;     // some token has U+2581 past its first symbol
 
+  // BPE family: dense ordinal of a key in the arc sort order (rank descending for with-merges,
+  // then id); -1 for an unusable row.  bpe_id_of_ord inverts it.  bpe_ord_ok: ordinals fit 20 bits.
+  std::vector<int32_t> bpe_ord;         // [max_key+1]
+  std::vector<int32_t> bpe_id_of_ord;
+  bool bpe_ord_ok = false;
+
   std::vector<uint8_t> norm_count;      // [0x110000] 0..10, 0xFF = unmapped (keep code point)
   std::vector<uint32_t> norm_first;     // [0x110000]
   std::vector<int32_t> norm_values;

@@ -26,8 +26,6 @@ namespace bfb200 {
 
 namespace {
 
-constexpr int kSpWarps = 8;
-constexpr int kSpThreads = kSpWarps * 32;
 constexpr int kSpWin = kSpWindow;         // symbols in the shared-memory window
 constexpr int kTileArcs = 1024;           // arc slots of one tile of start positions (Unigram)
 constexpr int kArcsPerSym = 8;            // warp-private BPE arc scratch, per symbol of capacity
@@ -563,16 +561,360 @@ __device__ __forceinline__ ArcScratch make_scratch(const SpLaunch& p, uint8_t* m
   return scratch;
 }
 
+constexpr int kUFallback = -2;   // the document does not fit a fast path: the caller takes sp_doc_generic
+
+// =====================================================================================
+// BPE streaming fast path (byte-level models: gpt2, roberta).  Tokens never contain U+2581 past
+// their first symbol, so the U+2581-delimited segments (words) are independent, and the document
+// never has to be resident: a 512-symbol window slides over it, cut at the last U+2581.
+//   front end   128 bytes per step: whitespace -> U+2581, runs collapsed, alphabet indices
+//   easy pass   one lane per segment: the bpe-opt whole-word shortcut (:188-206)
+//   hard pass   one lane per remaining segment (<= 64 symbols, <= 64 arcs): arcs are inserted into a
+//               lane-private sorted list as they are found -- the sort key (ordinal of (rank, id),
+//               start, end) is ONE 32-bit integer (seg_tables.h) -- then the reference's greedy
+//               claim (:264-296) with the intermediate[] marks in a 64-bit register
+//   coop        bigger segments (<= 1024 arcs): the warp together, bitonic sort in shared memory
+// A segment longer than the window, more arcs than that, or a symbol outside the alphabet sends the
+// whole document to sp_doc_generic.
+// =====================================================================================
+constexpr int kBWarps = 8;                 // per CTA
+constexpr int kBCtasPerSm = 2;
+constexpr int kBWin = 512;                 // symbols in the window
+constexpr int kBLaneArcs = 64;             // lane-serial segments: at most this many arcs, and symbols
+constexpr int kBCoopArcs = 1024;           // warp-cooperative segments: arcs (64-bit keys, same scratch)
+constexpr unsigned kBUnclaimed = 0xFFFFFu; // ordinal of "no arc claimed from this start"
+
+struct BWork {
+  uint32_t* scratch;    // [32][kBLaneArcs] lane-interleaved sorted keys; or kBCoopArcs 64-bit keys
+  int32_t* ids_at;      // [kBWin] claim state {ordinal, tos}, then the token id, at token starts
+  uint32_t* mark;       // [kBWin/32] bit p: a token starts at p
+  uint16_t* sym;        // [kBWin] alphabet indices
+  uint16_t* seg;        // [kBWin/2+8] segment starts, window-relative, and the end sentinel
+  uint16_t* hard;       // [kBWin/2+8] segments the easy pass left
+};
+constexpr int kBWorkBytes = 4 * 32 * kBLaneArcs + 4 * kBWin + 4 * (kBWin / 32) + 2 * kBWin + 4 * (kBWin / 2 + 8);
+static_assert(kBWorkBytes % 16 == 0 && 8 * kBCoopArcs <= 4 * 32 * kBLaneArcs && kBLaneArcs <= 64 && kBWin <= 1024, "workspace layout");
+
+__device__ inline BWork make_bwork(uint8_t* b) {
+  BWork w;
+  w.scratch = (uint32_t*)b; b += 4 * 32 * kBLaneArcs;
+  w.ids_at = (int32_t*)b; b += 4 * kBWin;
+  w.mark = (uint32_t*)b; b += 4 * (kBWin / 32);
+  w.sym = (uint16_t*)b; b += 2 * kBWin;
+  w.seg = (uint16_t*)b; b += 2 * (kBWin / 2 + 8);
+  w.hard = (uint16_t*)b;
+  return w;
+}
+
+// GetDestOw on alphabet indices
+__device__ __forceinline__ bool b_step(const uint4* da, uint32_t& q, uint16_t s, int& sum, bool& fin) {
+  if (s == kNoSym) return false;
+  const uint4 e = __ldg(da + ((size_t)q + s));
+  if (e.x != q) return false;
+  sum += (int)e.z; fin = (e.y & kDaFinalBit) != 0; q = e.y & ~kDaFinalBit;
+  return true;
+}
+
+__device__ __forceinline__ int b_ord(const SpModelDev& m, int key) {
+  return (key >= 0 && key < m.info_count) ? __ldg(m.bpe_ord + key) : -1;
+}
+
+// One segment [a, b) of the window, the warp together.  false: it does not fit (general path).
+__device__ bool bpe_coop(const SpModelDev& m, const BWork& w, int a, int b, int unk, int lane) {
+  const unsigned full = 0xffffffffu;
+  const uint4* da = reinterpret_cast<const uint4*>(m.da);
+  const int L = b - a;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(w.scratch);
+  // arcs of every start, grouped by start (count -> scan -> write)
+  int total = 0; bool bad = false;
+  for (int s0 = 0; s0 < L; s0 += 32) {
+    const int s = s0 + lane; int cnt = 0;
+    if (s < L) {
+      uint32_t q = m.root; int sum = 0;
+      for (int i = a + s; i < b; ++i) { bool fin; if (!b_step(da, q, w.sym[i], sum, fin)) break; if (fin) ++cnt; if (q == 0) break; }
+      if (cnt == 0) bad = true;                                // an unknown symbol run (:208-227)
+    }
+    const int incl = warp_incl_scan(cnt, lane);
+    if (s < L) w.ids_at[a + s] = total + incl - cnt;
+    total += __shfl_sync(full, incl, 31);
+  }
+  if (__any_sync(full, bad) || total > kBCoopArcs) return false;
+  __syncwarp();
+  for (int s0 = 0; s0 < L; s0 += 32) {
+    const int s = s0 + lane;
+    if (s < L) {
+      int wr = w.ids_at[a + s];
+      uint32_t q = m.root; int sum = 0;
+      for (int i = a + s; i < b; ++i) {
+        bool fin;
+        if (!b_step(da, q, w.sym[i], sum, fin)) break;
+        if (fin) {
+          const int ord = b_ord(m, sum);
+          if (ord < 0) bad = true;
+          keys[wr++] = ((unsigned long long)(unsigned)ord << 20) | ((unsigned long long)s << 10) | (unsigned long long)(i - a);
+        }
+        if (q == 0) break;
+      }
+    }
+  }
+  if (__any_sync(full, bad)) return false;
+  int P = 1; while (P < total) P <<= 1;
+  for (int i = total + lane; i < P; i += 32) keys[i] = ~0ull;
+  __syncwarp();
+  for (int k = 2; k <= P; k <<= 1) {                           // (:238-262) as a bitonic network
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += 32) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long x = keys[i], y = keys[l];
+          const bool up = (i & k) == 0;
+          if (up ? (y < x) : (x < y)) { keys[i] = y; keys[l] = x; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < L; i += 32) w.ids_at[a + i] = (int)((kBUnclaimed << 10) | (unsigned)i);
+  __syncwarp();
+  // greedy claim in sorted order (:264-296); lane i keeps bits 32i..32i+31 of intermediate[]
+  unsigned inter = 0;
+  for (int k = 0; k < total; ++k) {
+    const unsigned long long key = keys[k];
+    const int st = (int)(key >> 10) & 1023, en = (int)key & 1023;
+    const unsigned ws = __shfl_sync(full, inter, st >> 5), we = __shfl_sync(full, inter, ((en + 1) >> 5) & 31);
+    const bool end_free = (en + 1 >= L) || ((we >> ((en + 1) & 31)) & 1u) == 0;
+    if (((ws >> (st & 31)) & 1u) == 0 && end_free) {
+      if (lane == 0) w.ids_at[a + st] = (int)(((unsigned)(key >> 20) << 10) | (unsigned)en);
+      const int lo = max(st + 1, lane * 32), hi = min(en, lane * 32 + 31);
+      if (lo <= hi) inter |= ((2u << (hi & 31)) - 1u) & ~((1u << (lo & 31)) - 1u);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {                                             // tokens: follow tos[] (:299-313)
+    for (int s = 0; s < L;) {
+      const unsigned v = (unsigned)w.ids_at[a + s];
+      const unsigned ord = v >> 10;
+      w.ids_at[a + s] = ord == kBUnclaimed ? unk : __ldg(m.bpe_id_of_ord + ord);
+      w.mark[(a + s) >> 5] |= 1u << ((a + s) & 31);
+      s = (int)(v & 1023u) + 1;
+    }
+  }
+  __syncwarp();
+  return true;
+}
+
+// The segments of sym[0..cut): tokens appended to row[out..).  Returns the new out (it may pass
+// max_ids; nothing is written past it) or kUFallback.
+__device__ int bpe_window(const SpModelDev& m, const BWork& w, int cut, uint16_t delim, int32_t* row, int out, int max_ids,
+                          int unk, bool fast, int lane) {
+  const unsigned full = 0xffffffffu;
+  const uint4* da = reinterpret_cast<const uint4*>(m.da);
+  int nseg = 0;
+  for (int p0 = 0; p0 < cut; p0 += 32) {
+    const int p = p0 + lane;
+    const bool f = p < cut && (p == 0 || w.sym[p] == delim);
+    const unsigned bal = __ballot_sync(full, f);
+    if (f) w.seg[nseg + __popc(bal & bf_lanemask_lt())] = (uint16_t)p;
+    nseg += __popc(bal);
+  }
+  if (lane == 0) w.seg[nseg] = (uint16_t)cut;
+  for (int i = lane; i < kBWin / 32; i += 32) w.mark[i] = 0;
+  __syncwarp();
+  // ---- easy pass: the bpe-opt whole-word shortcut, one lane per segment ----
+  // Walking from the segment start, an arc that ends exactly at the segment end after a shorter
+  // arc was already seen makes the reference keep ONLY that arc and skip the interior starts
+  // (:188-206,:228-230); a one-symbol segment with an arc is a single arc as well.
+  int nhard = 0;
+  for (int g0 = 0; g0 < nseg; g0 += 32) {
+    const int g = g0 + lane;
+    bool hard = false;
+    if (g < nseg) {
+      const int a = w.seg[g], b = w.seg[g + 1];
+      uint32_t q = m.root; int sum = 0, narcs = 0, whole_key = -1; bool whole = false;
+      for (int i = a; i < b; ++i) {
+        bool fin;
+        if (!b_step(da, q, w.sym[i], sum, fin)) break;
+        if (fin) { if (i == b - 1 && (narcs > 0 || b - a == 1)) { whole = true; whole_key = sum; } ++narcs; }
+        if (q == 0) break;
+      }
+      if (whole && ((fast && w.sym[a] == delim) || b - a == 1)) {
+        int id; float r;
+        sp_info(m, whole_key, unk, id, r);
+        w.ids_at[a] = id;
+        atomicOr(&w.mark[a >> 5], 1u << (a & 31));
+      } else hard = true;
+    }
+    const unsigned hb = __ballot_sync(full, hard);
+    if (hard) w.hard[nhard + __popc(hb & bf_lanemask_lt())] = (uint16_t)g;
+    nhard += __popc(hb);
+  }
+  __syncwarp();
+  // ---- hard pass: one lane per segment ----
+  for (int h0 = 0; h0 < nhard; h0 += 32) {
+    const int h = h0 + lane;
+    int a = 0, b = 0; bool coop = false;
+    if (h < nhard) {
+      const int g = w.hard[h];
+      a = w.seg[g]; b = w.seg[g + 1];
+      const int L = b - a;
+      int A = 0;
+      bool ok = L <= kBLaneArcs;
+      for (int s = 0; s < L && ok; ++s) {                      // every arc of every start (:188-230), kept sorted
+        uint32_t q = m.root; int sum = 0, cnt = 0;
+        for (int i = a + s; i < b; ++i) {
+          bool fin;
+          if (!b_step(da, q, w.sym[i], sum, fin)) break;
+          if (fin) {
+            const int ord = b_ord(m, sum);
+            if (ord < 0 || A == kBLaneArcs) { ok = false; break; }
+            const uint32_t key = ((uint32_t)ord << 12) | ((uint32_t)s << 6) | (uint32_t)(i - a);
+            int j = A;
+            while (j > 0) {
+              const uint32_t pv = w.scratch[(j - 1) * 32 + lane];
+              if (pv <= key) break;
+              w.scratch[j * 32 + lane] = pv; --j;
+            }
+            w.scratch[j * 32 + lane] = key;
+            ++A; ++cnt;
+          }
+          if (q == 0) break;
+        }
+        if (cnt == 0) ok = false;                              // an unknown symbol run: not here
+      }
+      if (!ok) coop = true;
+      else {
+        for (int s = 0; s < L; ++s) w.ids_at[a + s] = (int)((kBUnclaimed << 6) | (unsigned)s);
+        unsigned long long inter = 0;                          // intermediate[] (:264-296)
+        for (int k = 0; k < A; ++k) {
+          const uint32_t key = w.scratch[k * 32 + lane];
+          const int st = (int)(key >> 6) & 63, en = (int)key & 63;
+          const bool end_free = (en + 1 >= L) || ((inter >> (en + 1)) & 1ull) == 0;
+          if (((inter >> st) & 1ull) == 0 && end_free) {
+            w.ids_at[a + st] = (int)(((key >> 12) << 6) | (unsigned)en);
+            inter |= ((2ull << en) - 1ull) & ~((2ull << st) - 1ull);
+          }
+        }
+        for (int s = 0; s < L;) {                              // tokens: follow tos[] (:299-313)
+          const unsigned v = (unsigned)w.ids_at[a + s];
+          const unsigned ord = v >> 6;
+          w.ids_at[a + s] = ord == kBUnclaimed ? unk : __ldg(m.bpe_id_of_ord + ord);
+          atomicOr(&w.mark[(a + s) >> 5], 1u << ((a + s) & 31));
+          s = (int)(v & 63u) + 1;
+        }
+      }
+    }
+    unsigned cb = __ballot_sync(full, coop);
+    while (cb) {
+      const int l = __ffs(cb) - 1; cb &= cb - 1;
+      const int sa = __shfl_sync(full, a, l), sb = __shfl_sync(full, b, l);
+      if (!bpe_coop(m, w, sa, sb, unk, lane)) return kUFallback;
+    }
+  }
+  __syncwarp();
+  // ---- ordered emission ----
+  for (int p0 = 0; p0 < cut && out < max_ids; p0 += 32) {
+    const uint32_t word = w.mark[p0 >> 5];
+    const int rank = out + __popc(word & bf_lanemask_lt());
+    if (((word >> lane) & 1u) && rank < max_ids) row[rank] = w.ids_at[p0 + lane] + m.id_offset;   // (:1516)
+    out += __popc(word);
+  }
+  return out;
+}
+
+__device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
+                           int64_t padded_bytes, int32_t* row, int max_ids, int unk, uint16_t delim, int lane) {
+  const unsigned full = 0xffffffffu;
+  const bool fast = m.tok_algo == kTokenizeBpeOpt || m.tok_algo == kTokenizeBpeOptWithMerges;
+  int64_t lo = lo0;
+  if (hi - lo >= 3) {
+    const uint32_t b0 = __ldg(text + lo), b1 = __ldg(text + lo + 1), b2 = __ldg(text + lo + 2);
+    if (b0 == 0xEF && b1 == 0xBB && b2 == 0xBF) lo += 3;      // FAStrUtf8AsBytesToArray skips the BOM
+  }
+  if (hi <= lo) return 0;                                      // no symbols (:1409)
+  const uint32_t* text32 = reinterpret_cast<const uint32_t*>(text);
+  int fill = 0, out = 0, last_delim = 0;
+  bool prior = false;                                          // an earlier window has been emitted
+  unsigned carry = 0;                                          // the previous raw symbol is white, or the dummy prefix
+  if (!m.no_dummy_prefix) { if (lane == 0) w.sym[0] = delim; fill = 1; carry = 1; }   // (:1372,:1387)
+  int64_t bpos = lo;
+  for (;;) {
+    // ---- fill: whitespace -> U+2581, a white symbol survives iff its predecessor is neither (:1462-1496) ----
+    while (bpos < hi && fill + 128 <= kBWin) {
+      const int64_t bs = bpos & ~(int64_t)3;
+      const int64_t pos0 = bs + lane * 4;
+      const uint32_t word = pos0 < padded_bytes ? __ldg(text32 + (pos0 >> 2)) : 0u;
+      unsigned white = 0, valid = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t pos = pos0 + k;
+        const unsigned c = (word >> (8 * k)) & 0xFFu;
+        if (pos < bpos) white |= carry << k;                   // filler before the first byte passes the carry on
+        else if (pos < hi) { valid |= 1u << k; if (c <= 0x20u || c == 0xa0u) white |= 1u << k; }
+      }
+      const unsigned up = __shfl_up_sync(full, white >> 3, 1) & 1u;
+      const unsigned prevw = ((white << 1) | (lane ? up : carry)) & 0xFu;
+      const unsigned keep = valid & ~(white & prevw);
+      const int c = __popc(keep);
+      const int incl = warp_incl_scan(c, lane);
+      int o = fill + incl - c, my_last = -1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if ((keep >> k) & 1u) {
+          const bool wh = (white >> k) & 1u;
+          w.sym[o] = wh ? delim : __ldg(m.sym_of_cp + ((word >> (8 * k)) & 0xFFu));
+          if (wh) my_last = o;
+          ++o;
+        }
+      }
+      last_delim = max(last_delim, __reduce_max_sync(full, my_last));   // a U+2581 at 0 is no cut point
+      fill += __shfl_sync(full, incl, 31);
+      const int last = (int)(min(hi, bs + 128) - 1 - bs);     // the step's last byte
+      carry = (__shfl_sync(full, white, last >> 2) >> (last & 3)) & 1u;
+      bpos = bs + 128;
+    }
+    __syncwarp();
+    const bool at_end = bpos >= hi;
+    int cut;
+    if (at_end) {
+      if ((prior || fill > 1) && fill > 0 && w.sym[fill - 1] == delim) --fill;   // one trailing U+2581 goes (:1491-1493)
+      cut = fill;
+    } else {
+      if (last_delim <= 0) return kUFallback;                  // a segment longer than the window
+      cut = last_delim;
+    }
+    if (cut > 0) {
+      out = bpe_window(m, w, cut, delim, row, out, max_ids, unk, fast, lane);
+      if (out == kUFallback) return kUFallback;
+      if (out >= max_ids) return max_ids;
+    }
+    if (at_end) break;
+    // ---- slide: the unfinished segment moves to the front ----
+    const int rest = fill - cut;
+    for (int i0 = 0; i0 < rest; i0 += 32) {
+      const int i = i0 + lane;
+      const uint16_t v = i < rest ? w.sym[cut + i] : (uint16_t)0;
+      __syncwarp();
+      if (i < rest) w.sym[i] = v;
+      __syncwarp();
+    }
+    fill = rest; last_delim = 0; prior = true;
+  }
+  return out;
+}
+
 // BPE family: one document per warp
-__global__ void __launch_bounds__(kSpThreads, 1) sp_bpe_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
+__global__ void __launch_bounds__(kBWarps * 32, kBCtasPerSm) sp_bpe_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gwarp = blockIdx.x * kSpWarps + warp;
-  Work ws = make_work(smem + (size_t)warp * work_bytes(kSpWin), kSpWin, false);
+  const int gwarp = blockIdx.x * kBWarps + warp;
+  const BWork w = make_bwork(smem + (size_t)warp * kBWorkBytes);
   uint8_t* my_arena = p.arena + (size_t)gwarp * p.arena_stride;
   Work wa = make_work(my_arena, p.arena_cap, p.starts != nullptr);
   const ArcScratch scratch = make_scratch(p, my_arena, error_flag);
   const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
+  const uint16_t delim = __ldg(m.sym_of_cp + kSpDelim);
+  const bool fast_model = p.starts == nullptr && m.use_raw_bytes && m.norm_count == nullptr && !m.delim_inside_tokens &&
+                          m.bpe_ord != nullptr && delim != kNoSym;
   for (;;) {
     unsigned long long d64 = 0;
     if (lane == 0) d64 = atomicAdd(p.work_counter, 1ull);
@@ -582,8 +924,13 @@ __global__ void __launch_bounds__(kSpThreads, 1) sp_bpe_kernel(const SpLaunch p,
     const int64_t lo = __ldg(p.offsets + doc), hi = __ldg(p.offsets + doc + 1);
     const int64_t n = hi - lo;
     int result = 0;
-    if (n > 0 && n <= 1000000000)                                         // :1362
-      result = sp_doc_generic<true>(p, m, &ws, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
+    if (n > 0 && n <= 1000000000) {                                       // :1362
+      result = kUFallback;
+      if (fast_model)
+        result = sp_bpe_fast(m, w, p.text, lo, hi, padded_bytes, p.ids + doc * (int64_t)p.max_ids, p.max_ids, p.unk_id, delim, lane);
+      if (result == kUFallback)
+        result = sp_doc_generic<true>(p, m, nullptr, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
+    }
     if (lane == 0) p.counts[doc] = result;
     __syncwarp();
   }
@@ -632,7 +979,6 @@ __device__ inline UWork make_uwork(uint8_t* b) {
   return w;
 }
 
-constexpr int kUFallback = -2;   // the document does not fit the fast path
 
 __device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
                                int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane) {
@@ -864,7 +1210,7 @@ int sp_preferred_warps(int tok_algo) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return is_bpe_algo(tok_algo) ? sms * kSpWarps : sms * kUWarps * kUCtasPerSm;
+  return is_bpe_algo(tok_algo) ? sms * kBWarps * kBCtasPerSm : sms * kUWarps * kUCtasPerSm;
 }
 
 int sp_fast_cap(int tok_algo, int max_arc_len, bool use_raw_bytes) {
@@ -874,8 +1220,8 @@ int sp_fast_cap(int tok_algo, int max_arc_len, bool use_raw_bytes) {
 cudaError_t sp_tokenize_launch(const SpLaunch& p, const SpModelDev& m, cudaStream_t stream, int* launches) {
   if (p.ndocs <= 0) return cudaSuccess;
   const bool bpe = is_bpe_algo(m.tok_algo);
-  const int cta_warps = bpe ? kSpWarps : kUWarps;
-  const size_t smem = bpe ? (size_t)kSpWarps * work_bytes(kSpWin) : (size_t)kUWarps * kUWorkBytes;
+  const int cta_warps = bpe ? kBWarps : kUWarps;
+  const size_t smem = bpe ? (size_t)kBWarps * kBWorkBytes : (size_t)kUWarps * kUWorkBytes;
   auto kern = bpe ? sp_bpe_kernel : sp_unigram_kernel;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

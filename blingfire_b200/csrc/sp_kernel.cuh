@@ -25,6 +25,10 @@ struct SpModelDev {
   int tok_algo, id_offset;
   bool use_raw_bytes, no_dummy_prefix, delim_inside_tokens;
   int max_arc_len;
+  // BPE family: ordinal of a key in the arc sort order and its inverse (seg_tables.h); nullptr when
+  // the ordinals do not fit a sort key (the streaming BPE path is then off)
+  const int32_t* bpe_ord;        // [info_count]
+  const int32_t* bpe_id_of_ord;
 };
 
 struct SpLaunch {
