@@ -199,7 +199,7 @@ bool build_seg_tables(const LdbImage& ldb, SegTables* T, std::string* err) {
   // The BPE family sorts a segment's arcs by (rank descending -- with-merges only), id, start
   // (FATokenSegmentationTools_1best_bpe_t.h:238-255, ..._with_merges_t.h:242-262).  rank is a function
   // of the key, so (rank, id) collapses into a dense per-key ordinal and a sort key is one integer.
-  T->bpe_ord.clear(); T->bpe_id_of_ord.clear(); T->bpe_ord_ok = false;
+  T->bpe_ord.clear(); T->bpe_id_of_ord.clear(); T->bpe_ord_ok = false; T->bpe_singles_first = false;
   const bool bpe = T->tok_algo == kTokenizeBpe || T->tok_algo == kTokenizeBpeOpt || T->tok_algo == kTokenizeBpeOptWithMerges;
   if (bpe && !T->info.empty()) {
     const bool merges = T->tok_algo == kTokenizeBpeOptWithMerges;
@@ -225,6 +225,21 @@ bool build_seg_tables(const LdbImage& ldb, SegTables* T, std::string* err) {
       T->bpe_ord[order[i]] = ord;
     }
     T->bpe_ord_ok = ok && ord < (1 << 20) - 1;               // 20 bits in a sort key, all-ones reserved
+    // do all one-symbol tokens sort before every longer token?  (byte-level BPE: the 256 bytes come
+    // first.)  Then the greedy claim takes every one-symbol arc before anything is marked
+    // intermediate, and a kernel may start from that state instead of sorting those arcs.
+    std::vector<uint8_t> single(n, 0);
+    int max_single = -1, min_multi = INT_MAX;
+    for (int s = 0; s < T->alphabet; ++s) {
+      const DaEntry& e = T->da[(size_t)T->root + (size_t)s];
+      if (e.check == T->root && (e.dst & kDaFinalBit) && e.ow >= 0 && (size_t)e.ow < n) single[(size_t)e.ow] = 1;
+    }
+    for (size_t k = 0; k < n; ++k) {
+      if (T->bpe_ord[k] < 0) continue;
+      if (single[k]) max_single = std::max(max_single, T->bpe_ord[k]);
+      else min_multi = std::min(min_multi, T->bpe_ord[k]);
+    }
+    T->bpe_singles_first = T->bpe_ord_ok && max_single < min_multi;
   }
   return true;
 }

@@ -59,6 +59,7 @@ struct SegTables {
   std::vector<int32_t> bpe_ord;         // [max_key+1]
   std::vector<int32_t> bpe_id_of_ord;
   bool bpe_ord_ok = false;
+  bool bpe_singles_first = false;       // every one-symbol token sorts before every longer one
 
   std::vector<uint8_t> norm_count;      // [0x110000] 0..10, 0xFF = unmapped (keep code point)
   std::vector<uint32_t> norm_first;     // [0x110000]

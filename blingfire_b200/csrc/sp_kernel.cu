@@ -620,30 +620,44 @@ __device__ __forceinline__ int b_ord(const SpModelDev& m, int key) {
 }
 
 // One segment [a, b) of the window, the warp together.  false: it does not fit (general path).
-__device__ bool bpe_coop(const SpModelDev& m, const BWork& w, int a, int b, int unk, int lane) {
+__device__ bool bpe_coop(const SpModelDev& m, const BWork& w, const ArcScratch& scratch, int a, int b, int unk, int lane) {
   const unsigned full = 0xffffffffu;
   const uint4* da = reinterpret_cast<const uint4*>(m.da);
   const int L = b - a;
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(w.scratch);
-  // arcs of every start, grouped by start (count -> scan -> write)
+  const bool sf = m.bpe_singles_first;
+  // arcs of every start, grouped by start (count -> scan -> write); one-symbol arcs are not listed
+  // when they sort first (see bpe_window)
   int total = 0; bool bad = false;
   for (int s0 = 0; s0 < L; s0 += 32) {
     const int s = s0 + lane; int cnt = 0;
     if (s < L) {
-      uint32_t q = m.root; int sum = 0;
-      for (int i = a + s; i < b; ++i) { bool fin; if (!b_step(da, q, w.sym[i], sum, fin)) break; if (fin) ++cnt; if (q == 0) break; }
-      if (cnt == 0) bad = true;                                // an unknown symbol run (:208-227)
+      uint32_t q = m.root; int sum = 0; bool any = false;
+      for (int i = a + s; i < b; ++i) {
+        bool fin;
+        if (!b_step(da, q, w.sym[i], sum, fin)) break;
+        if (fin) { any = true; if (!(sf && i == a + s)) ++cnt; }
+        if (q == 0) break;
+      }
+      if (!any) bad = true;                                    // an unknown symbol run (:208-227)
     }
     const int incl = warp_incl_scan(cnt, lane);
     if (s < L) w.ids_at[a + s] = total + incl - cnt;
     total += __shfl_sync(full, incl, 31);
   }
-  if (__any_sync(full, bad) || total > kBCoopArcs) return false;
+  if (__any_sync(full, bad)) return false;
+  // keys in the window's scratch, or -- the rare big case -- in the warp's arena
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(w.scratch);
+  int P = 1; while (P < total) P <<= 1;
+  if (P > kBCoopArcs) {
+    if ((int64_t)P > 2 * scratch.priv_cap) return false;
+    keys = reinterpret_cast<unsigned long long*>(scratch.priv);
+  }
   __syncwarp();
   for (int s0 = 0; s0 < L; s0 += 32) {
     const int s = s0 + lane;
     if (s < L) {
       int wr = w.ids_at[a + s];
+      unsigned init = (kBUnclaimed << 10) | (unsigned)s;
       uint32_t q = m.root; int sum = 0;
       for (int i = a + s; i < b; ++i) {
         bool fin;
@@ -651,14 +665,15 @@ __device__ bool bpe_coop(const SpModelDev& m, const BWork& w, int a, int b, int 
         if (fin) {
           const int ord = b_ord(m, sum);
           if (ord < 0) bad = true;
-          keys[wr++] = ((unsigned long long)(unsigned)ord << 20) | ((unsigned long long)s << 10) | (unsigned long long)(i - a);
+          if (sf && i == a + s) init = ((unsigned)ord << 10) | (unsigned)s;
+          else keys[wr++] = ((unsigned long long)(unsigned)ord << 20) | ((unsigned long long)s << 10) | (unsigned long long)(i - a);
         }
         if (q == 0) break;
       }
+      w.ids_at[a + s] = (int)init;
     }
   }
   if (__any_sync(full, bad)) return false;
-  int P = 1; while (P < total) P <<= 1;
   for (int i = total + lane; i < P; i += 32) keys[i] = ~0ull;
   __syncwarp();
   for (int k = 2; k <= P; k <<= 1) {                           // (:238-262) as a bitonic network
@@ -674,8 +689,6 @@ __device__ bool bpe_coop(const SpModelDev& m, const BWork& w, int a, int b, int 
       __syncwarp();
     }
   }
-  for (int i = lane; i < L; i += 32) w.ids_at[a + i] = (int)((kBUnclaimed << 10) | (unsigned)i);
-  __syncwarp();
   // greedy claim in sorted order (:264-296); lane i keeps bits 32i..32i+31 of intermediate[]
   unsigned inter = 0;
   for (int k = 0; k < total; ++k) {
@@ -705,8 +718,8 @@ __device__ bool bpe_coop(const SpModelDev& m, const BWork& w, int a, int b, int 
 
 // The segments of sym[0..cut): tokens appended to row[out..).  Returns the new out (it may pass
 // max_ids; nothing is written past it) or kUFallback.
-__device__ int bpe_window(const SpModelDev& m, const BWork& w, int cut, uint16_t delim, int32_t* row, int out, int max_ids,
-                          int unk, bool fast, int lane) {
+__device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch& scratch, int cut, uint16_t delim, int32_t* row,
+                          int out, int max_ids, int unk, bool fast, int lane) {
   const unsigned full = 0xffffffffu;
   const uint4* da = reinterpret_cast<const uint4*>(m.da);
   int nseg = 0;
@@ -749,65 +762,78 @@ __device__ int bpe_window(const SpModelDev& m, const BWork& w, int cut, uint16_t
     nhard += __popc(hb);
   }
   __syncwarp();
-  // ---- hard pass: one lane per segment ----
+  // ---- hard pass: one lane per segment, in four lock-step phases ----
+  const bool sf = m.bpe_singles_first;
   for (int h0 = 0; h0 < nhard; h0 += 32) {
     const int h = h0 + lane;
-    int a = 0, b = 0; bool coop = false;
+    int a = 0, b = 0, L = 0, A = 0; bool ok = false;
     if (h < nhard) {
       const int g = w.hard[h];
-      a = w.seg[g]; b = w.seg[g + 1];
-      const int L = b - a;
-      int A = 0;
-      bool ok = L <= kBLaneArcs;
-      for (int s = 0; s < L && ok; ++s) {                      // every arc of every start (:188-230), kept sorted
-        uint32_t q = m.root; int sum = 0, cnt = 0;
-        for (int i = a + s; i < b; ++i) {
-          bool fin;
-          if (!b_step(da, q, w.sym[i], sum, fin)) break;
-          if (fin) {
-            const int ord = b_ord(m, sum);
-            if (ord < 0 || A == kBLaneArcs) { ok = false; break; }
-            const uint32_t key = ((uint32_t)ord << 12) | ((uint32_t)s << 6) | (uint32_t)(i - a);
-            int j = A;
-            while (j > 0) {
-              const uint32_t pv = w.scratch[(j - 1) * 32 + lane];
-              if (pv <= key) break;
-              w.scratch[j * 32 + lane] = pv; --j;
-            }
-            w.scratch[j * 32 + lane] = key;
-            ++A; ++cnt;
+      a = w.seg[g]; b = w.seg[g + 1]; L = b - a;
+      ok = L <= kBLaneArcs;
+    }
+    // phase 1: every arc of every start (:188-230), appended to the lane's list; ids_at[] becomes the
+    // claim state {ordinal, tos}: unclaimed, or -- when one-symbol tokens sort first -- the one-symbol
+    // arc, which the claim loop would take before anything is marked intermediate
+    for (int s = 0; s < L && ok; ++s) {
+      uint32_t q = m.root; int sum = 0, cnt = 0;
+      unsigned init = (kBUnclaimed << 6) | (unsigned)s;
+      for (int i = a + s; i < b; ++i) {
+        bool fin;
+        if (!b_step(da, q, w.sym[i], sum, fin)) break;
+        if (fin) {
+          const int ord = b_ord(m, sum);
+          if (ord < 0) { ok = false; break; }
+          if (sf && i == a + s) init = ((unsigned)ord << 6) | (unsigned)s;
+          else {
+            if (A == kBLaneArcs) { ok = false; break; }
+            w.scratch[A * 32 + lane] = ((uint32_t)ord << 12) | ((uint32_t)s << 6) | (uint32_t)(i - a);
+            ++A;
           }
-          if (q == 0) break;
+          ++cnt;
         }
-        if (cnt == 0) ok = false;                              // an unknown symbol run: not here
+        if (q == 0) break;
       }
-      if (!ok) coop = true;
-      else {
-        for (int s = 0; s < L; ++s) w.ids_at[a + s] = (int)((kBUnclaimed << 6) | (unsigned)s);
-        unsigned long long inter = 0;                          // intermediate[] (:264-296)
-        for (int k = 0; k < A; ++k) {
-          const uint32_t key = w.scratch[k * 32 + lane];
-          const int st = (int)(key >> 6) & 63, en = (int)key & 63;
-          const bool end_free = (en + 1 >= L) || ((inter >> (en + 1)) & 1ull) == 0;
-          if (((inter >> st) & 1ull) == 0 && end_free) {
-            w.ids_at[a + st] = (int)(((key >> 12) << 6) | (unsigned)en);
-            inter |= ((2ull << en) - 1ull) & ~((2ull << st) - 1ull);
-          }
+      if (cnt == 0) ok = false;                                // an unknown symbol run: not here
+      w.ids_at[a + s] = (int)init;
+    }
+    if (ok) {
+      // phase 2: the order (:238-262): ordinal of (rank, id), then start -- one integer compare
+      for (int k = 1; k < A; ++k) {
+        const uint32_t key = w.scratch[k * 32 + lane];
+        int j = k;
+        while (j > 0) {
+          const uint32_t pv = w.scratch[(j - 1) * 32 + lane];
+          if (pv <= key) break;
+          w.scratch[j * 32 + lane] = pv; --j;
         }
-        for (int s = 0; s < L;) {                              // tokens: follow tos[] (:299-313)
-          const unsigned v = (unsigned)w.ids_at[a + s];
-          const unsigned ord = v >> 6;
-          w.ids_at[a + s] = ord == kBUnclaimed ? unk : __ldg(m.bpe_id_of_ord + ord);
-          atomicOr(&w.mark[(a + s) >> 5], 1u << ((a + s) & 31));
-          s = (int)(v & 63u) + 1;
+        w.scratch[j * 32 + lane] = key;
+      }
+      // phase 3: greedy claim in that order (:264-296), intermediate[] in a register
+      unsigned long long inter = 0;
+      for (int k = 0; k < A; ++k) {
+        const uint32_t key = w.scratch[k * 32 + lane];
+        const int st = (int)(key >> 6) & 63, en = (int)key & 63;
+        const bool end_free = (en + 1 >= L) || ((inter >> (en + 1)) & 1ull) == 0;
+        if (((inter >> st) & 1ull) == 0 && end_free) {
+          w.ids_at[a + st] = (int)(((key >> 12) << 6) | (unsigned)en);
+          inter |= ((2ull << en) - 1ull) & ~((2ull << st) - 1ull);
         }
+      }
+      // phase 4: tokens: follow tos[] (:299-313)
+      for (int s = 0; s < L;) {
+        const unsigned v = (unsigned)w.ids_at[a + s];
+        const unsigned ord = v >> 6;
+        w.ids_at[a + s] = ord == kBUnclaimed ? unk : __ldg(m.bpe_id_of_ord + ord);
+        atomicOr(&w.mark[(a + s) >> 5], 1u << ((a + s) & 31));
+        s = (int)(v & 63u) + 1;
       }
     }
-    unsigned cb = __ballot_sync(full, coop);
+    unsigned cb = __ballot_sync(full, h < nhard && !ok);
     while (cb) {
       const int l = __ffs(cb) - 1; cb &= cb - 1;
       const int sa = __shfl_sync(full, a, l), sb = __shfl_sync(full, b, l);
-      if (!bpe_coop(m, w, sa, sb, unk, lane)) return kUFallback;
+      if (!bpe_coop(m, w, scratch, sa, sb, unk, lane)) return kUFallback;
     }
   }
   __syncwarp();
@@ -821,7 +847,7 @@ __device__ int bpe_window(const SpModelDev& m, const BWork& w, int cut, uint16_t
   return out;
 }
 
-__device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
+__device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const ArcScratch& scratch, const uint8_t* text, int64_t lo0, int64_t hi,
                            int64_t padded_bytes, int32_t* row, int max_ids, int unk, uint16_t delim, int lane) {
   const unsigned full = 0xffffffffu;
   const bool fast = m.tok_algo == kTokenizeBpeOpt || m.tok_algo == kTokenizeBpeOptWithMerges;
@@ -883,7 +909,7 @@ __device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const uint8_t* t
       cut = last_delim;
     }
     if (cut > 0) {
-      out = bpe_window(m, w, cut, delim, row, out, max_ids, unk, fast, lane);
+      out = bpe_window(m, w, scratch, cut, delim, row, out, max_ids, unk, fast, lane);
       if (out == kUFallback) return kUFallback;
       if (out >= max_ids) return max_ids;
     }
@@ -927,7 +953,7 @@ __global__ void __launch_bounds__(kBWarps * 32, kBCtasPerSm) sp_bpe_kernel(const
     if (n > 0 && n <= 1000000000) {                                       // :1362
       result = kUFallback;
       if (fast_model)
-        result = sp_bpe_fast(m, w, p.text, lo, hi, padded_bytes, p.ids + doc * (int64_t)p.max_ids, p.max_ids, p.unk_id, delim, lane);
+        result = sp_bpe_fast(m, w, scratch, p.text, lo, hi, padded_bytes, p.ids + doc * (int64_t)p.max_ids, p.max_ids, p.unk_id, delim, lane);
       if (result == kUFallback)
         result = sp_doc_generic<true>(p, m, nullptr, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
     }

@@ -29,6 +29,7 @@ struct SpModelDev {
   // the ordinals do not fit a sort key (the streaming BPE path is then off)
   const int32_t* bpe_ord;        // [info_count]
   const int32_t* bpe_id_of_ord;
+  bool bpe_singles_first;        // one-symbol tokens sort before all others (seg_tables.h)
 };
 
 struct SpLaunch {
