@@ -580,8 +580,10 @@ constexpr int kUFallback = -2;   // the document does not fit a fast path: the c
 constexpr int kBWarps = 8;                 // per CTA
 constexpr int kBCtasPerSm = 2;
 constexpr int kBWin = 512;                 // symbols in the window
-constexpr int kBLaneArcs = 64;             // lane-serial segments: at most this many arcs, and symbols
-constexpr int kBCoopArcs = 1024;           // warp-cooperative segments: arcs (64-bit keys, same scratch)
+constexpr int kBLaneArcs = 48;             // lane-serial segments: at most this many listed arcs ...
+constexpr int kBMaxLen = 64;               // ... and symbols (intermediate[] is one 64-bit register)
+constexpr int kBSplitLen = 24;             // longer segments are first split at the positions no token spans
+constexpr int kBCoopArcs = 512;            // warp-cooperative segments: arcs sorted in the window's scratch (64-bit keys)
 constexpr unsigned kBUnclaimed = 0xFFFFFu; // ordinal of "no arc claimed from this start"
 
 struct BWork {
@@ -590,10 +592,13 @@ struct BWork {
   uint32_t* mark;       // [kBWin/32] bit p: a token starts at p
   uint16_t* sym;        // [kBWin] alphabet indices
   uint16_t* seg;        // [kBWin/2+8] segment starts, window-relative, and the end sentinel
-  uint16_t* hard;       // [kBWin/2+8] segments the easy pass left
+  uint16_t* hard_a;     // [kBWin] the pieces the easy pass left: first symbol ...
+  uint16_t* hard_b;     // [kBWin] ... and one past the last
+  uint32_t* cnt;        // [32] arcs listed per slot; [32] = slots that cannot be served lane-serially
+  uint8_t* order;       // [kBLaneArcs][32] list index of the arc of rank r
 };
-constexpr int kBWorkBytes = 4 * 32 * kBLaneArcs + 4 * kBWin + 4 * (kBWin / 32) + 2 * kBWin + 4 * (kBWin / 2 + 8);
-static_assert(kBWorkBytes % 16 == 0 && 8 * kBCoopArcs <= 4 * 32 * kBLaneArcs && kBLaneArcs <= 64 && kBWin <= 1024, "workspace layout");
+constexpr int kBWorkBytes = 4 * 32 * kBLaneArcs + 4 * kBWin + 4 * (kBWin / 32) + 2 * kBWin + 2 * (kBWin / 2 + 8) + 4 * kBWin + 4 * 36 + 32 * kBLaneArcs;
+static_assert(kBWorkBytes % 16 == 0 && 8 * kBCoopArcs <= 4 * 32 * kBLaneArcs && kBLaneArcs <= 64 && kBMaxLen <= 64 && kBWin <= 1024, "workspace layout");
 
 __device__ inline BWork make_bwork(uint8_t* b) {
   BWork w;
@@ -602,7 +607,10 @@ __device__ inline BWork make_bwork(uint8_t* b) {
   w.mark = (uint32_t*)b; b += 4 * (kBWin / 32);
   w.sym = (uint16_t*)b; b += 2 * kBWin;
   w.seg = (uint16_t*)b; b += 2 * (kBWin / 2 + 8);
-  w.hard = (uint16_t*)b;
+  w.hard_a = (uint16_t*)b; b += 2 * kBWin;
+  w.hard_b = (uint16_t*)b; b += 2 * kBWin;
+  w.cnt = (uint32_t*)b; b += 4 * 36;
+  w.order = b;
   return w;
 }
 
@@ -648,7 +656,7 @@ __device__ bool bpe_coop(const SpModelDev& m, const BWork& w, const ArcScratch& 
   // keys in the window's scratch, or -- the rare big case -- in the warp's arena
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(w.scratch);
   int P = 1; while (P < total) P <<= 1;
-  if (P > kBCoopArcs) {
+  if (P > kBCoopArcs) {                                        // (P is a power of two)
     if ((int64_t)P > 2 * scratch.priv_cap) return false;
     keys = reinterpret_cast<unsigned long long*>(scratch.priv);
   }
@@ -716,10 +724,27 @@ __device__ bool bpe_coop(const SpModelDev& m, const BWork& w, const ArcScratch& 
   return true;
 }
 
+// Farthest end (window position) of a token that starts at p and lies inside [p, limit); -1: none.
+// *open: the walk ran into `limit` while it could still continue.
+__device__ __forceinline__ int b_farthest(const SpModelDev& m, const uint4* da, const uint16_t* sym, int p, int limit, bool* open) {
+  uint32_t q = m.root; int sum = 0, fe = -1;
+  *open = false;
+  int i = p;
+  for (; i < limit; ++i) {
+    bool fin;
+    if (!b_step(da, q, sym[i], sum, fin)) break;
+    if (fin) fe = i;
+    if (q == 0) break;
+  }
+  if (i == limit) *open = true;
+  return fe;
+}
+
 // The segments of sym[0..cut): tokens appended to row[out..).  Returns the new out (it may pass
-// max_ids; nothing is written past it) or kUFallback.
+// max_ids; nothing is written past it) or kUFallback.  open_ended: the last segment does not end at a
+// U+2581 (nor at the end of the document) but at a position no token can span.
 __device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch& scratch, int cut, uint16_t delim, int32_t* row,
-                          int out, int max_ids, int unk, bool fast, int lane) {
+                          int out, int max_ids, int unk, bool fast, bool open_ended, int lane) {
   const unsigned full = 0xffffffffu;
   const uint4* da = reinterpret_cast<const uint4*>(m.da);
   int nseg = 0;
@@ -741,8 +766,11 @@ __device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch&
   for (int g0 = 0; g0 < nseg; g0 += 32) {
     const int g = g0 + lane;
     bool hard = false;
-    if (g < nseg) {
-      const int a = w.seg[g], b = w.seg[g + 1];
+    int a = 0, b = 0;
+    if (g < nseg && open_ended && g == nseg - 1) {             // its true end is not in the window: no shortcut
+      a = w.seg[g]; b = w.seg[g + 1]; hard = true;
+    } else if (g < nseg) {
+      a = w.seg[g]; b = w.seg[g + 1];
       uint32_t q = m.root; int sum = 0, narcs = 0, whole_key = -1; bool whole = false;
       for (int i = a; i < b; ++i) {
         bool fin;
@@ -758,61 +786,121 @@ __device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch&
       } else hard = true;
     }
     const unsigned hb = __ballot_sync(full, hard);
-    if (hard) w.hard[nhard + __popc(hb & bf_lanemask_lt())] = (uint16_t)g;
+    if (hard) { const int k = nhard + __popc(hb & bf_lanemask_lt()); w.hard_a[k] = (uint16_t)a; w.hard_b[k] = (uint16_t)b; }
     nhard += __popc(hb);
   }
   __syncwarp();
-  // ---- hard pass: one lane per segment, in four lock-step phases ----
+  // ---- split pass: a long segment falls apart at every position no token spans ----
+  // No arc crosses such a position, so it is never marked intermediate and the claim tests on
+  // either side never see the other side: the pieces are independent and each sorts only its own
+  // arcs.  (Long whitespace-free runs are URLs and CJK/Thai text; they split every few bytes.)
+  {
+    const int nhard0 = nhard;
+    for (int h0 = 0; h0 < nhard0; h0 += 32) {
+      const int h = h0 + lane;
+      unsigned lb = __ballot_sync(full, h < nhard0 && (int)w.hard_b[h] - (int)w.hard_a[h] > kBSplitLen);
+      while (lb) {
+        const int l = __ffs(lb) - 1; lb &= lb - 1;
+        const int hh = h0 + l;
+        const int sa = w.hard_a[hh], sb = w.hard_b[hh];
+        const int n0 = nhard;
+        int carry = -1; bool bad = false;
+        for (int p0 = sa; p0 < sb; p0 += 32) {
+          const int p = p0 + lane;
+          int fe = -1;
+          if (p < sb) { bool open; fe = b_farthest(m, da, w.sym, p, sb, &open); if (fe < 0) bad = true; }
+          int incl = fe;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(full, incl, o); if (lane >= o) incl = max(incl, t); }
+          int excl = __shfl_up_sync(full, incl, 1);
+          excl = lane ? max(excl, carry) : carry;
+          const bool piece = p < sb && p > sa && excl < p;     // (the segment start is piece 0: entry hh itself)
+          const unsigned pb = __ballot_sync(full, piece);
+          if (piece) w.hard_a[nhard + __popc(pb & bf_lanemask_lt())] = (uint16_t)p;
+          nhard += __popc(pb);
+          carry = max(carry, __shfl_sync(full, incl, 31));
+        }
+        if (__any_sync(full, bad)) return kUFallback;          // a symbol no token starts with: the general path
+        __syncwarp();
+        for (int k = n0 + lane; k < nhard; k += 32) w.hard_b[k] = k + 1 < nhard ? w.hard_a[k + 1] : (uint16_t)sb;
+        if (lane == 0 && nhard > n0) w.hard_b[hh] = w.hard_a[n0];
+        __syncwarp();
+      }
+    }
+  }
+  // ---- hard pass, 32 segments (slots) at a time; the lanes are re-dealt for every phase ----
   const bool sf = m.bpe_singles_first;
   for (int h0 = 0; h0 < nhard; h0 += 32) {
     const int h = h0 + lane;
-    int a = 0, b = 0, L = 0, A = 0; bool ok = false;
-    if (h < nhard) {
-      const int g = w.hard[h];
-      a = w.seg[g]; b = w.seg[g + 1]; L = b - a;
-      ok = L <= kBLaneArcs;
-    }
-    // phase 1: every arc of every start (:188-230), appended to the lane's list; ids_at[] becomes the
-    // claim state {ordinal, tos}: unclaimed, or -- when one-symbol tokens sort first -- the one-symbol
-    // arc, which the claim loop would take before anything is marked intermediate
-    for (int s = 0; s < L && ok; ++s) {
-      uint32_t q = m.root; int sum = 0, cnt = 0;
-      unsigned init = (kBUnclaimed << 6) | (unsigned)s;
-      for (int i = a + s; i < b; ++i) {
-        bool fin;
-        if (!b_step(da, q, w.sym[i], sum, fin)) break;
-        if (fin) {
-          const int ord = b_ord(m, sum);
-          if (ord < 0) { ok = false; break; }
-          if (sf && i == a + s) init = ((unsigned)ord << 6) | (unsigned)s;
-          else {
-            if (A == kBLaneArcs) { ok = false; break; }
-            w.scratch[A * 32 + lane] = ((uint32_t)ord << 12) | ((uint32_t)s << 6) | (uint32_t)(i - a);
-            ++A;
+    int a = 0, b = 0, L = 0; bool lane_ok = false;
+    if (h < nhard) { a = w.hard_a[h]; b = w.hard_b[h]; L = b - a; lane_ok = L <= kBMaxLen; }
+    const int preL = warp_incl_scan(lane_ok ? L : 0, lane);
+    const int T = __shfl_sync(full, preL, 31);
+    w.cnt[lane] = 0;
+    if (lane == 0) w.cnt[32] = 0;                              // bit s: slot s cannot be served here
+    __syncwarp();
+    // phase 1, one lane per (slot, start): every arc of that start (:188-230) goes to the slot's
+    // list.  ids_at[] becomes the claim state {ordinal, tos}: unclaimed, or -- when one-symbol
+    // tokens sort first -- the one-symbol arc, which the claim loop would take before anything is
+    // marked intermediate.
+    for (int t0 = 0; t0 < T; t0 += 32) {
+      const int t = t0 + lane;
+      int slot = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) { const int v = __shfl_sync(full, preL, slot + step - 1); if (v <= t) slot += step; }
+      const int sa = __shfl_sync(full, a, slot), sb = __shfl_sync(full, b, slot), sp = __shfl_sync(full, preL, slot);
+      if (t < T) {
+        const int s = t - (sp - (sb - sa));
+        uint32_t q = m.root; int sum = 0, cnt = 0;
+        unsigned init = (kBUnclaimed << 6) | (unsigned)s;
+        for (int i = sa + s; i < sb; ++i) {
+          bool fin;
+          if (!b_step(da, q, w.sym[i], sum, fin)) break;
+          if (fin) {
+            const int ord = b_ord(m, sum);
+            ++cnt;
+            if (ord < 0) { cnt = 0; break; }
+            if (sf && i == sa + s) init = ((unsigned)ord << 6) | (unsigned)s;
+            else {
+              const unsigned idx = atomicAdd(&w.cnt[slot], 1u);
+              if (idx < (unsigned)kBLaneArcs) w.scratch[idx * 32 + slot] = ((uint32_t)ord << 12) | ((uint32_t)s << 6) | (uint32_t)(i - sa);
+            }
           }
-          ++cnt;
+          if (q == 0) break;
         }
-        if (q == 0) break;
+        if (cnt == 0) atomicOr(&w.cnt[32], 1u << slot);        // an unknown symbol run (or an unusable key): not here
+        w.ids_at[sa + s] = (int)init;
       }
-      if (cnt == 0) ok = false;                                // an unknown symbol run: not here
-      w.ids_at[a + s] = (int)init;
     }
-    if (ok) {
-      // phase 2: the order (:238-262): ordinal of (rank, id), then start -- one integer compare
-      for (int k = 1; k < A; ++k) {
-        const uint32_t key = w.scratch[k * 32 + lane];
-        int j = k;
-        while (j > 0) {
-          const uint32_t pv = w.scratch[(j - 1) * 32 + lane];
-          if (pv <= key) break;
-          w.scratch[j * 32 + lane] = pv; --j;
-        }
-        w.scratch[j * 32 + lane] = key;
+    __syncwarp();
+    // phase 2, one lane per (slot, arc): its rank in the order (:238-262) -- ordinal of (rank, id),
+    // then start: one integer compare; keys are distinct, so the ranks are a permutation
+    const int A = (int)w.cnt[lane];
+    const bool ok = lane_ok && A <= kBLaneArcs && ((w.cnt[32] >> lane) & 1u) == 0;
+    const int Aw = ok ? A : 0;
+    const int preA = warp_incl_scan(Aw, lane);
+    const int U = __shfl_sync(full, preA, 31);
+    for (int u0 = 0; u0 < U; u0 += 32) {
+      const int u = u0 + lane;
+      int slot = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) { const int v = __shfl_sync(full, preA, slot + step - 1); if (v <= u) slot += step; }
+      const int sA = __shfl_sync(full, Aw, slot), spA = __shfl_sync(full, preA, slot);
+      if (u < U) {
+        const int idx = u - (spA - sA);
+        const uint32_t key = w.scratch[idx * 32 + slot];
+        int rank = 0;
+        for (int k = 0; k < sA; ++k) rank += w.scratch[k * 32 + slot] < key;
+        w.order[rank * 32 + slot] = (uint8_t)idx;
       }
-      // phase 3: greedy claim in that order (:264-296), intermediate[] in a register
+    }
+    __syncwarp();
+    // phases 3 and 4, one lane per slot: greedy claim in that order (:264-296) with intermediate[]
+    // in a register, then the tokens by following tos[] (:299-313)
+    if (ok) {
       unsigned long long inter = 0;
-      for (int k = 0; k < A; ++k) {
-        const uint32_t key = w.scratch[k * 32 + lane];
+      for (int r = 0; r < A; ++r) {
+        const uint32_t key = w.scratch[(int)w.order[r * 32 + lane] * 32 + lane];
         const int st = (int)(key >> 6) & 63, en = (int)key & 63;
         const bool end_free = (en + 1 >= L) || ((inter >> (en + 1)) & 1ull) == 0;
         if (((inter >> st) & 1ull) == 0 && end_free) {
@@ -820,7 +908,6 @@ __device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch&
           inter |= ((2ull << en) - 1ull) & ~((2ull << st) - 1ull);
         }
       }
-      // phase 4: tokens: follow tos[] (:299-313)
       for (int s = 0; s < L;) {
         const unsigned v = (unsigned)w.ids_at[a + s];
         const unsigned ord = v >> 6;
@@ -900,16 +987,38 @@ __device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const ArcScratch
     }
     __syncwarp();
     const bool at_end = bpos >= hi;
-    int cut;
+    int cut; bool open_ended = false;
     if (at_end) {
       if ((prior || fill > 1) && fill > 0 && w.sym[fill - 1] == delim) --fill;   // one trailing U+2581 goes (:1491-1493)
       cut = fill;
-    } else {
-      if (last_delim <= 0) return kUFallback;                  // a segment longer than the window
+    } else if (last_delim > 0) {
       cut = last_delim;
+    } else {
+      // One segment fills the window.  Cut it at the last position p that no token spans (see the
+      // split pass), provided every start before p has been walked to its end inside the window.
+      const uint4* da = reinterpret_cast<const uint4*>(m.da);
+      int carry = -1, best = 0; bool closed = true;
+      for (int p0 = 0; p0 < fill && closed; p0 += 32) {
+        const int p = p0 + lane;
+        int fe = -1; bool open = false;
+        if (p < fill) fe = b_farthest(m, da, w.sym, p, fill, &open);
+        int incl = fe;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(full, incl, o); if (lane >= o) incl = max(incl, t); }
+        int excl = __shfl_up_sync(full, incl, 1);
+        excl = lane ? max(excl, carry) : carry;
+        const unsigned ob = __ballot_sync(full, open);
+        const int first_open = ob ? p0 + __ffs(ob) - 1 : fill;   // starts at or after it are not fully known
+        const unsigned cb = __ballot_sync(full, p < fill && p > 0 && excl < p && p <= first_open);
+        if (cb) best = p0 + 31 - __clz(cb);
+        if (ob) closed = false;
+        carry = max(carry, __shfl_sync(full, incl, 31));
+      }
+      if (best <= 0) return kUFallback;                        // no such position: the general path
+      cut = best; open_ended = true;
     }
     if (cut > 0) {
-      out = bpe_window(m, w, scratch, cut, delim, row, out, max_ids, unk, fast, lane);
+      out = bpe_window(m, w, scratch, cut, delim, row, out, max_ids, unk, fast, open_ended, lane);
       if (out == kUFallback) return kUFallback;
       if (out >= max_ids) return max_ids;
     }
