@@ -1236,25 +1236,35 @@ __device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_
     for (int h = 0; h < 2; ++h) {
       const int t0 = tA + 16 * h;
       if (t0 >= N) break;
+      // off the serial chain: the score of the arc that reaches this lane's position from each of the
+      // 16 starts (if there is one), and which starts have no arc at all
+      float in_sc[16];
+      unsigned have = 0, none = 0;
+#pragma unroll
+      for (int l = 0; l < 16; ++l) {
+        const unsigned M = __shfl_sync(full, amask, 16 * h + l);
+        const int k = lane - 1 - l;
+        in_sc[l] = 0.0f;
+        if ((unsigned)k < (unsigned)kUMaxLen && ((M >> k) & 1u)) {
+          in_sc[l] = __int_as_float(w.arc[(16 * h + l) * kUMaxLen + k].y);
+          have |= 1u << l;
+        }
+        if (M == 0) none |= 1u << l;
+      }
 #pragma unroll
       for (int l = 0; l < 16; ++l) {
         const int st = t0 + l;
         if (st >= N) break;
-        const unsigned M = __shfl_sync(full, amask, 16 * h + l);
         const double prev = __shfl_sync(full, sc, l);          // score[st-1], final by now
-        if (M != 0) {                                          // AddArc (:118-142)
-          const int k = lane - 1 - l;
-          if ((unsigned)k < (unsigned)kUMaxLen && ((M >> k) & 1u)) {
-            const int2 a = w.arc[(16 * h + l) * kUMaxLen + k];
-            const double cand = (double)__int_as_float(a.y) + prev;
-            if (sc < cand) { sc = cand; bg = st; bi = a.x; }
-          }
-        } else {                                               // AddUnknownArc (:145-171)
+        if ((none >> l) & 1u) {                                // AddUnknownArc (:145-171)
           const int pid = __shfl_sync(full, bi, l), pbg = __shfl_sync(full, bg, l);
           if (lane == l + 1) {
             const double cand = (double)(-100000.0f) + prev;
             if (sc < cand) { sc = cand; bi = -1; bg = (st > 0 && pid == -1) ? pbg : st; }
           }
+        } else {                                               // AddArc (:118-142)
+          const double cand = (double)in_sc[l] + prev;
+          if (((have >> l) & 1u) && sc < cand) { sc = cand; bg = st; bi = w.arc[(16 * h + l) * kUMaxLen + lane - 1 - l].x; }
         }
       }
       // positions t0 .. t0+15 (lanes 1..16) are final: park them for the back-trace, slide the window
@@ -1264,15 +1274,13 @@ __device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_
     }
   }
   __syncwarp();
-  // ---- back-trace (:227-257): mark token starts, move each token's id to its start slot ----
+  // ---- back-trace (:227-257): mark the token ENDS (same order as the starts; the id already sits there) ----
   if (lane == 0) {
     int end = N - 1;
     while (end >= 0) {
+      w.mark[end >> 5] |= 1u << (end & 31);
       const int b = w.begin[end];
-      const int id = bid[end];
-      if (b == kUNoBegin) { w.mark[0] |= 1u; bid[0] = id; break; }   // never-set arc: the reference emits it first and stops
-      w.mark[b >> 5] |= 1u << (b & 31);
-      bid[b] = id;                                             // positions at or before b are not read again as ends
+      if (b == kUNoBegin) break;                               // never-set arc: the reference emits it first and stops
       end = b - 1;
     }
   }

@@ -23,6 +23,7 @@ def sptwin():
     L.sptwin_error.restype = ctypes.c_char_p
     L.sptwin_error.argtypes = [ctypes.c_void_p]
     L.sptwin_info.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.sptwin_check_bpe_order.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.sptwin_text_to_ids.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     return L
 
@@ -72,3 +73,21 @@ def test_model_properties(sptwin):
         assert sptwin.sptwin_info(h, 5) == algo and sptwin.sptwin_info(h, 7) == raw
         assert sptwin.sptwin_info(h, 4) == 0     # no token has U+2581 past its first symbol
         sptwin.sptwin_free(h)
+
+
+def test_bpe_order_is_one_integer(sptwin):
+    """The streaming BPE kernel sorts arcs by one integer: the ordinal of (rank, id) must order keys
+    exactly like the reference comparator.  gpt2 (ids = merge order) puts the one-symbol tokens first;
+    roberta sorts by rank first and gives them the lowest rank, so they come last."""
+    for name, singles_first in [("gpt2.bin", 1), ("roberta.bin", 0), ("bpe_example.bin", None)]:
+        h = sptwin.sptwin_load(model_path(name).encode())
+        assert sptwin.sptwin_error(h) == b""
+        assert sptwin.sptwin_info(h, 9) == 1
+        if singles_first is not None:
+            assert sptwin.sptwin_info(h, 10) == singles_first
+        assert sptwin.sptwin_info(h, 11) > 0
+        assert sptwin.sptwin_check_bpe_order(h, 37) == 0
+        sptwin.sptwin_free(h)
+    h = sptwin.sptwin_load(model_path("xlm_roberta_base.bin").encode())
+    assert sptwin.sptwin_info(h, 9) == 0 and sptwin.sptwin_check_bpe_order(h, 37) == -1   # Unigram: no such table
+    sptwin.sptwin_free(h)

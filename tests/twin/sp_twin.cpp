@@ -56,8 +56,36 @@ int sptwin_info(void* h, int what) {
     case 6: return S.id_offset;
     case 7: return S.use_raw_bytes ? 1 : 0;
     case 8: return S.has_charmap ? 1 : 0;
+    case 9: return S.bpe_ord_ok ? 1 : 0;
+    case 10: return S.bpe_singles_first ? 1 : 0;
+    case 11: return (int)S.bpe_id_of_ord.size();
     default: return -1;
   }
+}
+
+// The BPE arc order as one integer (seg_tables.h): for every pair of usable keys sampled with
+// `stride`, ord[a] < ord[b] must agree with the reference comparator on (rank desc when merges, id)
+// (FATokenSegmentationTools_1best_bpe_t.h:238-255, ..._with_merges_t.h:242-262), and id_of_ord must
+// invert it.  Returns the number of violations, -1 if the table is absent.
+int sptwin_check_bpe_order(void* h, int stride) {
+  const SegTables& S = ((SpTwin*)h)->S;
+  if (S.bpe_ord.size() != S.info.size() || S.bpe_ord.empty()) return -1;
+  const bool merges = S.tok_algo == kTokenizeBpeOptWithMerges;
+  int bad = 0;
+  std::vector<int> keys;
+  for (size_t k = 0; k < S.info.size(); k += (size_t)stride) if (S.bpe_ord[k] >= 0) keys.push_back((int)k);
+  for (int a : keys) {
+    if (S.bpe_id_of_ord[(size_t)S.bpe_ord[a]] != S.info[a].id) ++bad;
+    for (int b : keys) {
+      const SegInfo& x = S.info[a]; const SegInfo& y = S.info[b];
+      int cmp = 0;                                  // -1: a first
+      if (merges && x.score != y.score) cmp = x.score > y.score ? -1 : 1;
+      else if (x.id != y.id) cmp = x.id < y.id ? -1 : 1;
+      const int oc = S.bpe_ord[a] < S.bpe_ord[b] ? -1 : (S.bpe_ord[a] > S.bpe_ord[b] ? 1 : 0);
+      if (cmp != oc) ++bad;
+    }
+  }
+  return bad;
 }
 
 int sptwin_text_to_ids(void* h, const char* s, int n, int32_t* ids, int max_ids, int unk) {
