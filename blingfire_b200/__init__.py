@@ -129,6 +129,55 @@ def text_to_words(s):
     return text_to_words_with_model(None, s)
 
 
+def text_to_sentences_with_model(h, s):
+    """dist-pypi/blingfire/__init__.py:45-62."""
+    s_bytes = s.encode("utf-8")
+    o_cap = len(s_bytes) * 2 + 1
+    o = ctypes.create_string_buffer(o_cap)
+    L = lib()
+    L.TextToSentencesWithModel.restype = c_int
+    L.TextToSentencesWithModel.argtypes = [c_char_p, c_int, c_void_p, c_int, c_void_p]
+    n = L.TextToSentencesWithModel(s_bytes, len(s_bytes), o, o_cap, c_void_p(h) if h else None)
+    if n < 0 or n > o_cap:
+        return ""
+    return o.value.decode("utf-8")
+
+
+def text_to_sentences(s):
+    """dist-pypi/blingfire/__init__.py:25-42 (default sentence-breaking model)."""
+    return text_to_sentences_with_model(None, s)
+
+
+def _utf8_split_with_offsets(fn_name, s_bytes, h=None):
+    """Raw form of the WithOffsets calls: (text bytes without the NUL, starts, ends) with BYTE offsets of
+    the first byte of each token's first character and the last byte of its last character."""
+    L = lib()
+    f = getattr(L, fn_name)
+    f.restype = c_int
+    f.argtypes = [c_char_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    o_cap = len(s_bytes) * 2 + 1
+    o = ctypes.create_string_buffer(o_cap)
+    starts = np.zeros(o_cap, dtype=np.int32)
+    ends = np.zeros(o_cap, dtype=np.int32)
+    n = f(s_bytes, len(s_bytes), o, starts.ctypes.data, ends.ctypes.data, o_cap, c_void_p(h) if h else None)
+    if n <= 0 or n > o_cap:
+        return b"", starts[:0], ends[:0]
+    text = o.raw[: n - 1]
+    sep = b" " if "Words" in fn_name else b"\n"
+    k = text.count(sep) + 1 if text else 0
+    return text, starts[:k], ends[:k]
+
+
+def utf8text_to_words_with_offsets(s_bytes, h=None):
+    """TextToWordsWithOffsets[WithModel] (blingfiretokdll.cpp:415-566) on bytes, byte offsets."""
+    return _utf8_split_with_offsets("TextToWordsWithOffsetsWithModel", s_bytes, h)
+
+
+def utf8text_to_sentences_with_offsets(s_bytes, h=None):
+    """TextToSentencesWithOffsets[WithModel] (blingfiretokdll.cpp:163-355) on bytes, byte offsets."""
+    return _utf8_split_with_offsets("TextToSentencesWithOffsetsWithModel", s_bytes, h)
+
+
 # ---- additive batch API --------------------------------------------------------------------
 
 def make_csr(docs):

@@ -709,89 +709,132 @@ int TextToIds_sp(void* h, const char* s, int n, int32_t* ids, const int max_ids,
   return TextToIds(h, s, n, ids, max_ids, unk);
 }
 
-// The reference embeds wbd.bin as a byte array and initialises it once under a mutex
-// (blingfiretokdll.cpp:114-133, :426-434).  Here the same model is loaded from
-// $BLINGFIRE_B200_WBD, or from wbd.bin next to this shared library, on first use.
-static Model* default_wbd_model() {
+// The reference embeds wbd.bin and sbd.bin as byte arrays and initialises them once under a mutex
+// (blingfiretokdll.cpp:114-133, :426-434).  Here the same models are loaded from $BLINGFIRE_B200_WBD /
+// $BLINGFIRE_B200_SBD, or from wbd.bin / sbd.bin next to this shared library, on first use.
+static Model* default_model(int which) {        // 0 = word breaker, 1 = sentence breaker
   static std::mutex mu;
-  static Model* model = nullptr;
-  static bool tried = false;
+  static Model* model[2] = {nullptr, nullptr};
+  static bool tried[2] = {false, false};
   std::lock_guard<std::mutex> lock(mu);
-  if (tried) return model;
-  tried = true;
+  if (tried[which]) return model[which];
+  tried[which] = true;
   std::string path;
-  if (const char* env = std::getenv("BLINGFIRE_B200_WBD")) path = env;
+  if (const char* env = std::getenv(which ? "BLINGFIRE_B200_SBD" : "BLINGFIRE_B200_WBD")) path = env;
   if (path.empty()) {
     Dl_info info;
-    if (dladdr((const void*)&default_wbd_model, &info) && info.dli_fname) {
+    if (dladdr((const void*)&default_model, &info) && info.dli_fname) {
       path = info.dli_fname;
       const size_t slash = path.find_last_of('/');
-      path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/wbd.bin";
+      path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + (which ? "/sbd.bin" : "/wbd.bin");
     }
   }
-  model = (Model*)LoadModel(path.c_str());
-  if (!model) set_error("default word-breaking model not found (" + path + "): " + g_last_error);
-  return model;
+  model[which] = (Model*)LoadModel(path.c_str());
+  if (!model[which]) set_error(std::string("default ") + (which ? "sentence" : "word") + "-breaking model not found (" + path + "): " + g_last_error);
+  return model[which];
 }
 
-// blingfiretokdll.cpp:415-566 (TextToWordsWithOffsetsWithModel without offsets).  The lexer
-// (decode, classes, Process_int with every nested call) runs on the GPU; the host only turns the
-// (Tag, From, To) triples back into the ' '-joined UTF-8 string, like the reference's
-// ostringstream loop (:507-552).
-int TextToWordsWithModel(const char* s, int n, char* out, const int max_out, void* hModel) {
+namespace {
+
+// What the host needs to put a lexer's output back into text: the (Tag, From, To) triples and the byte
+// offset of every code point.  The lexer itself (decode, classes, Process_int with every nested call)
+// runs on the GPU.  Caller holds m->mu.  Returns false on any failure (invalid UTF-8 included).
+struct LexedText { int ncps = 0, rn = 0; const int32_t* tri = nullptr; std::vector<int> cp_off; };
+
+bool lex_on_gpu(Model* m, const char* s, int n, LexedText* R) {
+  if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return false;
+  Slot& sl = m->slots[0];
+  if (!ensure_stream(sl)) return false;
+  const size_t nb = (size_t)n;
+  if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve(2) || !sl.lex_cls.reserve(nb + 8) || !sl.lex_ncps.reserve(1) ||
+      !sl.lex_tri_count.reserve(1) || !sl.lex_tri.reserve(3 * nb + 8) || !m->h_words.reserve(3 * nb + 16))
+    return false;
+  const int64_t offs[2] = {0, n};
+  if (!cuda_ok(cudaMemcpyAsync(sl.text.p, s, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return false;
+  if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return false;
+  LexLaunch X = make_lex_launch(m, sl, 0, 0, n, 1, m->d_cls_words, 1);   // MaxOut = 3 * MaxBuffSize (:492-499, :249-251)
+  int nl = 0;
+  if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return false;
+  g_launches += nl;
+  int32_t* hw = m->h_words.p;
+  if (!cuda_ok(cudaMemcpyAsync(hw, sl.lex_ncps.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return false;
+  if (!cuda_ok(cudaMemcpyAsync(hw + 1, sl.lex_tri_count.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return false;
+  if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return false;
+  const int ncps = hw[0], rn = hw[1];
+  if (ncps <= 0) return false;                                      // invalid UTF-8 or nothing decoded (:475-478, :231-234)
+  if (rn < 0 || rn > 3 * ncps || rn % 3 != 0) return false;         // :500-502, :252-254
+  if (rn > 0) {
+    if (!cuda_ok(cudaMemcpyAsync(hw + 2, sl.lex_tri.p, (size_t)rn * 4, cudaMemcpyDeviceToHost, sl.stream), "D2H triples")) return false;
+    if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return false;
+  }
+  // code point -> byte offset of the (already validated) input, BOM skipped like the decoder
+  R->cp_off.resize((size_t)ncps + 1);
+  int p = (n >= 3 && (uint8_t)s[0] == 0xEF && (uint8_t)s[1] == 0xBB && (uint8_t)s[2] == 0xBF) ? 3 : 0;
+  for (int i = 0; i < ncps; ++i) {
+    R->cp_off[(size_t)i] = p;
+    const uint8_t c = (uint8_t)s[p];
+    p += c < 0x80 ? 1 : (c & 0xE0) == 0xC0 ? 2 : (c & 0xF0) == 0xE0 ? 3 : 4;
+  }
+  R->cp_off[(size_t)ncps] = p;
+  R->ncps = ncps; R->rn = rn; R->tri = hw + 2;
+  return true;
+}
+
+inline bool white_cp_at(const char* s, int b) {                      // __FAIsWhiteSpace__ (blingfiretokdll.h:17-21) of the code point at byte b
+  const uint8_t c0 = (uint8_t)s[b];
+  uint32_t cp;
+  if (c0 < 0x80) cp = c0;
+  else if ((c0 & 0xE0) == 0xC0) cp = ((c0 & 0x1Fu) << 6) | ((uint8_t)s[b + 1] & 0x3Fu);
+  else if ((c0 & 0xF0) == 0xE0) cp = ((c0 & 0x0Fu) << 12) | (((uint8_t)s[b + 1] & 0x3Fu) << 6) | ((uint8_t)s[b + 2] & 0x3Fu);
+  else cp = ((c0 & 0x07u) << 18) | (((uint8_t)s[b + 1] & 0x3Fu) << 12) | (((uint8_t)s[b + 2] & 0x3Fu) << 6) | ((uint8_t)s[b + 3] & 0x3Fu);
+  if (cp == 0) cp = 0x20;                                            // U+0000 was replaced before the lexer ran (:482, :237)
+  return cp <= 0x20 || cp == 0xa0 || (cp >= 0x2000 && cp <= 0x200f) || cp == 0x202f || cp == 0x205f || cp == 0x2060 ||
+         cp == 0x2420 || cp == 0x2424 || cp == 0x3000 || cp == 0xfeff;
+}
+
+inline int end_offset_of(const char* s, int off) {                   // ToOffset + FAUtf8Size(last char) - 1 (:526-530)
+  const uint8_t c = (uint8_t)s[off];
+  const int cs = c < 0x80 ? 1 : (c & 0xE0) == 0xC0 ? 2 : (c & 0xF0) == 0xE0 ? 3 : (c & 0xF8) == 0xF0 ? 4 : 0;
+  return off + (cs > 0 ? cs - 1 : 0);
+}
+
+int finish_text(const std::string& os, char* out, int max_out) {
+  const int len = (int)os.size();                                     // includes the trailing NUL (:555, :343)
+  if (len <= max_out && out) std::memcpy(out, os.data(), os.size());
+  return len;
+}
+
+}  // namespace
+
+// blingfiretokdll.cpp:415-566.  The host only turns the (Tag, From, To) triples back into the ' '-joined
+// UTF-8 string, like the reference's ostringstream loop (:507-552), and fills the offset arrays.
+int TextToWordsWithOffsetsWithModel(const char* s, int n, char* out, int* starts, int* ends, const int max_out, void* hModel) {
   try {
-    Model* m = hModel ? (Model*)hModel : default_wbd_model();
+    Model* m = hModel ? (Model*)hModel : default_model(0);
     if (!m) return -1;
     if (n == 0) return 0;                                           // :446-448
     if (n < 0 || n > 1000000000 || !s) return -1;                   // :449-454
     if (!m->has_wbd || !m->lex_ok) { set_error("model has no lexer engine"); return -1; }
+    if (starts && max_out > 0) std::memset(starts, 0, (size_t)max_out * sizeof(int));   // :467-472
+    if (ends && max_out > 0) std::memset(ends, 0, (size_t)max_out * sizeof(int));
     std::lock_guard<std::mutex> lock(m->mu);
-    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
-    Slot& sl = m->slots[0];
-    if (!ensure_stream(sl)) return -1;
-    const size_t nb = (size_t)n;
-    if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve(2) || !sl.lex_cls.reserve(nb + 8) || !sl.lex_ncps.reserve(1) ||
-        !sl.lex_tri_count.reserve(1) || !sl.lex_tri.reserve(3 * nb + 8) || !m->h_words.reserve(3 * nb + 16))
-      return -1;
-    const int64_t offs[2] = {0, n};
-    if (!cuda_ok(cudaMemcpyAsync(sl.text.p, s, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return -1;
-    if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return -1;
-    LexLaunch X = make_lex_launch(m, sl, 0, 0, n, 1, m->d_cls_words, 1);   // MaxOut = 3 * MaxBuffSize (:492-499)
-    int nl = 0;
-    if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return -1;
-    g_launches += nl;
-    int32_t* hw = m->h_words.p;
-    if (!cuda_ok(cudaMemcpyAsync(hw, sl.lex_ncps.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return -1;
-    if (!cuda_ok(cudaMemcpyAsync(hw + 1, sl.lex_tri_count.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return -1;
-    if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
-    const int ncps = hw[0], rn = hw[1];
-    if (ncps <= 0) return -1;                                       // invalid UTF-8 or nothing decoded (:475-478)
-    if (rn < 0 || rn > 3 * ncps || rn % 3 != 0) return -1;          // :500-502
-    if (rn > 0) {
-      if (!cuda_ok(cudaMemcpyAsync(hw + 2, sl.lex_tri.p, (size_t)rn * 4, cudaMemcpyDeviceToHost, sl.stream), "D2H triples")) return -1;
-      if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
-    }
-    // code point -> byte offset of the (already validated) input, BOM skipped like the decoder
-    std::vector<int> cp_off((size_t)ncps + 1);
-    {
-      int p = (n >= 3 && (uint8_t)s[0] == 0xEF && (uint8_t)s[1] == 0xBB && (uint8_t)s[2] == 0xBF) ? 3 : 0;
-      for (int i = 0; i < ncps; ++i) {
-        cp_off[i] = p;
-        const uint8_t c = (uint8_t)s[p];
-        p += c < 0x80 ? 1 : (c & 0xE0) == 0xC0 ? 2 : (c & 0xF0) == 0xE0 ? 3 : 4;
-      }
-      cp_off[ncps] = p;
-    }
+    LexedText R;
+    if (!lex_on_gpu(m, s, n, &R)) return -1;
     std::string os;
-    os.reserve(nb + (size_t)rn / 3 + 2);
+    os.reserve((size_t)n + (size_t)R.rn / 3 + 2);
     bool added = false;
-    const int32_t* tri = hw + 2;
-    for (int i = 0; i < rn; i += 3) {
-      if (tri[i] == 4) continue;                                    // WBD_IGNORE_TAG (:511-514)
-      const int from = tri[i + 1], to = tri[i + 2];
-      if (from < 0 || from > ncps || to >= ncps || to < -1) return -1;
+    int words = 0;
+    for (int i = 0; i < R.rn; i += 3) {
+      if (R.tri[i] == 4) continue;                                  // WBD_IGNORE_TAG (:511-514)
+      const int from = R.tri[i + 1], to = R.tri[i + 2];
+      if (from < 0 || from > R.ncps || to >= R.ncps || to < -1) return -1;
+      if (to >= 0 && from < R.ncps) {
+        if (starts && words < max_out) starts[words] = R.cp_off[(size_t)from];
+        if (ends && words < max_out) ends[words] = end_offset_of(s, R.cp_off[(size_t)to]);
+      }
+      ++words;
       if (added) os.push_back(' ');
-      for (int b = cp_off[from]; b < cp_off[to + 1]; ++b) {
+      for (int b = R.cp_off[(size_t)from]; b < R.cp_off[(size_t)to + 1]; ++b) {
         char c = s[b];
         if (c == 0) c = 0x20;                                       // U+0000 -> U+0020 (:482)
         if (c == ' ') c = '_';                                      // ' ' is the delimiter (:546)
@@ -800,11 +843,69 @@ int TextToWordsWithModel(const char* s, int n, char* out, const int max_out, voi
       added = true;
     }
     os.push_back('\0');                                             // :555
-    const int len = (int)os.size();
-    if (len <= max_out && out) std::memcpy(out, os.data(), os.size());
-    return len;
+    return finish_text(os, out, max_out);
   } catch (const std::exception& e) { set_error(e.what()); return -1; }
 }
-int TextToWords(const char* s, int n, char* out, const int max_out) { return TextToWordsWithModel(s, n, out, max_out, nullptr); }
+int TextToWordsWithOffsets(const char* s, int n, char* out, int* starts, int* ends, const int max_out) {
+  return TextToWordsWithOffsetsWithModel(s, n, out, starts, ends, max_out, nullptr);
+}
+int TextToWordsWithModel(const char* s, int n, char* out, const int max_out, void* hModel) {
+  return TextToWordsWithOffsetsWithModel(s, n, out, nullptr, nullptr, max_out, hModel);
+}
+int TextToWords(const char* s, int n, char* out, const int max_out) { return TextToWordsWithOffsetsWithModel(s, n, out, nullptr, nullptr, max_out, nullptr); }
+
+// blingfiretokdll.cpp:163-355.  One sentence per triple of the sentence-breaking lexer: it starts right
+// after the previous one (tags and Froms are ignored, :262-266), leading white space is dropped, '\n'
+// inside becomes ' ', sentences are joined by '\n'; what follows the last boundary is the last sentence.
+int TextToSentencesWithOffsetsWithModel(const char* s, int n, char* out, int* starts, int* ends, const int max_out, void* hModel) {
+  try {
+    Model* m = hModel ? (Model*)hModel : default_model(1);
+    if (!m) return -1;
+    if (n == 0) return 0;                                           // :206-208
+    if (n < 0 || n > 1000000000 || !s) return -1;                   // :209-214
+    if (!m->has_wbd || !m->lex_ok) { set_error("model has no lexer engine"); return -1; }
+    if (starts && max_out > 0) std::memset(starts, 0, (size_t)max_out * sizeof(int));   // :227-232
+    if (ends && max_out > 0) std::memset(ends, 0, (size_t)max_out * sizeof(int));
+    std::lock_guard<std::mutex> lock(m->mu);
+    LexedText R;
+    if (!lex_on_gpu(m, s, n, &R)) return -1;
+    std::string os;
+    os.reserve((size_t)n + 2);
+    bool added = false;
+    int count = 0, prev_end = -1;
+    auto sentence = [&](int from, int to) {
+      int first = from;
+      while (first <= to && white_cp_at(s, R.cp_off[(size_t)first])) ++first;   // FAGetFirstNonWhiteSpace (:138-150)
+      if (first > to) return;
+      if (starts && count < max_out) starts[count] = R.cp_off[(size_t)first];
+      if (ends && count < max_out) ends[count] = end_offset_of(s, R.cp_off[(size_t)to]);
+      ++count;
+      if (added) os.push_back('\n');
+      for (int b = R.cp_off[(size_t)first]; b < R.cp_off[(size_t)to + 1]; ++b) {
+        char c = s[b];
+        if (c == 0) c = 0x20;                                       // :237
+        if (c == '\n') c = ' ';                                     // '\n' is the delimiter (:292)
+        os.push_back(c);
+      }
+      added = true;
+    };
+    for (int i = 0; i < R.rn; i += 3) {
+      const int to = R.tri[i + 2];
+      if (to < -1 || to >= R.ncps) return -1;                      // (never: To is a position of the input)
+      sentence(prev_end + 1, to);
+      prev_end = to;
+    }
+    if (prev_end + 1 < R.ncps) sentence(prev_end + 1, R.ncps - 1);   // the end of the paragraph ends a sentence (:303-338)
+    os.push_back('\0');                                             // :343
+    return finish_text(os, out, max_out);
+  } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+int TextToSentencesWithOffsets(const char* s, int n, char* out, int* starts, int* ends, const int max_out) {
+  return TextToSentencesWithOffsetsWithModel(s, n, out, starts, ends, max_out, nullptr);
+}
+int TextToSentencesWithModel(const char* s, int n, char* out, const int max_out, void* hModel) {
+  return TextToSentencesWithOffsetsWithModel(s, n, out, nullptr, nullptr, max_out, hModel);
+}
+int TextToSentences(const char* s, int n, char* out, const int max_out) { return TextToSentencesWithOffsetsWithModel(s, n, out, nullptr, nullptr, max_out, nullptr); }
 
 }  // extern "C"

@@ -89,6 +89,27 @@ int TextToWords(const char* pInUtf8Str, int InUtf8StrByteCount,
 int TextToWordsWithModel(const char* pInUtf8Str, int InUtf8StrByteCount,
                                char* pOutUtf8Str, const int MaxOutUtf8StrByteCount, void* hModel);
 
+/* blingfiretokdll.h:37-38 / :35-36, blingfiretokdll.cpp:415-566 / :575-581.  TextToWords plus, for word
+ * k, the byte offset of the first byte of its first character and of the LAST byte of its last
+ * character.  Both arrays (either may be NULL) must hold MaxOutUtf8StrByteCount ints and are
+ * zero-filled first, like the reference does. */
+int TextToWordsWithOffsetsWithModel(const char* pInUtf8Str, int InUtf8StrByteCount, char* pOutUtf8Str,
+                                    int* pStartOffsets, int* pEndOffsets, const int MaxOutUtf8StrByteCount, void* hModel);
+int TextToWordsWithOffsets(const char* pInUtf8Str, int InUtf8StrByteCount, char* pOutUtf8Str,
+                           int* pStartOffsets, int* pEndOffsets, const int MaxOutUtf8StrByteCount);
+
+/* blingfiretokdll.h:33 / :31-32 / :29-30 / :27-28, blingfiretokdll.cpp:398-401 / :378-381 / :364-368 / :163-355.
+ * Splits a paragraph into sentences, '\n'-joined (a '\n' inside a sentence becomes ' '); same return
+ * convention as TextToWords.  The sentence-breaking lexer (default: sbd.bin, loaded from
+ * $BLINGFIRE_B200_SBD or <library dir>/sbd.bin on first use) runs on the GPU. */
+int TextToSentences(const char* pInUtf8Str, int InUtf8StrByteCount, char* pOutUtf8Str, const int MaxOutUtf8StrByteCount);
+int TextToSentencesWithModel(const char* pInUtf8Str, int InUtf8StrByteCount, char* pOutUtf8Str,
+                             const int MaxOutUtf8StrByteCount, void* hModel);
+int TextToSentencesWithOffsets(const char* pInUtf8Str, int InUtf8StrByteCount, char* pOutUtf8Str,
+                               int* pStartOffsets, int* pEndOffsets, const int MaxOutUtf8StrByteCount);
+int TextToSentencesWithOffsetsWithModel(const char* pInUtf8Str, int InUtf8StrByteCount, char* pOutUtf8Str,
+                                        int* pStartOffsets, int* pEndOffsets, const int MaxOutUtf8StrByteCount, void* hModel);
+
 /* ---------------------------------------------------------------------------------------
  * Additive batch entry points (new)
  * ------------------------------------------------------------------------------------- */

@@ -909,23 +909,28 @@ int bfo_text_to_ids(const bfo_model* m, const char* s, int n, int32_t* ids, int 
     return bfo_text_to_ids_with_offsets(m, s, n, ids, NULL, NULL, max_ids, unk);  /* :1619-1646 */
 }
 
-/* blingfiretokdll.cpp:415-566 (TextToWordsWithOffsetsWithModel without offsets) */
-int bfo_text_to_words(const bfo_model* m, const char* s, int n, char* out, int max_out) {
+/* blingfiretokdll.cpp:415-566 (TextToWordsWithOffsetsWithModel); starts/ends may be NULL */
+int bfo_text_to_words_with_offsets(const bfo_model* m, const char* s, int n, char* out, int* starts, int* ends, int max_out) {
     if (!m || !m->has_wbd) return -1;
     if (n == 0) return 0;
     if (n < 0 || n > MAX_ARR_SIZE || !s) return -1;
-    int* buf = (int*)malloc(sizeof(int) * (size_t)n * 4);
-    int* res = buf + n;
+    int* buf = (int*)malloc(sizeof(int) * (size_t)n * 5);
+    int* offs = buf + n; int* res = buf + 2 * (size_t)n;
     int ret = -1;
-    const int size = str_utf8_to_array(s, n, buf, NULL, n);
+    if (starts && max_out > 0) memset(starts, 0, sizeof(int) * (size_t)max_out);   /* :467-472 */
+    if (ends && max_out > 0) memset(ends, 0, sizeof(int) * (size_t)max_out);
+    const int size = str_utf8_to_array(s, n, buf, offs, n);
     if (size <= 0 || size > n) { free(buf); return -1; }
     for (int i = 0; i < size; ++i) if (buf[i] == 0) buf[i] = 0x20;
     const int rn = bfo_lex_process(m, buf, size, res, size * 3);
     if (rn > size * 3 || rn % 3 != 0 || rn < 0) { free(buf); return -1; }
-    char* acc = (char*)malloc((size_t)n * 2 + 16); size_t len = 0; int added = 0;
+    char* acc = (char*)malloc((size_t)n * 2 + 16); size_t len = 0; int added = 0, words = 0;
     for (int i = 0; i < rn; i += 3) {
         if (res[i] == WBD_IGNORE_TAG) continue;
         const int from = res[i + 1], to = res[i + 2];
+        if (starts && words < max_out) starts[words] = offs[from];                 /* :523-525 */
+        if (ends && words < max_out) { const int cs = utf8_size_of_lead(s + offs[to]); ends[words] = offs[to] + (cs > 0 ? cs - 1 : 0); }
+        words++;
         if (added) acc[len++] = ' ';
         char* p = acc + len; char* q = p; int budget = n;
         for (int k = from; k <= to; ++k) {
@@ -941,6 +946,64 @@ int bfo_text_to_words(const bfo_model* m, const char* s, int n, char* out, int m
     acc[len++] = 0;
     ret = (int)len;
     if (ret <= max_out && out) memcpy(out, acc, len);
+    free(acc); free(buf);
+    return ret;
+}
+int bfo_text_to_words(const bfo_model* m, const char* s, int n, char* out, int max_out) {
+    return bfo_text_to_words_with_offsets(m, s, n, out, NULL, NULL, max_out);
+}
+
+/* blingfiretokdll.cpp:163-355 (TextToSentencesWithOffsetsWithModel); starts/ends may be NULL.
+ * One sentence per triple: From = previous To + 1 (tags and Froms of the triples are ignored), leading
+ * white space skipped, '\n' inside a sentence -> ' ', sentences joined by '\n', the rest of the
+ * paragraph after the last boundary is the last sentence. */
+static size_t sentence_append(const char* s, const int* buf, const int* offs, int from, int to, int n, char* acc, size_t len,
+                              int* added, int* count, int* starts, int* ends, int max_out, int* err) {
+    int delta = 0;
+    while (delta < to - from + 1 && is_white(buf[from + delta])) delta++;           /* FAGetFirstNonWhiteSpace :138-150 */
+    if (delta >= to - from + 1) return len;
+    if (starts && *count < max_out) starts[*count] = offs[from + delta];
+    if (ends && *count < max_out) { const int cs = utf8_size_of_lead(s + offs[to]); ends[*count] = offs[to] + (cs > 0 ? cs - 1 : 0); }
+    (*count)++;
+    if (*added) acc[len++] = '\n';
+    char* p = acc + len; char* q = p;
+    for (int k = from + delta; k <= to; ++k) {
+        char* nx = int_to_utf8(buf[k], q, n - (int)(q - p));
+        if (!nx) { *err = 1; return len; }
+        q = nx;
+    }
+    for (char* c = p; c < q; ++c) if (*c == '\n') *c = ' ';
+    size_t tl = 0; while (p + tl < q && p[tl] != 0) tl++;                             /* appended as a C string */
+    *added = 1;
+    return len + tl;
+}
+int bfo_text_to_sentences_with_offsets(const bfo_model* m, const char* s, int n, char* out, int* starts, int* ends, int max_out) {
+    if (!m || !m->has_wbd) return -1;
+    if (n == 0) return 0;
+    if (n < 0 || n > MAX_ARR_SIZE || !s) return -1;
+    int* buf = (int*)malloc(sizeof(int) * (size_t)n * 5);
+    int* offs = buf + n; int* res = buf + 2 * (size_t)n;
+    if (starts && max_out > 0) memset(starts, 0, sizeof(int) * (size_t)max_out);
+    if (ends && max_out > 0) memset(ends, 0, sizeof(int) * (size_t)max_out);
+    const int size = str_utf8_to_array(s, n, buf, offs, n);
+    if (size <= 0 || size > n) { free(buf); return -1; }
+    for (int i = 0; i < size; ++i) if (buf[i] == 0) buf[i] = 0x20;
+    const int rn = bfo_lex_process(m, buf, size, res, size * 3);
+    if (rn > size * 3 || rn % 3 != 0 || rn < 0) { free(buf); return -1; }
+    char* acc = (char*)malloc((size_t)n * 2 + 16); size_t len = 0; int added = 0, count = 0, err = 0, prev_end = -1;
+    for (int i = 0; i < rn && !err; i += 3) {
+        const int from = prev_end + 1, to = res[i + 2];
+        prev_end = to;
+        len = sentence_append(s, buf, offs, from, to, n, acc, len, &added, &count, starts, ends, max_out, &err);
+    }
+    if (!err && prev_end + 1 < size)                                                  /* :303-338 */
+        len = sentence_append(s, buf, offs, prev_end + 1, size - 1, n, acc, len, &added, &count, starts, ends, max_out, &err);
+    int ret = -1;
+    if (!err) {
+        acc[len++] = 0;
+        ret = (int)len;
+        if (ret <= max_out && out) memcpy(out, acc, len);
+    }
     free(acc); free(buf);
     return ret;
 }

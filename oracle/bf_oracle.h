@@ -43,6 +43,10 @@ int bfo_text_to_ids_with_offsets(const bfo_model* m, const char* utf8, int nbyte
 /* blingfiretokdll.cpp:415-566 (TextToWordsWithOffsetsWithModel, offsets omitted). */
 int bfo_text_to_words(const bfo_model* m, const char* utf8, int nbytes,
                       char* out, int max_out);
+/* blingfiretokdll.cpp:415-566 with the offset arrays (either may be NULL; both are zero-filled first, :467-472) */
+int bfo_text_to_words_with_offsets(const bfo_model* m, const char* utf8, int nbytes, char* out, int* starts, int* ends, int max_out);
+/* blingfiretokdll.cpp:163-355 (TextToSentencesWithOffsetsWithModel) over a sentence-breaking [wbd] model (sbd.bin) */
+int bfo_text_to_sentences_with_offsets(const bfo_model* m, const char* utf8, int nbytes, char* out, int* starts, int* ends, int max_out);
 
 /* FALexTools_t.h:403-421 (Process): raw (Tag,From,To) triples over UTF-32 input. */
 int bfo_lex_process(const bfo_model* m, const int* in, int n, int* out, int max_out);

@@ -50,6 +50,9 @@ class Oracle:
         L.bfo_text_to_ids_with_offsets.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p,
                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.bfo_text_to_words.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        for fn in ("bfo_text_to_words_with_offsets", "bfo_text_to_sentences_with_offsets"):
+            getattr(L, fn).argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_int]
         L.bfo_text_to_ids_batch.restype = ctypes.c_int64
         L.bfo_text_to_ids_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -81,6 +84,16 @@ class Oracle:
         en = np.full(max_ids, -7, np.int32)
         n = self.lib.bfo_text_to_ids_with_offsets(h, data, len(data), ids.ctypes.data, st.ctypes.data, en.ctypes.data, max_ids, unk)
         return n, ids, st, en
+
+    def split(self, kind, h, data: bytes, max_out=None):
+        """(ret, text, starts, ends) of the words / sentences call with offsets."""
+        fn = self.lib.bfo_text_to_words_with_offsets if kind == "words" else self.lib.bfo_text_to_sentences_with_offsets
+        max_out = max_out if max_out is not None else 2 * len(data) + 16
+        out = ctypes.create_string_buffer(max(max_out, 1))
+        st = np.full(max(max_out, 1), -7, np.int32)
+        en = np.full(max(max_out, 1), -7, np.int32)
+        n = fn(h, data, len(data), out, st.ctypes.data, en.ctypes.data, max_out)
+        return n, (out.raw[: max(n, 0)] if n <= max_out else b""), st, en
 
     def text_to_words(self, h, data: bytes, max_out=None):
         max_out = max_out if max_out is not None else 2 * len(data) + 16
@@ -116,6 +129,13 @@ class Ref:
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.TextToWords.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.TextToWordsWithModel.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        for fn in ("TextToWordsWithOffsetsWithModel", "TextToSentencesWithOffsetsWithModel"):
+            getattr(L, fn).argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int, ctypes.c_void_p]
+
+    def split(self, kind, data: bytes, model=None, max_out=None):
+        return split_call(getattr(self.lib, "TextToWordsWithOffsetsWithModel" if kind == "words" else
+                                  "TextToSentencesWithOffsetsWithModel"), data, model, max_out)
 
     def load(self, path):
         h = self.lib.LoadModel(path.encode())
@@ -145,6 +165,18 @@ class Ref:
         else:
             n = self.lib.TextToWordsWithModel(data, len(data), out, max_out, ctypes.c_void_p(model))
         return n, out.raw[: max(n, 0)] if n <= max_out else b""
+
+
+def split_call(fn, data: bytes, model, max_out=None):
+    """Calls a TextTo{Words,Sentences}WithOffsetsWithModel-shaped function: (ret, text, starts, ends) with the
+    offset arrays sized max_out like the reference wants them (it zero-fills max_out entries)."""
+    max_out = max_out if max_out is not None else 2 * len(data) + 16
+    out = ctypes.create_string_buffer(max(max_out, 1))
+    st = np.full(max(max_out, 1), -7, np.int32)
+    en = np.full(max(max_out, 1), -7, np.int32)
+    n = fn(data, len(data), out, st.ctypes.data, en.ctypes.data, max_out, ctypes.c_void_p(model) if model else None)
+    text = out.raw[: max(n, 0)] if n <= max_out else b""
+    return n, text, st, en
 
 
 def read_lines(name, limit=None, drop_empty=True):

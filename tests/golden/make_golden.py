@@ -49,7 +49,7 @@ def b64(b):
 def main():
     r = Ref()
     out = {"generator": "tests/golden/make_golden.py over oracle/_ref (the reference built from its own sources)",
-           "edge_cases": [], "digests": [], "words": [], "ids_with_offsets": []}
+           "edge_cases": [], "digests": [], "words": [], "ids_with_offsets": [], "split_with_offsets": []}
     handles = {}
     for m, unk in MODELS:
         handles[m] = r.load(model_path(m))
@@ -86,6 +86,17 @@ def main():
             n, ids, st, en = r.text_to_ids_with_offsets(handles[m], data, 256, unk)
             out["ids_with_offsets"].append({"model": m, "unk": unk, "input": b64(data), "count": int(n),
                                             "ids": ids[:n].tolist(), "starts": st[:n].tolist(), "ends": en[:n].tolist()})
+    # words / sentences with offsets: default models (embedded wbd / sbd) and the files in ldbsrc
+    para = [b" ".join(read_lines("test.txt")[i:i + 6]) for i in range(0, 240, 6)] + read_lines("test.multi.txt")[:40]
+    para += [b"Hello world! How are you?  I am fine.\nThanks. ", b"  \n ", b"No terminator", b"A.\x00B. C", b"\xef\xbb\xbfBom. Second one.",
+             "Dr. Smith went to Washington. He arrived at 5 p.m. It was late!".encode(), "一。二。三".encode()]
+    for kind in ("words", "sentences"):
+        for data in para + EDGE[:16]:
+            for max_out in (None, 3):
+                n, text, st, en = r.split(kind, data, None, max_out)
+                k = max_out if max_out is not None else 2 * len(data) + 16
+                out["split_with_offsets"].append({"kind": kind, "input": b64(data), "max_out": k, "ret": int(n), "out": b64(text),
+                                                  "starts": st[:max(k, 1)].tolist()[:64], "ends": en[:max(k, 1)].tolist()[:64]})
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print("wrote golden.json", os.path.getsize(os.path.join(HERE, "golden.json")), "bytes")

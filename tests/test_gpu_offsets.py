@@ -110,3 +110,56 @@ def test_sp_offsets_vs_oracle(bf, name, unk):
     L.TextToIdsWithOffsets_wp.argtypes = L.TextToIdsWithOffsets_sp.argtypes
     assert L.TextToIdsWithOffsets_wp(ctypes.c_void_p(h), b"hello world", 11, a.ctypes.data, b.ctypes.data, c.ctypes.data, 64, unk) == 0
     bf.free_model(h)
+
+
+def _split_via_capi(bf, fn_name, data, model, max_out):
+    from _common import split_call
+    L = bf.lib()
+    f = getattr(L, fn_name)
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    return split_call(f, data, model, max_out)
+
+
+def test_words_and_sentences_with_offsets_vs_golden(bf):
+    """TextTo{Words,Sentences}WithOffsetsWithModel with the default models (wbd.bin / sbd.bin next to the
+    library; the reference embeds the same bytes) against what the reference itself returned."""
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        golden = json.load(f)
+    n_checked = 0
+    for c in golden["split_with_offsets"]:
+        data = base64.b64decode(c["input"])
+        fn = "TextToWordsWithOffsetsWithModel" if c["kind"] == "words" else "TextToSentencesWithOffsetsWithModel"
+        n, text, st, en = _split_via_capi(bf, fn, data, None, c["max_out"])
+        assert n == c["ret"], (c["kind"], data[:40], bf.last_error())
+        assert text == base64.b64decode(c["out"]), (c["kind"], data[:40])
+        assert st[:64].tolist() == c["starts"] and en[:64].tolist() == c["ends"], (c["kind"], data[:40])
+        n_checked += 1
+    assert n_checked > 300
+
+
+@pytest.mark.parametrize("kind,name", [("sentences", "sbd.bin"), ("words", "wbd.bin"), ("words", "wbd_chuni.bin")])
+def test_words_and_sentences_vs_oracle(bf, kind, name):
+    """The same calls with a model handle, on multilingual paragraphs, against the oracle; and the plain
+    spellings (no offsets, default model) through the Python wrapper."""
+    h = bf.load_model(model_path(name))
+    o = Oracle()
+    ho = o.load(model_path(name))
+    lines = read_lines("test.multi.txt")[:600] + read_lines("test.txt")[:600]
+    docs = [b" ".join(lines[i:i + 5]) for i in range(0, len(lines), 5)] + [b"\xef\xbb\xbfBom. Next!", b"abc \xff def", b" \n ", b"x",
+                                                                          b"One.\nTwo?\r\nThree!  ", "句子一。句子二！".encode()]
+    fn = "TextToWordsWithOffsetsWithModel" if kind == "words" else "TextToSentencesWithOffsetsWithModel"
+    for d in docs:
+        for max_out in (None, 2):
+            n1, t1, s1, e1 = o.split(kind, ho, d, max_out)
+            n2, t2, s2, e2 = _split_via_capi(bf, fn, d, h, max_out)
+            assert n1 == n2 and t1 == t2, (kind, d[:40])
+            assert (s1 == s2).all() and (e1 == e2).all(), (kind, d[:40])
+    if kind == "sentences":
+        assert bf.text_to_sentences("Hello world! How are you?  Fine.") == bf.text_to_sentences_with_model(h, "Hello world! How are you?  Fine.")
+        text, st, en = bf.utf8text_to_sentences_with_offsets(b"Hello world! How are you?")
+        assert text == b"Hello world!\nHow are you?" and st.tolist() == [0, 13] and en.tolist() == [11, 24]
+    elif name == "wbd.bin":
+        text, st, en = bf.utf8text_to_words_with_offsets("naïve café.".encode())
+        assert text == "naïve café .".encode() and st.tolist() == [0, 7, 12] and en.tolist() == [5, 11, 12]
+    bf.free_model(h)
