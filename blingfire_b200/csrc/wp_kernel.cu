@@ -29,7 +29,7 @@ constexpr int kWarpsPerCta = 16;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kWin = 576;            // window capacity in code points (per warp)
 constexpr int kBlockBytes = 128;     // bytes consumed per decode step (32 lanes x uchar4)
-constexpr int kWarpSmem = kWin * (2 + 4 + 1 + 2 + 2);   // cls u16, ids_at i32, has_id u8, starts u16, order u16
+constexpr int kWarpSmem = kWin * (2 + 4 + 1 + 2 + 2);   // cls u16, ids_at i32, meta u8, starts u16, order u16
 
 static_assert(kWin % 32 == 0, "window must be a multiple of the warp size");
 
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
   int32_t* ids_at = reinterpret_cast<int32_t*>(wbase);
   uint16_t* cls = reinterpret_cast<uint16_t*>(wbase + kWin * 4);
   uint16_t* starts = reinterpret_cast<uint16_t*>(wbase + kWin * 6);
-  uint8_t* has_id = wbase + kWin * 8;
+  uint8_t* meta = wbase + kWin * 8;          // top-level class | kHasId (wp_core.cuh)
   uint16_t* order = reinterpret_cast<uint16_t*>(wbase + kWin * 9 + (kWin & 1));
 
   const uint32_t* text32 = reinterpret_cast<const uint32_t*>(p.text);
@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
           for (int k = 0; k < 4; ++k) {
             if (dcd.start_mask & (1u << k)) {
               const uint32_t cp = dcd.cp[k];
-              cls[idx++] = cp < 128 ? top.ascii_cls[cp] : __ldg(g.cls_of_cp + cp);
+              const uint16_t c = cp < 128 ? top.ascii_cls[cp] : __ldg(g.cls_of_cp + cp);
+              cls[idx] = c;
+              meta[idx] = top.tc_of_class[c];          // also clears the position's kHasId bit
+              ++idx;
             }
           }
           m += __shfl_sync(0xffffffffu, incl, 31);
@@ -245,16 +248,15 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
         __syncwarp();
 
         // ---- sync points -> chunk starts ----
-        for (int i = lane; i < (m + 3) / 4; i += 32) reinterpret_cast<uint32_t*>(has_id)[i] = 0u;
         int nst = 0;
         for (int p0 = 0; p0 < m; p0 += 32) {
           const int q = p0 + lane;
           bool flag = false;
           if (q < m) {
-            const unsigned t2 = top.tc_of_class[cls[q]];
+            const unsigned t2 = meta[q];
             if (q == 0) flag = true;
             else {
-              const unsigned t1 = top.tc_of_class[cls[q - 1]];
+              const unsigned t1 = meta[q - 1];
               const bool sync = !((top.cross[t1] >> t2) & 1ull);
               flag = sync && top.ttop[t2] != 0xFF;
             }
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
             if (fe > limit) fe = limit;
             if (i == 0 && first) fb = -1;
             if (fb < fe) {
-              const int r = wp_chunk<TE>(top, g, cls, m, at_end, fb, fe, p.unk_id, ids_at, has_id);
+              const int r = wp_chunk<TE>(top, g, cls, m, at_end, fb, fe, p.unk_id, ids_at, meta);
               carry = max(carry, r);
             }
           }
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
         // ---- ordered compaction of the ids of positions [0, carry) ----
         for (int p0 = 0; p0 < carry; p0 += 32) {
           const int q = p0 + lane;
-          const bool f = q < carry && has_id[q];
+          const bool f = q < carry && (meta[q] & kHasId);
           const unsigned bal = __ballot_sync(0xffffffffu, f);
           const int rank = out + __popc(bal & lanemask_lt());
           if (f && rank < p.max_ids) row[rank] = ids_at[q];
@@ -331,8 +333,9 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
         for (int k0 = 0; k0 < rest; k0 += 32) {
           const int k = k0 + lane;
           const uint16_t v = k < rest ? cls[carry + k] : (uint16_t)0;
+          const uint8_t mt = k < rest ? (uint8_t)(meta[carry + k] & ~kHasId) : (uint8_t)0;
           __syncwarp();
-          if (k < rest) cls[k] = v;
+          if (k < rest) { cls[k] = v; meta[k] = mt; }
         }
         __syncwarp();
         m = rest;

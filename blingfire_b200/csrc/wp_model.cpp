@@ -52,7 +52,11 @@ void build_wp_blob(const LexerTables& T, WpBlob* out) {
   uint8_t* b = out->bytes.data();
   for (int cp = 0; cp < 128; ++cp) reinterpret_cast<uint16_t*>(b + L.off_ascii)[cp] = T.cls_of_cp[cp];
   std::memcpy(b + L.off_tc, F.tc_of_class.data(), NC1);
-  std::memcpy(b + L.off_ttop, F.ttop.data(), (size_t)F.K * F.NT);
+  // bit 7 of a top-level transition = "the destination is final" (wp_core.cuh kTopFinal); 0xFF stays "none"
+  for (size_t i = 0; i < (size_t)F.K * F.NT; ++i) {
+    const uint8_t d = F.ttop[i];
+    b[L.off_ttop + i] = (d != 0xFF && F.top_final[d]) ? (uint8_t)(d | 0x80) : d;
+  }
   std::memcpy(b + L.off_cross, F.cross.data(), (size_t)F.NT * 8);
   std::memcpy(b + L.off_final, F.top_final.data(), (size_t)F.K);
   std::memcpy(b + L.off_tag, F.top_tag.data(), (size_t)F.K * 4);
