@@ -69,7 +69,8 @@ template <typename T> inline T bf_ldg(const T* p) { return *p; }
 // One step in the global table.  `q` must be a valid state.
 template <typename TE>
 BF_HD uint32_t wp_step(const WpGlobal<TE>& g, uint32_t q, uint32_t c) {
-  const uint32_t v = bf_ldg(g.trans + (size_t)q * g.NC1 + c);
+  // 16-bit tables have < 65 536 states and <= 65 537 columns: the flat index fits 32 bits
+  const uint32_t v = sizeof(TE) == 2 ? bf_ldg(g.trans + (uint32_t)(q * g.NC1 + c)) : bf_ldg(g.trans + ((size_t)q * g.NC1 + c));
   return v == TeTraits<TE>::none ? kNone32 : v;
 }
 template <typename TE>
@@ -110,14 +111,16 @@ BF_HD bool wp_word(const WpTop& t, const WpGlobal<TE>& g, const uint16_t* cls, i
     first_from_staged = row >= 0;
     uint32_t fq = kNone32;
     int fpos = -1;
-    for (; j < bound; ++j) {
-      const uint32_t c = cls[w0 + j];
-      uint32_t d;
-      if (first_from_staged) { d = wp_row_step<TE>(t.staged_rows, row, g.NC1, c); first_from_staged = false; }
-      else d = wp_step(g, q, c);
-      if (d == kNone32) break;
-      if (d >= g.first_final) { fq = d; fpos = j; }
-      q = d;
+    if (j < bound) {
+      // the first hop comes from the staged copy of the row when there is one; then the table
+      uint32_t d = first_from_staged ? wp_row_step<TE>(t.staged_rows, row, g.NC1, cls[w0 + j]) : wp_step(g, q, cls[w0 + j]);
+      first_from_staged = false;
+      while (d != kNone32) {
+        if (d >= g.first_final) { fq = d; fpos = j; }
+        q = d;
+        if (++j >= bound) break;
+        d = wp_step(g, q, cls[w0 + j]);
+      }
     }
     if (j == L) {                        // right anchor only when the walk consumed the span (:280-290)
       uint32_t d;
