@@ -7,15 +7,16 @@
 // GetDestOw.  Integer work plus fp64 adds in the reference's operand order (no FMA: there is no
 // multiply to contract).
 //
-// One document per warp, persistent grid, documents handed out by an atomic counter.  Symbols
-// live in a shared-memory window when the document fits, in the warp's global arena otherwise.
-//   Unigram: lanes enumerate the arcs of up to 32 start positions in parallel; the relaxation
-//            runs in start order (the reference's order: ties keep the earlier start) with the
-//            arcs of one start spread over the lanes; back-trace by one lane; ordered emission.
-//   BPE:     tokens never contain U+2581 past their first symbol (checked at load), so the
-//            U+2581-delimited segments are independent: one lane per segment takes the bpe-opt
-//            whole-word shortcut; the remaining segments are processed warp-cooperatively
-//            (arc enumeration -> (rank,id,start) bitonic sort -> the reference's greedy claim).
+// One document per warp, persistent grid, documents handed out by an atomic counter.  Three paths
+// (DESIGN.md section 4), each behind the other:
+//   sp_unigram_fast  Unigram models with tokens <= 16 symbols, documents <= 576 symbols: everything
+//                    in shared memory, the relaxation in a register window (lane = position)
+//   sp_bpe_fast      byte-level BPE models: a 512-symbol window slides over the document, cut at
+//                    U+2581 (segments are independent); lanes re-dealt per phase (per segment, per
+//                    start, per arc); long segments split at the positions no token spans
+//   sp_doc_generic   everything else (any length, any token length, byte offsets): the document in
+//                    the warp's global arena; Unigram with an arc tile in start order, BPE with the
+//                    reference's arc vector, bitonic sort and sequential claim
 #include "sp_kernel.cuh"
 
 #include <cfloat>
@@ -26,7 +27,6 @@ namespace bfb200 {
 
 namespace {
 
-constexpr int kSpWin = kSpWindow;         // symbols in the shared-memory window
 constexpr int kTileArcs = 1024;           // arc slots of one tile of start positions (Unigram)
 constexpr int kArcsPerSym = 8;            // warp-private BPE arc scratch, per symbol of capacity
 
@@ -492,10 +492,10 @@ __device__ int sp_bpe(const SpModelDev& m, Work& w, int N, int32_t* row, int max
   return sp_emit(w, ids_at, N, row, max_ids, unk, m.id_offset, false, lane, oo);
 }
 
-// One document through the general path: any length (arena), any token length, offsets if wanted.
-// `ws` is the warp's shared-memory workspace (nullptr: none, everything goes to the arena `wa`).
+// One document through the general path: any length, any token length, offsets if wanted.  The
+// document lives in the warp's arena workspace `wa`.
 template <bool kBpe>
-__device__ int sp_doc_generic(const SpLaunch& p, const SpModelDev& m, Work* ws, Work& wa, const ArcScratch& scratch, int64_t doc,
+__device__ int sp_doc_generic(const SpLaunch& p, const SpModelDev& m, Work& wa, const ArcScratch& scratch, int64_t doc,
                               int64_t lo, int64_t hi, int64_t padded_bytes, int lane, int* error_flag) {
   const bool want_offsets = p.starts != nullptr;              // offsets ride in the arena workspace only
   const int64_t n = hi - lo;
@@ -505,10 +505,9 @@ __device__ int sp_doc_generic(const SpLaunch& p, const SpModelDev& m, Work* ws, 
       const int nraw = sp_raw_symbols(m, p.text, lo, hi, padded_bytes, nullptr, nullptr, false, lane);
       bool ok = nraw > 0;
       const int64_t need = (m.norm_count ? 2 * (n + 1) : (int64_t)nraw) + 2;   // staging bound (:1423)
-      const bool fits_smem = ws != nullptr && !want_offsets && need <= kSpWin;
-      if (ok && !fits_smem && need > (int64_t)p.arena_cap) { ok = false; if (lane == 0) atomicExch(error_flag, 2); }
+      if (ok && need > (int64_t)p.arena_cap) { ok = false; if (lane == 0) atomicExch(error_flag, 2); }
       if (ok) {
-        Work& w = fits_smem ? *ws : wa;
+        Work& w = wa;
         int32_t* boff = w.boff_a; int32_t* boff_other = w.boff_b;           // nullptr unless offsets are wanted
         sp_raw_symbols(m, p.text, lo, hi, padded_bytes, w.sym, boff, true, lane);
         __syncwarp();
@@ -1064,7 +1063,7 @@ __global__ void __launch_bounds__(kBWarps * 32, kBCtasPerSm) sp_bpe_kernel(const
       if (fast_model)
         result = sp_bpe_fast(m, w, scratch, p.text, lo, hi, padded_bytes, p.ids + doc * (int64_t)p.max_ids, p.max_ids, p.unk_id, delim, lane);
       if (result == kUFallback)
-        result = sp_doc_generic<true>(p, m, nullptr, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
+        result = sp_doc_generic<true>(p, m, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
     }
     if (lane == 0) p.counts[doc] = result;
     __syncwarp();
@@ -1323,7 +1322,7 @@ __global__ void __launch_bounds__(kUWarps * 32, kUCtasPerSm) sp_unigram_kernel(c
       if (fast_model && n <= 4ll * kUCap)                                 // a code point takes at most 4 bytes
         result = sp_unigram_fast(m, w, p.text, lo, hi, padded_bytes, p.ids + doc * (int64_t)p.max_ids, p.max_ids, p.unk_id, lane);
       if (result == kUFallback)
-        result = sp_doc_generic<false>(p, m, nullptr, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
+        result = sp_doc_generic<false>(p, m, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
     }
     if (lane == 0) p.counts[doc] = result;
     __syncwarp();

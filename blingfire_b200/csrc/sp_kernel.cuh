@@ -1,5 +1,6 @@
 // sp_kernel.cuh -- launch interface of the [pos-dict] (SentencePiece-style) engines: Unigram-LM
-// best path and BPE over the Mealy MPH automaton (sp_kernel.cu).
+// best path and BPE over the Mealy MPH automaton (sp_kernel.cu): a shared-memory fast path per family,
+// the general path in a per-warp global arena behind it.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -8,10 +9,6 @@
 #include "seg_tables.h"
 
 namespace bfb200 {
-
-// symbols (after normalisation staging) a document may have to be served from shared memory;
-// 8 warps x 27 KB of workspace = 216 KB per CTA
-constexpr int kSpWindow = 896;
 
 struct SpModelDev {
   const DaEntry* da;             // double-array automaton
@@ -46,7 +43,7 @@ struct SpLaunch {
   int32_t* ends;
   int max_ids, unk_id;
   unsigned long long* work_counter;
-  // per-warp global scratch for documents that do not fit the shared-memory window
+  // per-warp global scratch for the documents (or segments) the fast paths do not hold
   uint8_t* arena;                // [grid_warps][arena_stride] bytes
   int64_t arena_stride;          // bytes per warp
   int arena_cap;                 // symbols a warp's arena region can hold
