@@ -239,7 +239,7 @@ SpModelDev make_sp_model(const Model* m) {
   d.da = m->d_da; d.root = S.root; d.sym_of_cp = m->d_sym; d.info = m->d_info; d.info_count = (int)S.info.size();
   d.norm_count = S.has_charmap ? m->d_norm_count : nullptr; d.norm_first = m->d_norm_first; d.norm_values = m->d_norm_values;
   d.tok_algo = S.tok_algo; d.id_offset = S.id_offset; d.use_raw_bytes = S.use_raw_bytes; d.no_dummy_prefix = S.no_dummy_prefix;
-  d.delim_inside_tokens = S.delim_inside_tokens; d.max_arc_len = S.max_arc_len;
+  d.delim_inside_tokens = S.delim_inside_tokens; d.delim_is_token = S.delim_is_token; d.max_arc_len = S.max_arc_len;
   d.bpe_ord = S.bpe_ord_ok ? m->d_bpe_ord : nullptr; d.bpe_id_of_ord = m->d_bpe_id_of_ord;
   d.bpe_singles_first = S.bpe_singles_first;
   return d;

@@ -186,6 +186,14 @@ bool build_seg_tables(const LdbImage& ldb, SegTables* T, std::string* err) {
   }
   T->root = base[0];
   if (T->root == 0) { *err = "initial state has no transitions"; return false; }
+  {
+    const uint16_t ds = T->sym_of_cp[kSpDelim];
+    T->delim_is_token = false;
+    if (ds != kNoSym) {
+      const DaEntry& e = T->da[(size_t)T->root + ds];
+      T->delim_is_token = e.check == T->root && (e.dst & kDaFinalBit) != 0;
+    }
+  }
 
   // ---- charmap ----
   T->has_charmap = charmap_dump >= 0;

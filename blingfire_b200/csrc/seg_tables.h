@@ -53,6 +53,7 @@ struct SegTables {
   std::vector<SegInfo> info;            // [max_key+1]; id == INT32_MIN marks an unusable row
   int max_arc_len = 0;                  // longest path from the root (symbols)
   bool delim_inside_tokens = false;     // some token has U+2581 past its first symbol
+  bool delim_is_token = false;          // "U+2581" alone is a token: a start on U+2581 always has an arc
 
   // BPE family: dense ordinal of a key in the arc sort order (rank descending for with-merges,
   // then id); -1 for an unusable row.  bpe_id_of_ord inverts it.  bpe_ord_ok: ordinals fit 20 bits.

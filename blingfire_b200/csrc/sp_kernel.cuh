@@ -21,6 +21,7 @@ struct SpModelDev {
   const int32_t* norm_values;
   int tok_algo, id_offset;
   bool use_raw_bytes, no_dummy_prefix, delim_inside_tokens;
+  bool delim_is_token;           // "U+2581" alone is a token (seg_tables.h)
   int max_arc_len;
   // BPE family: ordinal of a key in the arc sort order and its inverse (seg_tables.h); nullptr when
   // the ordinals do not fit a sort key (the streaming BPE path is then off)

@@ -117,7 +117,10 @@ def test_ragged_invalid_and_long_documents(bf, oracle, name, unk):
     docs = [b"", b" ", b"  a  b  ", b"\xef\xbb\xbf", b"\xef\xbb\xbfhello", b"abc \xff def", b"hello\x00world", b"a" * 400,
             b"-" * 300, b"-" * 3000, b"\xc2\xa0nbsp\xc2\xa0", "▁already▁marked ▁".encode(), "我爱北京".encode() * 200,
             b"\t\ttabs\n\nnl  ", b"x", b"!", "é".encode() * 900, ("word " * 1500).encode(), b"ab" * 2500,
-            b" ".join(lines[:400]), b"".join(lines[400:500])]
+            b" ".join(lines[:400]), b"".join(lines[400:500]),
+            # several windows, then an invalid byte / a truncated sequence: 0 ids even when MaxIds was reached long before
+            b" ".join(lines[:100]) + b"\xff", b" ".join(lines[100:200]) + b" \xe2\x82", b"\x80" + b" ".join(lines[200:300]),
+            b" ".join(lines[3000:3200]), ("ﬁ ½ ™ " * 800).encode()]
     for _ in range(2500):
         d = b" ".join(rng.choice(lines) for _ in range(rng.randint(1, 14)))
         r = rng.random()
