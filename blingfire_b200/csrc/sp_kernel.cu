@@ -1219,13 +1219,104 @@ __device__ int unigram_window(const SpModelDev& m, const UWork& w, int N, double
   return out;
 }
 
+// The whole document in one window: one fused decode + charmap pass into stage[], one collapse pass.
+// kUFallback when it has more than kUCap symbols after the charmap (the streamed form takes over).
+__device__ int unigram_whole(const SpModelDev& m, const UWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
+                               int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane) {
+  const unsigned full = 0xffffffffu;
+  int64_t lo = lo0;
+  if (hi - lo >= 3) {
+    const uint32_t b0 = __ldg(text + lo), b1 = __ldg(text + lo + 1), b2 = __ldg(text + lo + 2);
+    if (b0 == 0xEF && b1 == 0xBB && b2 == 0xBF) lo += 3;      // FAStrUtf8ToArray skips the BOM
+  }
+  if (hi <= lo) return 0;                                      // no symbols (:1409)
+  const int64_t n = hi - lo0;
+  const bool cm = m.norm_count != nullptr;
+  // ---- pass 1: decode + charmap (FANormalize, FAUtils_cl.h:311-369), dummy prefix included (:1372,:1432) ----
+  int total = 0;
+  if (!m.no_dummy_prefix) {
+    const unsigned nc = cm ? (unsigned)__ldg(m.norm_count + kSpDelim) : 0xFFu;
+    if (nc == 0xFFu) { if (lane == 0) w.stage[0] = kSpDelim; total = 1; }
+    else {
+      const uint32_t f = __ldg(m.norm_first + kSpDelim);
+      if (lane == 0) for (unsigned k = 0; k < nc; ++k) w.stage[k] = __ldg(m.norm_values + f + k);
+      total = (int)nc;
+    }
+  }
+  {
+    const uint32_t* text32 = reinterpret_cast<const uint32_t*>(text);
+    unsigned bad = 0, sumlen = 0;
+    for (int64_t bpos = lo; bpos < hi;) {
+      const int64_t bs = bpos & ~(int64_t)3;
+      const int64_t pos0 = bs + lane * 4;
+      uint32_t w0, w1;
+      utf8_load_words(text32, pos0, padded_bytes, &w0, &w1);
+      const Utf8Lane d = utf8_decode_lane(w0, w1, pos0, bpos, hi);
+      bad |= d.bad; sumlen += d.sumlen;
+      unsigned nck[4]; int c = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        nck[k] = 0xFFu;
+        if (d.start_mask & (1u << k)) {
+          if (cm) nck[k] = (unsigned)__ldg(m.norm_count + d.cp[k]);
+          c += nck[k] == 0xFFu ? 1 : (int)nck[k];
+        }
+      }
+      const int incl = warp_incl_scan(c, lane);
+      const int wt = __shfl_sync(full, incl, 31);
+      if (total + wt > kUCap) return kUFallback;
+      int o = total + incl - c;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (d.start_mask & (1u << k)) {
+          if (nck[k] == 0xFFu) w.stage[o++] = (int)d.cp[k];
+          else {
+            const uint32_t f = __ldg(m.norm_first + d.cp[k]);
+            for (unsigned j = 0; j < nck[k]; ++j) w.stage[o++] = __ldg(m.norm_values + f + j);
+          }
+        }
+      }
+      total += wt;
+      bpos = bs + 128;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sumlen += __shfl_xor_sync(full, sumlen, o);
+    if (__any_sync(full, bad != 0) || (int64_t)sumlen != hi - lo) return 0;
+  }
+  if (cm && (total <= 0 || (int64_t)total > 2 * (n + 1))) return 0;      // :1442-1446
+  __syncwarp();
+  // ---- pass 2: whitespace runs -> one U+2581, trailing one dropped (:1462-1496); alphabet indices ----
+  int N = 0, last_c = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int i = base + lane;
+    bool keep = false; int c = 0;
+    if (i < total) {
+      c = w.stage[i];
+      const bool white = sp_is_white(c);
+      if (!white || i == 0) keep = true;
+      else { const int q = w.stage[i - 1]; keep = !sp_is_white(q) && q != kSpDelim; }
+      if (white) c = kSpDelim;
+    }
+    const unsigned bal = __ballot_sync(full, keep);
+    if (keep) w.sym[N + __popc(bal & bf_lanemask_lt())] = (unsigned)c <= 0x10FFFFu ? __ldg(m.sym_of_cp + c) : kNoSym;
+    if (bal) last_c = __shfl_sync(full, c, 31 - __clz(bal));
+    N += __popc(bal);
+  }
+  if (N > 1 && last_c == kSpDelim) --N;
+  if (N <= 0) return 0;
+  __syncwarp();
+  double carry = 0.0;                                          // "position -1": the empty prefix
+  const int out = unigram_window(m, w, N, &carry, row, 0, max_ids, unk, lane);
+  return out < max_ids ? out : max_ids;
+}
+
 // Streams one document through the window.  A U+2581 is a forced token boundary: no token contains it
 // past its first symbol, and "U+2581" itself is a token (both checked at load), so its start always
 // has an arc and no unknown run merges across it.  Hence the best path up to the last U+2581 of the
 // window is final: it is traced back and emitted, the rest slides to the front, and the best score of
 // the last position carries over (the scores are absolute, as in the reference).
-__device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
-                               int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane) {
+__device__ int unigram_streamed(const SpModelDev& m, const UWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
+                                int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane) {
   const unsigned full = 0xffffffffu;
   int64_t lo = lo0;
   if (hi - lo >= 3) {
@@ -1332,9 +1423,36 @@ __device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_
       if (cm && (stream <= 0 || stream > 2 * (n + 1))) return 0;                  // :1442-1446
       if ((prior || fill > 1) && fill > 0 && last_is_delim) --fill;               // one trailing U+2581 goes (:1491-1493)
       cut = fill;
-    } else {
-      if (last_delim <= 0) return kUFallback;                  // a run without U+2581 fills the window
+    } else if (last_delim > 0) {
       cut = last_delim;
+    } else {
+      // A run without U+2581 fills the window (a URL, CJK text).  Any position p that no token spans is a
+      // forced boundary as well, unless p-1 and p are both unknown symbols (an unknown run is one token,
+      // :145-171); every start before p must have been walked to its end inside the window.
+      const uint4* da = reinterpret_cast<const uint4*>(m.da);
+      int reach = -1, best = 0, prev_unknown = 0; bool closed = true;
+      for (int p0 = 0; p0 < fill && closed; p0 += 32) {
+        const int p = p0 + lane;
+        int fe = -1; bool open = false;
+        if (p < fill) fe = b_farthest(m, da, w.sym, p, fill, &open);
+        const bool unknown = p < fill && fe < 0;
+        int incl = unknown ? p : fe;                           // an unknown symbol covers itself
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(full, incl, o); if (lane >= o) incl = max(incl, t); }
+        int excl = __shfl_up_sync(full, incl, 1);
+        excl = lane ? max(excl, reach) : reach;
+        const unsigned ub = __ballot_sync(full, unknown);
+        const bool before_unknown = lane ? ((ub >> (lane - 1)) & 1u) : (prev_unknown != 0);
+        const unsigned ob = __ballot_sync(full, open);
+        const int first_open = ob ? p0 + __ffs(ob) - 1 : fill;   // starts at or after it are not fully known
+        const unsigned cb = __ballot_sync(full, p < fill && p > 0 && excl < p && p <= first_open && !(unknown && before_unknown));
+        if (cb) best = p0 + 31 - __clz(cb);
+        if (ob) closed = false;
+        reach = max(reach, __shfl_sync(full, incl, 31));
+        prev_unknown = (int)(ub >> 31);
+      }
+      if (best <= 0) return kUFallback;                        // no such position: the general path
+      cut = best;
     }
     if (cut > 0) {
       out = unigram_window(m, w, cut, &carry, row, out, max_ids, unk, lane);
@@ -1379,6 +1497,16 @@ __device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_
     fill = rest; last_delim = 0; prior = true;
   }
   return out;
+}
+
+// Short documents take the one-window form (fewer passes); anything longer is streamed.
+__device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
+                               int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane) {
+  if (hi - lo0 <= 4ll * kUCap) {                               // a code point takes at most 4 bytes
+    const int r = unigram_whole(m, w, text, lo0, hi, padded_bytes, row, max_ids, unk, lane);
+    if (r != kUFallback) return r;
+  }
+  return unigram_streamed(m, w, text, lo0, hi, padded_bytes, row, max_ids, unk, lane);
 }
 
 __global__ void __launch_bounds__(kUWarps * 32, kUCtasPerSm) sp_unigram_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
