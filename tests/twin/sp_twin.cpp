@@ -274,8 +274,25 @@ int sptwin_text_to_ids_streamed(void* h, const char* s, int n, int32_t* ids, int
       int cut = N;
       if (pos + window < N) {
         cut = -1;
-        for (int p = pos + window - 1; p > pos; --p) if (buf[p] == kSpDelim) { cut = p; break; }
-        if (cut < 0) return -4;
+        const int end = pos + window;
+        for (int p = end - 1; p > pos; --p) if (buf[p] == kSpDelim) { cut = p; break; }
+        if (cut < 0) {
+          // no U+2581 in the window: the last position no token spans, not inside an unknown run, with
+          // every earlier start walked to its end inside the window (sp_kernel.cu unigram_streamed)
+          int reach = -1; bool prev_unknown = false;
+          for (int p = pos; p < end; ++p) {
+            uint32_t q = S.root; int far = -1; bool open = false;
+            int i = p;
+            for (; i < end; ++i) { int ow; bool fin; if (!step(S, &q, buf[i], &ow, &fin)) break; if (fin) far = i; if (q == 0) break; }
+            if (i == end) open = true;
+            const bool unknown = far < 0;
+            if (p > pos && reach < p && !(unknown && prev_unknown)) cut = p;
+            if (open) break;
+            reach = std::max(reach, unknown ? p : far);
+            prev_unknown = unknown;
+          }
+          if (cut < 0) return -4;
+        }
       }
       if (!unigram_range(S, buf, pos, cut, &carry, unk, &res)) return -3;
       pos = cut;

@@ -68,8 +68,10 @@ def main():
         ("cfg3_gpt2", "gpt2.bin", 0, 4096, lambda n: corpus.gen_docs("EN", n, seed=3, fixed_len=0)),
         ("cfg4_xlmr", "xlm_roberta_base.bin", 3, 512, lambda n: corpus.gen_docs("MULTI", n, seed=4, fixed_len=512, emoji_every=16)),
         ("cfg2_bert_same_path", "bert_base_tok.bin", 100, 512, lambda n: corpus.gen_docs("EN", n, seed=2, fixed_len=512)),
+        # not a BASELINE configuration: the Unigram model on cfg 3's long documents (only with --only)
+        ("extra_xlmr_long_docs", "xlm_roberta_base.bin", 3, 4096, lambda n: corpus.gen_docs("EN", n, seed=3, fixed_len=0)),
     ]:
-        if only and name not in only:
+        if (only and name not in only) or (not only and name.startswith("extra_")):
             continue
         text, offs = gen(args.docs)
         n, nbytes = len(offs) - 1, int(offs[-1])
