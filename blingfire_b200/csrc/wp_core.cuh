@@ -39,8 +39,10 @@ struct WpTop {
   const int8_t* top_row_root;     // [K] index of the staged copy of trans[top_fn_root], -1 if not staged
   const int8_t* top_row_caret;    // [K] same for top_fn_caret
   const void* staged_rows;        // [R][NC+1] copies of hot transition rows
+  const uint8_t* sync_start;      // [1<<sync_shift][1<<sync_shift] (previous top class, top class) -> a chunk may start here:
+                                  //           no walk crosses the pair, and some match starts with the class
   int K, NT;
-  uint8_t tc_caret, tc_dollar, tc_none;
+  uint8_t tc_caret, tc_dollar, tc_none, sync_shift;
 };
 
 template <typename TE>

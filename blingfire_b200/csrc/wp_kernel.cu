@@ -253,13 +253,7 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
           const int q = p0 + lane;
           bool flag = false;
           if (q < m) {
-            const unsigned t2 = meta[q];
-            if (q == 0) flag = true;
-            else {
-              const unsigned t1 = meta[q - 1];
-              const bool sync = !((top.cross[t1] >> t2) & 1ull);
-              flag = sync && top.ttop[t2] != 0xFF;
-            }
+            flag = q == 0 || top.sync_start[((unsigned)meta[q - 1] << top.sync_shift) | (unsigned)meta[q]] != 0;
           }
           const unsigned bal = __ballot_sync(0xffffffffu, flag);
           if (flag) starts[nst + __popc(bal & lanemask_lt())] = (uint16_t)q;

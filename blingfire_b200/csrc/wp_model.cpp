@@ -45,6 +45,9 @@ void build_wp_blob(const LexerTables& T, WpBlob* out) {
   L.off_caret = place((uint32_t)F.K * 4, 16);
   L.off_row_root = place((uint32_t)F.K, 16);
   L.off_row_caret = place((uint32_t)F.K, 16);
+  L.sync_shift = 1;
+  while ((1 << L.sync_shift) < F.NT) ++L.sync_shift;
+  L.off_sync = place(1u << (2 * L.sync_shift), 16);
   L.off_rows = place(L.row_bytes * (uint32_t)(rows.empty() ? 1 : rows.size()), 16);
   L.total_bytes = (off + 15) / 16 * 16;
 
@@ -58,6 +61,9 @@ void build_wp_blob(const LexerTables& T, WpBlob* out) {
     b[L.off_ttop + i] = (d != 0xFF && F.top_final[d]) ? (uint8_t)(d | 0x80) : d;
   }
   std::memcpy(b + L.off_cross, F.cross.data(), (size_t)F.NT * 8);
+  for (int t1 = 0; t1 < F.NT; ++t1)
+    for (int t2 = 0; t2 < F.NT; ++t2)
+      b[L.off_sync + ((size_t)t1 << L.sync_shift) + t2] = (!((F.cross[(size_t)t1] >> t2) & 1ull) && F.ttop[(size_t)t2] != 0xFF) ? 1 : 0;
   std::memcpy(b + L.off_final, F.top_final.data(), (size_t)F.K);
   std::memcpy(b + L.off_tag, F.top_tag.data(), (size_t)F.K * 4);
   std::memcpy(b + L.off_root, F.top_fn_root.data(), (size_t)F.K * 4);

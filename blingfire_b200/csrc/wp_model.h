@@ -19,10 +19,11 @@ constexpr size_t kMaxStagedBytes = 24 * 1024;   // shared-memory budget for stag
 struct WpBlobLayout {
   uint32_t total_bytes;       // multiple of 16 (cp.async.bulk granularity)
   uint32_t off_ascii, off_tc, off_ttop, off_cross, off_final, off_tag, off_root, off_caret;
-  uint32_t off_row_root, off_row_caret, off_rows;
+  uint32_t off_row_root, off_row_caret, off_rows, off_sync;
   int32_t K, NT, num_rows;
   uint32_t row_bytes;         // (NC+1) * sizeof(table entry)
-  uint8_t tc_caret, tc_dollar, tc_none, pad;
+  uint8_t tc_caret, tc_dollar, tc_none;
+  uint8_t sync_shift;         // sync_start is [1 << sync_shift][1 << sync_shift]
 };
 
 struct WpBlob {
@@ -47,6 +48,7 @@ BF_HD WpTop make_wp_top(const uint8_t* base, const WpBlobLayout& L) {
   t.top_row_root = reinterpret_cast<const int8_t*>(base + L.off_row_root);
   t.top_row_caret = reinterpret_cast<const int8_t*>(base + L.off_row_caret);
   t.staged_rows = base + L.off_rows;
+  t.sync_start = base + L.off_sync; t.sync_shift = L.sync_shift;
   t.K = L.K; t.NT = L.NT;
   t.tc_caret = L.tc_caret; t.tc_dollar = L.tc_dollar; t.tc_none = L.tc_none;
   return t;
