@@ -14,6 +14,7 @@
 // identical flattened tables on the CPU; the product only ever calls it from wp_kernel.cu.
 #pragma once
 
+#include <climits>
 #include <cstdint>
 
 #if defined(__CUDACC__)
@@ -81,18 +82,17 @@ BF_HD uint32_t wp_row_step(const void* rows, int row, uint32_t nc1, uint32_t c) 
   return v == TeTraits<TE>::none ? kNone32 : v;
 }
 
-// Per-position byte next to cls[]: the top-level class of the position in the low bits (written by the
-// decoder, read by the top-level walk) and "a piece starts here" in bit 7 (written by the walks).
-constexpr uint8_t kHasId = 0x80;
+// ids_at[p] of a position where no piece starts (a real id is a rule tag or the caller's UnkId)
+constexpr int32_t kNoPiece = INT_MIN;
 constexpr uint8_t kTopFinal = 0x80;      // ttop entries: bit 7 = the destination is final (K <= 127 states)
 
 // The function sub-grammar over the word span cls[w0..w1] (inclusive), i.e. Process_int with
-// Initial = FnIni at RecDepth 2.  Pieces are written position-indexed: ids_at[p] and the kHasId bit
-// of meta[p] for a piece starting at p.  Returns true when the pieces tile the word exactly.
+// Initial = FnIni at RecDepth 2.  Pieces are written position-indexed: ids_at[p] for a piece starting
+// at p (kNoPiece elsewhere).  Returns true when the pieces tile the word exactly.
 template <typename TE>
 BF_HD bool wp_word(const WpTop& t, const WpGlobal<TE>& g, const uint16_t* cls, int w0, int w1,
                    uint32_t root, uint32_t caret, int row_root, int row_caret,
-                   int32_t* ids_at, uint8_t* meta) {
+                   int32_t* ids_at) {
   const int L = w1 - w0 + 1;
   int expect = w0;          // ExpectedFrom of the post-pass
   bool contiguous = true;   // still inside the leading run of gap-free sub-tokens
@@ -135,7 +135,6 @@ BF_HD bool wp_word(const WpTop& t, const WpGlobal<TE>& g, const uint16_t* cls, i
     const int t2 = fpos > L - 1 ? L - 1 : fpos;         // clamp(FinalPos - 0, 0, L-1)
     const int32_t tag = bf_ldg(g.tag_of_state + fq);
     ids_at[w0 + f2] = tag;
-    meta[w0 + f2] |= kHasId;
     if (contiguous && w0 + f2 == expect) { expect = w0 + t2 + 1; ++nsub; }   // tag > 4 by FastPath
     else contiguous = false;
     if (fpos > from) from = fpos;                       // resume after the token (:389-393)
@@ -149,7 +148,7 @@ BF_HD bool wp_word(const WpTop& t, const WpGlobal<TE>& g, const uint16_t* cls, i
 // processed (>= from_end).
 template <typename TE>
 BF_HD int wp_chunk(const WpTop& t, const WpGlobal<TE>& g, const uint16_t* cls, int m, bool at_doc_end,
-                   int from_begin, int from_end, int unk_id, int32_t* ids_at, uint8_t* meta) {
+                   int from_begin, int from_end, int unk_id, int32_t* ids_at, const uint8_t* tcs) {
   int from = from_begin;
   for (; from < from_end; ++from) {
     uint32_t q = 0;                      // local id of the initial state
@@ -163,7 +162,7 @@ BF_HD int wp_chunk(const WpTop& t, const WpGlobal<TE>& g, const uint16_t* cls, i
     }
     int fq = -1, fpos = -1;
     for (; j < bound; ++j) {
-      const uint8_t d = t.ttop[q * t.NT + (meta[j] & ~kHasId)];
+      const uint8_t d = t.ttop[q * t.NT + tcs[j]];
       if (d == 0xFF) break;
       q = d & ~kTopFinal;
       if (d & kTopFinal) { fq = (int)q; fpos = j; }
@@ -179,11 +178,10 @@ BF_HD int wp_chunk(const WpTop& t, const WpGlobal<TE>& g, const uint16_t* cls, i
       bool tiled = false;
       const uint32_t root = t.top_fn_root[fq];
       if (root != kNone32)
-        tiled = wp_word<TE>(t, g, cls, f2, t2, root, t.top_fn_caret[fq], t.top_row_root[fq], t.top_row_caret[fq], ids_at, meta);
+        tiled = wp_word<TE>(t, g, cls, f2, t2, root, t.top_fn_caret[fq], t.top_row_root[fq], t.top_row_caret[fq], ids_at);
       if (!tiled) {                      // not covered without gaps -> one UnkId (:1282-1301)
-        for (int p = f2 + 1; p <= t2; ++p) meta[p] &= (uint8_t)~kHasId;
+        for (int p = f2 + 1; p <= t2; ++p) ids_at[p] = kNoPiece;
         ids_at[f2] = unk_id;
-        meta[f2] |= kHasId;
       }
     }
     if (fpos > from) from = fpos;

@@ -29,7 +29,7 @@ constexpr int kWarpsPerCta = 16;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kWin = 576;            // window capacity in code points (per warp)
 constexpr int kBlockBytes = 128;     // bytes consumed per decode step (32 lanes x uchar4)
-constexpr int kWarpSmem = kWin * (2 + 4 + 1 + 2 + 2);   // cls u16, ids_at i32, meta u8, starts u16, order u16
+constexpr int kWarpSmem = kWin * (2 + 4 + 1 + 2 + 2);   // cls u16, ids_at i32, top class u8, starts u16, order u16
 
 static_assert(kWin % 32 == 0, "window must be a multiple of the warp size");
 
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
   int32_t* ids_at = reinterpret_cast<int32_t*>(wbase);
   uint16_t* cls = reinterpret_cast<uint16_t*>(wbase + kWin * 4);
   uint16_t* starts = reinterpret_cast<uint16_t*>(wbase + kWin * 6);
-  uint8_t* meta = wbase + kWin * 8;          // top-level class | kHasId (wp_core.cuh)
+  uint8_t* meta = wbase + kWin * 8;          // top-level class of every position
   uint16_t* order = reinterpret_cast<uint16_t*>(wbase + kWin * 9 + (kWin & 1));
 
   const uint32_t* text32 = reinterpret_cast<const uint32_t*>(p.text);
@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
               const uint32_t cp = dcd.cp[k];
               const uint16_t c = cp < 128 ? top.ascii_cls[cp] : __ldg(g.cls_of_cp + cp);
               cls[idx] = c;
-              meta[idx] = top.tc_of_class[c];          // also clears the position's kHasId bit
+              meta[idx] = top.tc_of_class[c];
+              ids_at[idx] = kNoPiece;
               ++idx;
             }
           }
@@ -314,10 +315,11 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
         // ---- ordered compaction of the ids of positions [0, carry) ----
         for (int p0 = 0; p0 < carry; p0 += 32) {
           const int q = p0 + lane;
-          const bool f = q < carry && (meta[q] & kHasId);
+          const int32_t id = q < carry ? ids_at[q] : kNoPiece;
+          const bool f = id != kNoPiece;
           const unsigned bal = __ballot_sync(0xffffffffu, f);
           const int rank = out + __popc(bal & lanemask_lt());
-          if (f && rank < p.max_ids) row[rank] = ids_at[q];
+          if (f && rank < p.max_ids) row[rank] = id;
           out += __popc(bal);
         }
         if (at_end) break;
@@ -327,9 +329,9 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
         for (int k0 = 0; k0 < rest; k0 += 32) {
           const int k = k0 + lane;
           const uint16_t v = k < rest ? cls[carry + k] : (uint16_t)0;
-          const uint8_t mt = k < rest ? (uint8_t)(meta[carry + k] & ~kHasId) : (uint8_t)0;
+          const uint8_t mt = k < rest ? meta[carry + k] : (uint8_t)0;
           __syncwarp();
-          if (k < rest) { cls[k] = v; meta[k] = mt; }
+          if (k < rest) { cls[k] = v; meta[k] = mt; ids_at[k] = kNoPiece; }
         }
         __syncwarp();
         m = rest;

@@ -167,7 +167,7 @@ int twin_text_to_ids(void* h, const char* s, int n, int32_t* ids, int max_ids, i
     }
     const bool at_end = bpos >= hi;
     if (m == 0) break;
-    for (int p = 0; p < m; ++p) has_id[p] = top.tc_of_class[cls[p]];   // the per-position byte: top-level class, kHasId clear
+    for (int p = 0; p < m; ++p) { has_id[p] = top.tc_of_class[cls[p]]; ids_at[p] = kNoPiece; }   // top-level class of every position; no piece yet
     // chunk starts: sync points whose first class can start a match; position 0 always
     starts.clear();
     starts.push_back(0);
@@ -191,7 +191,7 @@ int twin_text_to_ids(void* h, const char* s, int n, int32_t* ids, int max_ids, i
       if (i + 1 < starts.size() && starts[i + 1] <= limit && r != starts[i + 1]) return -3;
     }
     for (int p = 0; p < carry && p < m; ++p)
-      if (has_id[p] & kHasId) { if (out < max_ids) ids[out] = ids_at[p]; ++out; }
+      if (ids_at[p] != kNoPiece) { if (out < max_ids) ids[out] = ids_at[p]; ++out; }
     if (at_end) break;
     std::memmove(cls.data(), cls.data() + carry, sizeof(uint16_t) * (size_t)(m - carry));
     m -= carry;
