@@ -52,7 +52,8 @@ int FreeModel(void* ModelPtr);
 /* blingfiretokdll.h:93-100, blingfiretokdll.cpp:1619-1646.  Writes at most MaxIdsArrLength
  * ids, leaves the rest of pIdsArr untouched, returns the number written.  Returns 0 for a
  * NULL model/text, InUtf8StrByteCount <= 0 or > 1e9, invalid UTF-8 anywhere in the input,
- * or normalisation overflow -- exactly like the reference. */
+ * or normalisation overflow -- exactly like the reference.  (UnkId may be any int except INT32_MIN,
+ * which the WordPiece kernel uses as its "no piece starts here" marker.) */
 int TextToIds(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
                     int32_t* pIdsArr, const int MaxIdsArrLength, const int UnkId);
 
