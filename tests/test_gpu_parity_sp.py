@@ -72,6 +72,17 @@ def test_known_answer_xlnet(bf):
     assert ids.tolist() == [14363, 651, 7201, 25263, 35, 685, 24, 1615, 33, 24, 16163, 9]
 
 
+def test_known_answer_xlmr_with_offsets(bf):
+    """README.md:232,267-268: ids, and the token text cut out by the byte offsets."""
+    from test_oracle import XLMR_TEXT, XLMR_TOKENS
+    h = gpu_model(bf, "xlm_roberta_base.bin")
+    data = XLMR_TEXT.encode()
+    assert bf.text_to_ids(h, XLMR_TEXT, 128, 0, no_padding=True).tolist() == [t[1] for t in XLMR_TOKENS]
+    ids, st, en = bf.utf8text_to_ids_with_offsets(h, data, 128, 0, no_padding=True)
+    assert ids.tolist() == [t[1] for t in XLMR_TOKENS]
+    assert [data[max(int(a), 0): int(b) + 1].decode() for a, b in zip(st, en)] == [t[0] for t in XLMR_TOKENS]
+
+
 def test_edge_cases_vs_golden(bf, golden):
     import ctypes
     L = bf.lib()
