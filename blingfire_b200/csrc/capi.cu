@@ -207,8 +207,8 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
       m->engine = 2;
     }
     // the dense table is the bulk of the host footprint; the device copy is the one that serves
-    std::vector<uint16_t>().swap(T.trans16);
-    std::vector<uint32_t>().swap(T.trans32);
+    DenseVec<uint16_t>().swap(T.trans16);
+    DenseVec<uint32_t>().swap(T.trans32);
   }
   if (m->has_seg) {
     // blingfiretokdll.cpp:1636-1645: a [pos-dict] model is served by the segmentation engine

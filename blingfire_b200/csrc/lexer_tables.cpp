@@ -2,6 +2,7 @@
 #include "lexer_tables.h"
 
 #include <algorithm>
+#include <thread>
 #include <map>
 #include <set>
 
@@ -128,23 +129,38 @@ bool build_lexer_tables(const LdbImage& ldb, LexerTables* T, std::string* err) {
   const size_t W = (size_t)NC + 1;
   const size_t cells = (size_t)T->NS * W;
   if (cells > ((size_t)1 << 33)) { *err = "dense transition table too large"; return false; }
-  std::vector<uint32_t> row(W);
-  if (T->wide_states) T->trans32.assign(cells, kNoState); else T->trans16.assign(cells, 0xFFFF);
-  for (int s = 0; s < n; ++s) {
-    std::fill(row.begin(), row.end(), kNoState);
-    for (int64_t k = A.arc_begin[s]; k < A.arc_begin[s + 1]; ++k) {
-      const Arc& a = A.arcs[k];
-      if (a.label < 0 || a.label >= NC) continue;   // a class no input can produce
-      row[a.label] = a.dst == kDeadState ? T->dead : newid[a.dst];
+  // The table starts as "no transition" everywhere and only the arcs are written: a row is touched in
+  // full only when its state has an IW_ANY arc (the 9.3 GB table of bert_multi_cased has 0.03 % of its
+  // cells set).
+  auto fill_parallel = [&](auto* p, auto none) {
+    unsigned nt = cells < ((size_t)1 << 26) ? 1u : std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    const size_t per = (cells + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+      const size_t lo = (size_t)t * per, hi = std::min(cells, lo + per);
+      if (lo >= hi) break;
+      th.emplace_back([=] { std::fill(p + lo, p + hi, none); });
     }
-    if (cls_any < (uint32_t)NC && row[cls_any] != kNoState) {
-      const uint32_t any = row[cls_any];
-      for (size_t c = 0; c < W; ++c) if (row[c] == kNoState) row[c] = any;
+    for (auto& x : th) x.join();
+  };
+  if (T->wide_states) { T->trans32.resize(cells); fill_parallel(T->trans32.data(), (uint32_t)kNoState); }
+  else { T->trans16.resize(cells); fill_parallel(T->trans16.data(), (uint16_t)0xFFFF); }
+  auto fill_rows = [&](auto* table, auto none) {
+    using E = decltype(none);
+    for (int s = 0; s < n; ++s) {
+      E* row = table + (size_t)newid[s] * W;
+      for (int64_t k = A.arc_begin[s]; k < A.arc_begin[s + 1]; ++k) {
+        const Arc& a = A.arcs[k];
+        if (a.label < 0 || a.label >= NC) continue;   // a class no input can produce
+        row[a.label] = (E)(a.dst == kDeadState ? T->dead : newid[a.dst]);
+      }
+      if (cls_any < (uint32_t)NC && row[cls_any] != none) {
+        const E any = row[cls_any];
+        for (size_t c = 0; c < W; ++c) if (row[c] == none) row[c] = any;
+      }
     }
-    const size_t base = (size_t)newid[s] * W;
-    if (T->wide_states) std::copy(row.begin(), row.end(), T->trans32.begin() + base);
-    else for (size_t c = 0; c < W; ++c) T->trans16[base + c] = row[c] == kNoState ? 0xFFFF : (uint16_t)row[c];
-  }
+  };
+  if (T->wide_states) fill_rows(T->trans32.data(), (uint32_t)kNoState); else fill_rows(T->trans16.data(), (uint16_t)0xFFFF);
 
   // ---- rule ids, actions ----
   T->ow_of_state.assign((size_t)T->NS, -1);

@@ -18,11 +18,30 @@
 
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ldb.h"
 
 namespace bfb200 {
+
+// A vector whose resize() leaves new elements uninitialised: the dense transition table (9.3 GB for
+// bert_multi_cased) is first touched by several threads at once -- one thread faulting the pages in
+// takes most of a minute.
+template <class T>
+struct NoInitAllocator {
+  using value_type = T;
+  NoInitAllocator() = default;
+  template <class U> NoInitAllocator(const NoInitAllocator<U>&) {}
+  T* allocate(size_t n) { return static_cast<T*>(::operator new(n * sizeof(T))); }
+  void deallocate(T* p, size_t) { ::operator delete(p); }
+  template <class U> void construct(U*) {}
+  template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+  template <class U> bool operator==(const NoInitAllocator<U>&) const { return true; }
+  template <class U> bool operator!=(const NoInitAllocator<U>&) const { return false; }
+};
+template <class T> using DenseVec = std::vector<T, NoInitAllocator<T>>;
+
 
 constexpr int kMaxCodePoint = 0x10FFFF;
 constexpr uint32_t kNoState = 0xFFFFFFFFu;     // "no transition" in host-side tables
@@ -77,8 +96,8 @@ struct LexerTables {
   uint32_t initial = 0;
   uint32_t dead = 0;                   // explicit sink standing for DFA_DEAD_STATE
   bool wide_states = false;            // NS >= 65535 -> 32-bit table entries
-  std::vector<uint16_t> trans16;       // [NS*(NC+1)] when !wide_states, 0xFFFF = none
-  std::vector<uint32_t> trans32;       // [NS*(NC+1)] when wide_states, kNoState = none
+  DenseVec<uint16_t> trans16;          // [NS*(NC+1)] when !wide_states, 0xFFFF = none
+  DenseVec<uint32_t> trans32;          // [NS*(NC+1)] when wide_states, kNoState = none
   std::vector<int32_t> ow_of_state;    // [NS] rule id for finals, -1 otherwise
   std::vector<int32_t> orig_offset;    // [NS] the state's id in the packed image (byte offset), -1 for the sink
 

@@ -162,6 +162,8 @@ EDGE = [b"", b"abc \xff def", b"\xe6\x88", b"   ", b"\xef\xbb\xbfhello", b"hello
     ("bert_base_tok.bin", "test.multi.txt", 8000, 3, 640, 100),
     ("bert_base_cased_tok.bin", "test.txt", 8000, 2, 640, 512),
     ("bert_chinese.bin", "test.multi.txt", 8000, 2, 400, 512),
+    # 232k states x 10 004 classes: the 32-bit table variant (9.3 GB on the host, filled by several threads)
+    ("bert_multi_cased.bin", "test.multi.txt", 3000, 2, 640, 512),
 ])
 def test_twin_matches_oracle(twin, oracle, name, corpus, nlines, group, window, max_ids):
     h = twin.load(name)
