@@ -9,8 +9,9 @@
 //
 // One document per warp, persistent grid, documents handed out by an atomic counter.  Three paths
 // (DESIGN.md section 4), each behind the other:
-//   sp_unigram_fast  Unigram models with tokens <= 16 symbols, documents <= 576 symbols: everything
-//                    in shared memory, the relaxation in a register window (lane = position)
+//   sp_unigram_fast  Unigram models with tokens <= 16 symbols: a 576-symbol window in shared memory (the
+//                    whole document when it fits, else streamed and cut at U+2581 with the best score
+//                    carried over), the relaxation in a register window (lane = position)
 //   sp_bpe_fast      byte-level BPE models: a 512-symbol window slides over the document, cut at
 //                    U+2581 (segments are independent); lanes re-dealt per phase (per segment, per
 //                    start, per arc); long segments split at the positions no token spans
