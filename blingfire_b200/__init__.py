@@ -164,8 +164,46 @@ def _utf8_split_with_offsets(fn_name, s_bytes, h=None):
         return b"", starts[:0], ends[:0]
     text = o.raw[: n - 1]
     sep = b" " if "Words" in fn_name else b"\n"
-    k = text.count(sep) + 1 if text else 0
+    k = text.count(sep) + 1          # like the reference wrapper (:188): an empty output still counts one token
     return text, starts[:k], ends[:k]
+
+
+def _string_offsets(s, s_bytes, starts, ends):
+    """The reference wrapper's mapping (dist-pypi/blingfire/__init__.py:192-219) from the byte offsets the C
+    ABI returns (first byte of the first character, last byte of the last one) to (begin, end) pairs in
+    code points of the Python string, end exclusive."""
+    utf8_offsets = [o for pair in zip(starts, ends) for o in pair]
+    string_offsets = []
+    string_offset = 0
+    is_end_offset = False
+    for utf8_offset, b in enumerate(s_bytes):
+        if b & 0xC0 != 0x80:
+            while len(string_offsets) < len(utf8_offsets) and utf8_offsets[len(string_offsets)] + is_end_offset == utf8_offset:
+                string_offsets.append(string_offset)
+                is_end_offset = not is_end_offset
+            string_offset += 1
+    if len(string_offsets) < len(utf8_offsets):
+        string_offsets.append(len(s))
+    assert len(string_offsets) == len(utf8_offsets), "%s != %s" % (len(string_offsets), len(utf8_offsets))
+    return list(zip(string_offsets[::2], string_offsets[1::2]))
+
+
+def text_to_words_with_offsets(s):
+    """dist-pypi/blingfire/__init__.py:222-223: (' '-joined words, [(begin, end)] in code points)."""
+    s_bytes = s.encode("utf-8")
+    text, st, en = utf8text_to_words_with_offsets(s_bytes)
+    if len(st) == 0:
+        return "", []
+    return text.decode("utf-8"), _string_offsets(s, s_bytes, [int(x) for x in st], [int(x) for x in en])
+
+
+def text_to_sentences_and_offsets(s):
+    """dist-pypi/blingfire/__init__.py:225-226: ('\\n'-joined sentences, [(begin, end)] in code points)."""
+    s_bytes = s.encode("utf-8")
+    text, st, en = utf8text_to_sentences_with_offsets(s_bytes)
+    if len(st) == 0:
+        return "", []
+    return text.decode("utf-8"), _string_offsets(s, s_bytes, [int(x) for x in st], [int(x) for x in en])
 
 
 def utf8text_to_words_with_offsets(s_bytes, h=None):

@@ -49,7 +49,7 @@ def b64(b):
 def main():
     r = Ref()
     out = {"generator": "tests/golden/make_golden.py over oracle/_ref (the reference built from its own sources)",
-           "edge_cases": [], "digests": [], "words": [], "ids_with_offsets": [], "split_with_offsets": []}
+           "edge_cases": [], "digests": [], "words": [], "ids_with_offsets": [], "split_with_offsets": [], "py_offsets": []}
     handles = {}
     for m, unk in MODELS:
         handles[m] = r.load(model_path(m))
@@ -97,6 +97,17 @@ def main():
                 k = max_out if max_out is not None else 2 * len(data) + 16
                 out["split_with_offsets"].append({"kind": kind, "input": b64(data), "max_out": k, "ret": int(n), "out": b64(text),
                                                   "starts": st[:max(k, 1)].tolist()[:64], "ends": en[:max(k, 1)].tolist()[:64]})
+    # the reference's own Python wrapper (dist-pypi/blingfire/__init__.py:170-227): code-point offsets
+    sys.path.insert(0, "/root/reference/dist-pypi")
+    import blingfire as ref_py
+    out["py_offsets"] = []
+    texts = [l.decode("utf-8") for l in read_lines("test.multi.txt")[:60] + read_lines("test.txt")[:60]]
+    texts += [" ".join(texts[i:i + 4]) for i in range(0, 40, 4)] + ["naïve café. Hello 我爱北京!", "x", "^", "Hello world! How are you?  Fine. Ünïcode ok."]
+    for t in texts:
+        w, wo = ref_py.text_to_words_with_offsets(t)
+        sn, so = ref_py.text_to_sentences_and_offsets(t)
+        out["py_offsets"].append({"text": t, "words": w, "word_offsets": [list(x) for x in wo], "sentences": sn,
+                                  "sentence_offsets": [list(x) for x in so]})
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print("wrote golden.json", os.path.getsize(os.path.join(HERE, "golden.json")), "bytes")

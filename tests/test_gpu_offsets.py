@@ -163,3 +163,15 @@ def test_words_and_sentences_vs_oracle(bf, kind, name):
         text, st, en = bf.utf8text_to_words_with_offsets("naïve café.".encode())
         assert text == "naïve café .".encode() and st.tolist() == [0, 7, 12] and en.tolist() == [5, 11, 12]
     bf.free_model(h)
+
+
+def test_python_wrapper_string_offsets_vs_golden(bf):
+    """text_to_words_with_offsets / text_to_sentences_and_offsets (code-point offsets) against the
+    reference's own Python wrapper."""
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        golden = json.load(f)
+    for c in golden["py_offsets"]:
+        w, wo = bf.text_to_words_with_offsets(c["text"])
+        assert w == c["words"] and [list(x) for x in wo] == c["word_offsets"], c["text"][:40]
+        sn, so = bf.text_to_sentences_and_offsets(c["text"])
+        assert sn == c["sentences"] and [list(x) for x in so] == c["sentence_offsets"], c["text"][:40]
