@@ -70,7 +70,7 @@ def test_segmentation_tables_match_oracle(sptwin, name, unks):
     ho = o.load(model_path(name))
     out = np.zeros(4096, np.int32)
     for unk in unks:
-        for d in docs_for_fuzz(11, 800):
+        for d in docs_for_fuzz(11, 6000):
             for max_ids in (4096, 5):
                 n1, a = o.text_to_ids(ho, d, max_ids, unk)
                 out[:] = -7
@@ -88,12 +88,12 @@ def test_streaming_decompositions_are_exact(sptwin, name, unk):
     ho = o.load(model_path(name))
     out = np.zeros(8192, np.int32)
     lines = read_lines("test.multi.txt")[:1500] + read_lines("test.txt")[:1500]
-    docs = docs_for_fuzz(23, 200) + [b" ".join(lines[i:i + 40]) for i in range(0, 480, 40)] + [
+    docs = docs_for_fuzz(23, 2000) + [b" ".join(lines[i:i + 40]) for i in range(0, 1200, 40)] + [
         b"http://www.example.com/a/very/long/path/without/any/space/" * 6, "我爱北京天安门".encode() * 60, b"=" * 500 + b" x"]
     uncut = 0
     for d in docs:
         n1, a = o.text_to_ids(ho, d, 8192, unk)
-        for window in (24, 576):
+        for window in (16, 24, 97, 576):
             n2 = sptwin.sptwin_text_to_ids_streamed(h, d, len(d), out.ctypes.data, 8192, unk, window)
             if n2 == -4:          # a run without U+2581 longer than the window: the kernel takes the general path
                 uncut += 1
