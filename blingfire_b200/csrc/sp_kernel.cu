@@ -1039,7 +1039,11 @@ __device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const ArcScratch
 
 // BPE family: one document per warp
 __global__ void __launch_bounds__(kBWarps * 32, kBCtasPerSm) sp_bpe_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
+#ifdef BF_SIMT_HOST                        // tests/simt: the kernel source on the CPU
+  uint8_t* smem = simt::shared_base();
+#else
   extern __shared__ __align__(16) uint8_t smem[];
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * kBWarps + warp;
   const BWork w = make_bwork(smem + (size_t)warp * kBWorkBytes);
@@ -1511,7 +1515,11 @@ __device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_
 }
 
 __global__ void __launch_bounds__(kUWarps * 32, kUCtasPerSm) sp_unigram_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
+#ifdef BF_SIMT_HOST                        // tests/simt: the kernel source on the CPU
+  uint8_t* smem = simt::shared_base();
+#else
   extern __shared__ __align__(16) uint8_t smem[];
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * kUWarps + warp;
   const UWork w = make_uwork(smem + (size_t)warp * kUWorkBytes);
@@ -1561,6 +1569,7 @@ static bool is_bpe_algo(int tok_algo) {
   return tok_algo == kTokenizeBpe || tok_algo == kTokenizeBpeOpt || tok_algo == kTokenizeBpeOptWithMerges;
 }
 
+#ifndef BF_SIMT_HOST
 int sp_preferred_warps(int tok_algo) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -1568,10 +1577,13 @@ int sp_preferred_warps(int tok_algo) {
   return is_bpe_algo(tok_algo) ? sms * kBWarps * kBCtasPerSm : sms * kUWarps * kUCtasPerSm;
 }
 
+#endif
+
 int sp_fast_cap(int tok_algo, int max_arc_len, bool use_raw_bytes) {
   return (!is_bpe_algo(tok_algo) && !use_raw_bytes && max_arc_len <= kUMaxLen) ? kUCap : 0;
 }
 
+#ifndef BF_SIMT_HOST
 cudaError_t sp_tokenize_launch(const SpLaunch& p, const SpModelDev& m, cudaStream_t stream, int* launches) {
   if (p.ndocs <= 0) return cudaSuccess;
   const bool bpe = is_bpe_algo(m.tok_algo);
@@ -1591,5 +1603,7 @@ cudaError_t sp_tokenize_launch(const SpLaunch& p, const SpModelDev& m, cudaStrea
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
+
+#endif
 
 }  // namespace bfb200

@@ -13,9 +13,13 @@
 namespace bfb200 {
 
 __device__ __forceinline__ unsigned bf_lanemask_lt() {
+#ifdef BF_SIMT_HOST                        // tests/simt: the kernel source on the CPU
+  return (1u << simt::tl.lane) - 1u;
+#else
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+#endif
 }
 
 struct Utf8Lane {

@@ -1,0 +1,120 @@
+"""The SOURCE of the segmentation kernels (blingfire_b200/csrc/sp_kernel.cu: sp_unigram_kernel, sp_bpe_kernel)
+compiled for the host over the SIMT shim (tests/simt: one OS thread per lane, full-mask warp intrinsics as
+rendezvous) and run on the CPU against the oracle: the warp-level logic itself -- shuffles, ballots, the
+register window of the Unigram relaxation, the streaming windows, the lane re-dealing of the BPE hard pass,
+the general path with offsets -- not a twin of it.  A kernel whose lanes do not reach the same intrinsics
+in the same order deadlocks here, hence the timeouts.  The GPU suite remains the parity test proper."""
+import ctypes
+import os
+import random
+
+import numpy as np
+import pytest
+
+from _common import ROOT, Oracle, have_data, model_path, read_lines
+
+pytestmark = [pytest.mark.skipif(not have_data(), reason="data/ not staged (run __graft_entry__.build())"),
+              pytest.mark.timeout(600)]
+
+
+@pytest.fixture(scope="module")
+def sim():
+    L = ctypes.CDLL(os.path.join(ROOT, "tests", "simt", "libsp_simt.so"))
+    L.spsim_load.restype = ctypes.c_void_p
+    L.spsim_load.argtypes = [ctypes.c_char_p]
+    L.spsim_error.restype = ctypes.c_char_p
+    L.spsim_error.argtypes = [ctypes.c_void_p]
+    L.spsim_batch.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return L
+
+
+_models = {}
+
+
+def sim_model(sim, name):
+    if name not in _models:
+        _models[name] = sim.spsim_load(model_path(name).encode())
+        assert sim.spsim_error(_models[name]) == b"", sim.spsim_error(_models[name])
+    return _models[name]
+
+
+def run_batch(sim, name, docs, max_ids, unk, warps=3, offsets=False):
+    h = sim_model(sim, name)
+    offs = np.zeros(len(docs) + 1, np.int64)
+    np.cumsum([len(d) for d in docs], out=offs[1:])
+    buf = b"".join(docs) + b"\0"
+    ids = np.full((len(docs), max_ids), -7, np.int32)
+    counts = np.full(len(docs), -7, np.int32)
+    st = np.full((len(docs), max_ids), -7, np.int32)
+    en = np.full((len(docs), max_ids), -7, np.int32)
+    flag = sim.spsim_batch(h, buf, offs.ctypes.data, len(docs), ids.ctypes.data, counts.ctypes.data,
+                           st.ctypes.data if offsets else None, en.ctypes.data if offsets else None, max_ids, unk, warps)
+    assert flag == 0, f"kernel error flag {flag}"
+    return ids, counts, st, en
+
+
+def check(sim, name, docs, max_ids, unk, offsets=False):
+    o = Oracle()
+    ho = o.load(model_path(name))
+    ids, counts, st, en = run_batch(sim, name, docs, max_ids, unk, offsets=offsets)
+    for i, d in enumerate(docs):
+        n, a, s, e = o.text_to_ids_with_offsets(ho, d, max_ids, unk)
+        assert counts[i] == n, (name, i, d[:60], int(counts[i]), n)
+        assert (ids[i, :n] == a[:n]).all(), (name, i, d[:60])
+        # (a streamed document that turns out to be invalid has count 0 after earlier windows were emitted:
+        # the device row is scratch, the host API copies `count` entries only)
+        assert n == 0 or (ids[i, n:] == -7).all(), "a row was written beyond its count"
+        if offsets:
+            assert (st[i, :n] == s[:n]).all() and (en[i, :n] == e[:n]).all(), (name, i, d[:60])
+    o.free(ho)
+
+
+def corpus_docs(seed, n):
+    rng = random.Random(seed)
+    lines = read_lines("test.multi.txt")[:3000] + read_lines("test.txt")[:3000]
+    docs = [b"", b" ", b"  a  b  ", b"\xef\xbb\xbf", b"\xef\xbb\xbfhello", b"abc \xff def", b"hello\x00world", b"a" * 400, b"-" * 300,
+            b"\xc2\xa0nbsp\xc2\xa0", "▁already▁marked ▁".encode(), "我爱北京".encode() * 40, b"\t\ttabs\n\nnl  ", b"x", b"!",
+            "é".encode() * 300, "ﬁ ½ ™ ｶﾞ ＡＢＣ".encode(), b"http://www.example.com/a/long/path/without/space?x=1&y=2" * 3]
+    for _ in range(n):
+        d = b" ".join(rng.choice(lines) for _ in range(rng.randint(1, 4)))
+        r = rng.random()
+        if r < 0.15:
+            d = d[: rng.randint(0, len(d))]
+        elif r < 0.25:
+            p = rng.randint(0, len(d))
+            d = d[:p] + bytes([rng.randint(0, 255)]) + d[p:]
+        elif r < 0.30:
+            d = bytes(rng.randint(0, 255) for _ in range(rng.randint(1, 40)))
+        docs.append(d)
+    return docs
+
+
+SP_MODELS = [("xlm_roberta_base.bin", 3), ("xlnet.bin", 0), ("laser100k.bin", 1), ("gpt2.bin", 0), ("roberta.bin", 3), ("bpe_example.bin", 1)]
+
+
+@pytest.mark.parametrize("name,unk", SP_MODELS)
+def test_kernel_source_matches_oracle(sim, name, unk):
+    docs = corpus_docs(31, 110)
+    check(sim, name, docs, 512, unk)
+    check(sim, name, docs[:60], 5, unk)              # truncation, incl. invalid bytes after MaxIds was reached
+
+
+@pytest.mark.parametrize("name,unk", [("xlm_roberta_base.bin", 3), ("xlnet.bin", 0), ("gpt2.bin", 0), ("roberta.bin", 3)])
+def test_kernel_source_long_documents(sim, name, unk):
+    """Several windows per document: the streamed Unigram form (cuts at U+2581 and inside U+2581-free runs, the
+    score carried over) and the sliding BPE window (split pass, cooperative pass, the general path behind)."""
+    lines = read_lines("test.multi.txt")[:1200] + read_lines("test.txt")[:1200]
+    docs = [b" ".join(lines[i:i + 25]) for i in range(0, 200, 25)] + [b" ".join(lines[1200 + i:1200 + i + 25]) for i in range(0, 200, 25)]
+    docs += [b" ".join(lines[:40]) + b"\xff", b"\x80" + b" ".join(lines[60:100]), ("word " * 500).encode(), b"ab" * 700,
+             "我爱北京天安门".encode() * 90, b"=" * 700 + b" x", ("ﬁ ½ ™ " * 300).encode(),
+             b"https://homedepot.ugc.bazaarvoice.com/answers/submit/1999aa/product/205299499/question/4069427/undohelpfulness.djs?authsourcetype=__AUTHTYPE__&format=" * 5]
+    check(sim, name, docs, 4096, unk)
+    check(sim, name, docs[::2], 37, unk)
+
+
+@pytest.mark.parametrize("name,unk", [("xlm_roberta_base.bin", 3), ("gpt2.bin", 0), ("bpe_example.bin", 1), ("xlnet_nonorm.bin", 0)])
+def test_kernel_source_offsets(sim, name, unk):
+    """TextToIdsWithOffsets_sp: the general path with the byte offsets carried through."""
+    docs = corpus_docs(7, 60)
+    check(sim, name, docs, 300, unk, offsets=True)
