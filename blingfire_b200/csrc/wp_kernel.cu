@@ -34,11 +34,16 @@ constexpr int kWarpSmem = kWin * (2 + 4 + 1 + 2 + 2);   // cls u16, ids_at i32, 
 static_assert(kWin % 32 == 0, "window must be a multiple of the warp size");
 
 __device__ __forceinline__ unsigned lanemask_lt() {
+#ifdef BF_SIMT_HOST                        // tests/simt: the kernel source on the CPU
+  return (1u << simt::tl.lane) - 1u;
+#else
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+#endif
 }
 
+#ifndef BF_SIMT_HOST
 // ---- bulk async copy (TMA 1-D) of the model blob into shared memory ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
@@ -66,6 +71,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+
+#endif  // BF_SIMT_HOST
 
 // ---- UTF-8: decode the (up to 4) sequences that START in this lane's word ----
 // Strictness follows FAUtf8ToInt (FAUtf8Utils.cpp:121-196): shortest form, no surrogates,
@@ -117,11 +124,15 @@ __device__ __forceinline__ void load_words(const uint32_t* text32, int64_t pos0,
 
 template <typename TE>
 __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t blob_bar;
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned blob_bytes = (p.layout.total_bytes + 127u) & ~127u;
+#ifdef BF_SIMT_HOST                        // tests/simt: the kernel source on the CPU
+  uint8_t* smem = simt::shared_base();
+  if (threadIdx.x == 0) std::memcpy(smem, p.blob, p.layout.total_bytes);
+  __syncthreads();
+#else
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t blob_bar;
 
   // stage the model blob: one bulk async copy per CTA, completion through an mbarrier
   if (threadIdx.x == 0) {
@@ -134,6 +145,7 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
     bulk_copy_g2s(smem, p.blob, p.layout.total_bytes, &blob_bar);
   }
   mbar_wait(&blob_bar, 0);
+#endif
 
   const WpTop top = make_wp_top(smem, p.layout);
   WpGlobal<TE> g;
@@ -344,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
   }
 }
 
+#ifndef BF_SIMT_HOST
 __global__ void wp_compact_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ counts,
                                   const int64_t* __restrict__ row_off, int64_t ndocs, int max_ids,
                                   int32_t* __restrict__ csr) {
@@ -397,8 +410,11 @@ __global__ void __launch_bounds__(1024) wp_scan_kernel(const int32_t* __restrict
   if (threadIdx.x == 0) row_off[n] = carry_s;
 }
 
+#endif  // BF_SIMT_HOST
+
 }  // namespace
 
+#ifndef BF_SIMT_HOST
 cudaError_t wp_tokenize_launch(const WpLaunch& p, cudaStream_t stream, WpLaunchInfo* info) {
   const size_t blob_bytes = ((size_t)p.layout.total_bytes + 127) & ~(size_t)127;
   const size_t smem = blob_bytes + (size_t)kWarpsPerCta * kWarpSmem;
@@ -449,5 +465,7 @@ cudaError_t wp_scan_counts(const int32_t* counts, int64_t* row_off, int64_t ndoc
   wp_scan_kernel<<<1, 1024, 0, stream>>>(counts, row_off, ndocs);
   return cudaGetLastError();
 }
+
+#endif  // BF_SIMT_HOST
 
 }  // namespace bfb200

@@ -52,6 +52,7 @@ struct LaneState {
   Warp* warp = nullptr;
   unsigned phase = 0;
   uint8_t* smem = nullptr;
+  std::barrier<>* cta = nullptr;       // all emulated threads of the CTA (__syncthreads)
 };
 inline thread_local LaneState tl;
 inline uint8_t* shared_base() { return tl.smem; }
@@ -85,6 +86,7 @@ inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
 inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, p) == 0xffffffffu; }
 inline int __reduce_max_sync(unsigned, int v) { const uint64_t* b = simt::exchange(simt::pack(v)); int r = simt::unpack<int>(b[0]); for (int i = 1; i < 32; ++i) r = std::max(r, simt::unpack<int>(b[i])); return r; }
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::exchange(0); }
+inline void __syncthreads() { simt::tl.cta->arrive_and_wait(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 
@@ -108,11 +110,12 @@ inline void run_cta(int warps, size_t smem_bytes, const std::function<void()>& k
   std::vector<uint8_t> smem(smem_bytes + 64);
   uint8_t* base = smem.data() + ((64 - (reinterpret_cast<uintptr_t>(smem.data()) & 63)) & 63);
   std::vector<Warp> ws((size_t)warps);
+  std::barrier<> cta_bar(warps * 32);
   std::vector<std::thread> th;
   for (int w = 0; w < warps; ++w)
     for (int l = 0; l < 32; ++l)
       th.emplace_back([&, w, l] {
-        tl.lane = l; tl.warp = &ws[(size_t)w]; tl.phase = 0; tl.smem = base;
+        tl.lane = l; tl.warp = &ws[(size_t)w]; tl.phase = 0; tl.smem = base; tl.cta = &cta_bar;
         threadIdx.x = (unsigned)(w * 32 + l); blockIdx.x = 0;
         kernel_body();
       });

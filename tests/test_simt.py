@@ -1,5 +1,5 @@
-"""The SOURCE of the segmentation kernels (blingfire_b200/csrc/sp_kernel.cu: sp_unigram_kernel, sp_bpe_kernel)
-compiled for the host over the SIMT shim (tests/simt: one OS thread per lane, full-mask warp intrinsics as
+"""The SOURCE of the kernels (blingfire_b200/csrc/wp_kernel.cu: wp_tokenize_kernel; sp_kernel.cu: sp_unigram_kernel,
+sp_bpe_kernel) compiled for the host over the SIMT shim (tests/simt: one OS thread per lane, full-mask warp intrinsics as
 rendezvous) and run on the CPU against the oracle: the warp-level logic itself -- shuffles, ballots, the
 register window of the Unigram relaxation, the streaming windows, the lane re-dealing of the BPE hard pass,
 the general path with offsets -- not a twin of it.  A kernel whose lanes do not reach the same intrinsics
@@ -118,3 +118,73 @@ def test_kernel_source_offsets(sim, name, unk):
     """TextToIdsWithOffsets_sp: the general path with the byte offsets carried through."""
     docs = corpus_docs(7, 60)
     check(sim, name, docs, 300, unk, offsets=True)
+
+
+# ---- the fused WordPiece kernel ----------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def wpsim():
+    L = ctypes.CDLL(os.path.join(ROOT, "tests", "simt", "libwp_simt.so"))
+    L.wpsim_load.restype = ctypes.c_void_p
+    L.wpsim_load.argtypes = [ctypes.c_char_p]
+    L.wpsim_error.restype = ctypes.c_char_p
+    L.wpsim_error.argtypes = [ctypes.c_void_p]
+    L.wpsim_free.argtypes = [ctypes.c_void_p]
+    L.wpsim_batch.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                              ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return L
+
+
+def check_wp(wpsim, name, docs, max_ids, unk=100, warps=4):
+    h = wpsim.wpsim_load(model_path(name).encode())
+    assert wpsim.wpsim_error(h) == b"", wpsim.wpsim_error(h)
+    o = Oracle()
+    ho = o.load(model_path(name))
+    offs = np.zeros(len(docs) + 1, np.int64)
+    np.cumsum([len(d) for d in docs], out=offs[1:])
+    buf = b"".join(docs) + b"\0"
+    ids = np.full((len(docs), max_ids), -7, np.int32)
+    counts = np.full(len(docs), -7, np.int32)
+    assert wpsim.wpsim_batch(h, buf, offs.ctypes.data, len(docs), ids.ctypes.data, counts.ctypes.data, max_ids, unk, warps) == 0
+    for i, d in enumerate(docs):
+        n, a = o.text_to_ids(ho, d, max_ids, unk)
+        assert counts[i] == n, (name, i, d[:60], int(counts[i]), n)
+        assert (ids[i, :n] == a[:n]).all(), (name, i, d[:60])
+        assert (ids[i, n:] == -7).all(), "a row was written beyond its count"
+    o.free(ho)
+    wpsim.wpsim_free(h)
+
+
+def wp_docs(seed, n):
+    rng = random.Random(seed)
+    lines = read_lines("test.multi.txt")[:3000] + read_lines("test.txt")[:3000]
+    docs = [b"", b" ", b"\xef\xbb\xbf", b"\xef\xbb\xbfhello", b"abc \xff def", b"\xe6\x88", b"hello\x00world", b"a" * 400,
+            b"a" * 1000 + b" " + b"b" * 700, "我".encode() * 900, b"ab" * 700 + b"\xff", b"." * 700, ("word " * 300).encode(),
+            b"x" * 573, b"y" * 571 + "é".encode(), ("é" * 700).encode(), b"\xf0\x9f\x98\x80" * 300, b"\x80" + b"a" * 600,
+            b"[unk] [UNK] [cls][sep] [mask] [unused0] [mas", b"don't stop-me now!!! (ok?)", b" ".join(lines[:80])]
+    for _ in range(n):
+        d = b" ".join(rng.choice(lines) for _ in range(rng.randint(1, 14)))
+        r = rng.random()
+        if r < 0.2:
+            d = d[: rng.randint(0, len(d))]
+        elif r < 0.3:
+            p = rng.randint(0, len(d))
+            d = d[:p] + bytes([rng.randint(0, 255)]) + d[p:]
+        elif r < 0.35:
+            d = bytes(rng.randint(0, 255) for _ in range(rng.randint(1, 60)))
+        docs.append(d)
+    return docs
+
+
+@pytest.mark.parametrize("name", ["bert_base_tok.bin", "bert_base_cased_tok.bin", "bert_chinese.bin"])
+def test_wp_kernel_source_matches_oracle(wpsim, name):
+    """wp_tokenize_kernel<uint16_t>: decode and validation, sync points, chunk ordering, walks, emission, and the
+    multi-window carry (documents beyond 576 code points), ragged and invalid inputs, truncation."""
+    docs = wp_docs(5, 320)
+    check_wp(wpsim, name, docs, 512)
+    check_wp(wpsim, name, docs[:120], 7, unk=7777)
+
+
+def test_wp_kernel_source_wide_table(wpsim):
+    """wp_tokenize_kernel<uint32_t>: bert_multi_cased (232k states x 10 004 classes, 32-bit table entries)."""
+    check_wp(wpsim, "bert_multi_cased.bin", wp_docs(9, 120), 512)
