@@ -188,3 +188,90 @@ def test_wp_kernel_source_matches_oracle(wpsim, name):
 def test_wp_kernel_source_wide_table(wpsim):
     """wp_tokenize_kernel<uint32_t>: bert_multi_cased (232k states x 10 004 classes, 32-bit table entries)."""
     check_wp(wpsim, "bert_multi_cased.bin", wp_docs(9, 120), 512)
+
+
+# ---- the generic lexer engine ------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def lexsim():
+    L = ctypes.CDLL(os.path.join(ROOT, "tests", "simt", "liblex_simt.so"))
+    L.lexsim_load.restype = ctypes.c_void_p
+    L.lexsim_load.argtypes = [ctypes.c_char_p]
+    L.lexsim_error.restype = ctypes.c_char_p
+    L.lexsim_error.argtypes = [ctypes.c_void_p]
+    L.lexsim_free.argtypes = [ctypes.c_void_p]
+    L.lexsim_ids.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.lexsim_triples.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_int]
+    return L
+
+
+def lex_docs(n):
+    lines = read_lines("test.multi.txt")[:n] + read_lines("test.txt")[:n]
+    return lines + [b" ".join(lines[i:i + 5]) for i in range(0, 2 * n, 40)] + [
+        b"\xef\xbb\xbfbom first", b"abc \xff def", b"a" * 400, "naïve café 我爱北京 [unk] qwrtzx".encode(), b" ", b"x", b"hello\x00world",
+        b"Dr. Smith went to Washington. He arrived at 5 p.m. It was late!", b"tab\tnew\nline\r\n"]
+
+
+@pytest.mark.parametrize("name", ["wbd.bin", "wbd_chuni.bin", "bert_base_tok.bin", "bert_chinese.bin"])
+def test_lexer_kernel_source_ids_and_offsets(lexsim, name):
+    """lex_decode_kernel -> lex_run_kernel -> lex_wp[_offsets]_kernel: TextToIds[WithOffsets]_wp for any [wbd] grammar."""
+    h = lexsim.lexsim_load(model_path(name).encode())
+    assert lexsim.lexsim_error(h) == b"", lexsim.lexsim_error(h)
+    o = Oracle()
+    ho = o.load(model_path(name))
+    docs = [d for d in lex_docs(150) if d]
+    offs = np.zeros(len(docs) + 1, np.int64)
+    np.cumsum([len(d) for d in docs], out=offs[1:])
+    buf = b"".join(docs) + b"\0"
+    for max_ids, with_offsets in ((256, True), (256, False), (3, True)):
+        ids = np.full((len(docs), max_ids), -7, np.int32)
+        counts = np.full(len(docs), -7, np.int32)
+        st = np.full((len(docs), max_ids), -7, np.int32)
+        en = np.full((len(docs), max_ids), -7, np.int32)
+        assert lexsim.lexsim_ids(h, buf, offs.ctypes.data, len(docs), ids.ctypes.data, counts.ctypes.data,
+                                 st.ctypes.data if with_offsets else None, en.ctypes.data if with_offsets else None, max_ids, 100, 2) == 0
+        for i, d in enumerate(docs):
+            n, a, s, e = o.text_to_ids_with_offsets(ho, d, max_ids, 100)
+            assert counts[i] == n and (ids[i, :n] == a[:n]).all() and (ids[i, n:] == -7).all(), (name, d[:60])
+            if with_offsets:
+                assert (st[i, :n] == s[:n]).all() and (en[i, :n] == e[:n]).all(), (name, d[:60])
+    o.free(ho)
+    lexsim.lexsim_free(h)
+
+
+@pytest.mark.parametrize("name", ["wbd.bin", "sbd.bin", "wbd_chuni.bin"])
+def test_lexer_kernel_source_triples(lexsim, name):
+    """The TextToWords / TextToSentences view (no charmap, U+0000 -> U+0020): the (Tag, From, To) triples of the lexer
+    kernels against FALexTools_t::Process in the oracle."""
+    h = lexsim.lexsim_load(model_path(name).encode())
+    assert lexsim.lexsim_error(h) == b"", lexsim.lexsim_error(h)
+    o = Oracle()
+    ho = o.load(model_path(name))
+    o.lib.bfo_lex_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    docs = [d for d in lex_docs(120) if d]
+    offs = np.zeros(len(docs) + 1, np.int64)
+    np.cumsum([len(d) for d in docs], out=offs[1:])
+    buf = b"".join(docs) + b"\0"
+    ncps = np.zeros(len(docs), np.int32)
+    tri = np.zeros(3 * int(offs[-1]) + 8, np.int32)
+    tri_count = np.zeros(len(docs), np.int32)
+    assert lexsim.lexsim_triples(h, buf, offs.ctypes.data, len(docs), ncps.ctypes.data, tri.ctypes.data, tri_count.ctypes.data, 2) == 0
+    for i, d in enumerate(docs):
+        try:
+            body = d[3:] if d[:3] == b"\xef\xbb\xbf" else d
+            cps = np.array([0x20 if ord(ch) == 0 else ord(ch) for ch in body.decode("utf-8")], np.int32)
+        except UnicodeDecodeError:
+            assert ncps[i] <= 0, d[:40]
+            continue
+        if len(cps) == 0:
+            assert ncps[i] <= 0
+            continue
+        assert ncps[i] == len(cps), d[:40]
+        exp = np.zeros(3 * len(cps) + 3, np.int32)
+        rn = o.lib.bfo_lex_process(ho, cps.ctypes.data, len(cps), exp.ctypes.data, 3 * len(cps))
+        got = tri[3 * int(offs[i]): 3 * int(offs[i]) + int(tri_count[i])]
+        assert tri_count[i] == rn and (got == exp[:rn]).all(), (name, d[:60])
+    o.free(ho)
+    lexsim.lexsim_free(h)
