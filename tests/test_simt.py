@@ -105,7 +105,7 @@ def test_kernel_source_long_documents(sim, name, unk):
     """Several windows per document: the streamed Unigram form (cuts at U+2581 and inside U+2581-free runs, the
     score carried over) and the sliding BPE window (split pass, cooperative pass, the general path behind)."""
     lines = read_lines("test.multi.txt")[:1200] + read_lines("test.txt")[:1200]
-    docs = [b" ".join(lines[i:i + 25]) for i in range(0, 200, 25)] + [b" ".join(lines[1200 + i:1200 + i + 25]) for i in range(0, 200, 25)]
+    docs = [b" ".join(lines[i:i + 25]) for i in range(0, 100, 25)] + [b" ".join(lines[1200 + i:1200 + i + 25]) for i in range(0, 100, 25)]
     docs += [b" ".join(lines[:40]) + b"\xff", b"\x80" + b" ".join(lines[60:100]), ("word " * 500).encode(), b"ab" * 700,
              "我爱北京天安门".encode() * 90, b"=" * 700 + b" x", ("ﬁ ½ ™ " * 300).encode(),
              b"https://homedepot.ugc.bazaarvoice.com/answers/submit/1999aa/product/205299499/question/4069427/undohelpfulness.djs?authsourcetype=__AUTHTYPE__&format=" * 5]
