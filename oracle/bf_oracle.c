@@ -455,7 +455,8 @@ static int init_seg(bfo_model* m, const int* v, int n) {
         case PARAM_FSM_TYPE: fsm_type = v[++i]; break;
         case PARAM_MAP_MODE: m->i2info_mode = v[++i]; break;
         case PARAM_FSM: if (fsm_type != TYPE_MEALY_DFA) return 0;
-                        if (!dfa_set(&m->seg_dfa, m->dumps[v[++i]], 1)) return 0; break;
+                        if (!dfa_set(&m->seg_dfa, m->dumps[v[++i]], 1)) return 0;
+                        break;
         case PARAM_ARRAY: ++i; break;  /* K2I: identity, never read on this path */
         case PARAM_CHARMAP: mmapf_set(&m->seg_charmap, m->dumps[v[++i]]); m->has_seg_charmap = 1; break;
         case PARAM_MULTI_MAP:
@@ -508,12 +509,17 @@ bfo_model* bfo_load_model(const char* path) {
 /* ---- UTF-8: FAUtf8Utils.cpp ---- */
 static int utf8_size_of_symbol(int s) {  /* :44-57 */
     unsigned u = (unsigned)s;
-    if (u <= 0x7F) return 1; if (u <= 0x7FF) return 2; if (u <= 0xFFFF) return 3; if (u <= 0x10FFFF) return 4;
+    if (u <= 0x7F) return 1;
+    if (u <= 0x7FF) return 2;
+    if (u <= 0xFFFF) return 3;
+    if (u <= 0x10FFFF) return 4;
     return 0;
 }
 static int utf8_size_of_lead(const char* p) {  /* :23-42 */
     int ch = (u8)*p;
-    if ((ch & 0x80) == 0) return 1; if ((ch & 0xE0) == 0xC0) return 2; if ((ch & 0xF0) == 0xE0) return 3;
+    if ((ch & 0x80) == 0) return 1;
+    if ((ch & 0xE0) == 0xC0) return 2;
+    if ((ch & 0xF0) == 0xE0) return 3;
     if ((ch & 0xF8) == 0xF0) return 4;
     return 0;
 }
@@ -1061,7 +1067,8 @@ static void* batch_worker(void* arg) {
 }
 int64_t bfo_text_to_ids_batch(const bfo_model* m, const char* utf8, const int64_t* offsets, int64_t ndocs,
                               int32_t* ids, int32_t* counts, int max_ids, int unk, int threads) {
-    if (threads < 1) threads = 1; if (threads > 256) threads = 256;
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
     batch_job jobs[256]; pthread_t th[256]; int64_t total = 0;
     for (int t = 0; t < threads; ++t) {
         batch_job j = { m, utf8, offsets, ndocs, ids, counts, max_ids, unk, t, threads, 0 }; jobs[t] = j;
