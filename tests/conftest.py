@@ -11,13 +11,15 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "timeout: per-test time limit (pytest-timeout; the SIMT tests deadlock on a malformed kernel)")
 
 
 @pytest.fixture(scope="session", autouse=True)
 def _built():
-    """Checkers (oracle, twin, corpus generator) are built on demand; the product .so is built by
-    __graft_entry__.build() and travels with the snapshot."""
+    """Checkers (oracle, twins, the kernel sources over the SIMT shim) are built on demand; the product .so is
+    built by __graft_entry__.build() and travels with the snapshot."""
     import subprocess
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "twin")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "simt")])
     yield
