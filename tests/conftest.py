@@ -21,5 +21,6 @@ def _built():
     import subprocess
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "twin")])
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "simt")])
+    # (not fatal here: only tests/test_simt.py needs these, and it fails on its own if they are missing)
+    subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "tests", "simt")])
     yield
