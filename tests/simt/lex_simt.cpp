@@ -45,11 +45,12 @@ LexLaunch make_launch(const LexerTables& T, const char* text, const int64_t* off
   S->text.assign((size_t)total + 64, 0);
   std::memcpy(S->text.data(), text, (size_t)total);
   const int tri_mul = words ? 1 : 2;
-  S->cls.assign((size_t)total + 8, 0);
-  S->ncps.assign((size_t)ndocs, 0);
-  S->tri_count.assign((size_t)ndocs, 0);
-  S->tri.assign((size_t)(3 * tri_mul) * (size_t)total + 8, 0);
-  if (want_boff) S->boff.assign((size_t)total + 8, 0);
+  // (device scratch is not zeroed: poison it)
+  S->cls.assign((size_t)total + 8, 0xCDCD);
+  S->ncps.assign((size_t)ndocs, (int32_t)0xCDCDCDCD);
+  S->tri_count.assign((size_t)ndocs, (int32_t)0xCDCDCDCD);
+  S->tri.assign((size_t)(3 * tri_mul) * (size_t)total + 8, (int32_t)0xCDCDCDCD);
+  if (want_boff) S->boff.assign((size_t)total + 8, (int32_t)0xCDCDCDCD);
   LexLaunch X{};
   X.text = S->text.data(); X.offsets = offsets; X.ndocs = ndocs; X.text_bytes = total; X.base_offset = offsets[0];
   X.cls_of_cp = words ? T.cls_words_of_cp.data() : T.cls_of_cp.data();

@@ -107,7 +107,7 @@ using std::min;
 
 namespace simt {
 inline void run_cta(int warps, size_t smem_bytes, const std::function<void()>& kernel_body) {
-  std::vector<uint8_t> smem(smem_bytes + 64);
+  std::vector<uint8_t> smem(smem_bytes + 64, 0xCD);   // shared memory is NOT zero at kernel start on the device either
   uint8_t* base = smem.data() + ((64 - (reinterpret_cast<uintptr_t>(smem.data()) & 63)) & 63);
   std::vector<Warp> ws((size_t)warps);
   std::barrier<> cta_bar(warps * 32);

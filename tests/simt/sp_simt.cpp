@@ -64,9 +64,9 @@ int spsim_batch(void* h, const char* text, const int64_t* offsets, int64_t ndocs
   for (int64_t d = 0; d < ndocs; ++d) max_len = std::max(max_len, offsets[d + 1] - offsets[d]);
   const int cap = (int)((S.has_charmap ? 2 * (max_len + 1) : max_len + 1) + 2);       // capi.cu launch_segmentation
   const int64_t per_warp = sp_arena_bytes_per_warp(cap, S.max_arc_len);
-  std::vector<uint8_t> arena((size_t)per_warp * (size_t)cta_warps + 64);
+  std::vector<uint8_t> arena((size_t)per_warp * (size_t)cta_warps + 64, 0xCD);   // cudaMalloc'ed scratch is not zeroed
   const int64_t ovf_entries = bpe ? sp_overflow_entries(cap, S.max_arc_len) : 1;
-  std::vector<uint8_t> overflow((size_t)ovf_entries * 16 + 64);
+  std::vector<uint8_t> overflow((size_t)ovf_entries * 16 + 64, 0xCD);
   // a padded copy of the text (the kernels read whole 32-bit words)
   const int64_t total = offsets[ndocs];
   std::vector<uint8_t> padded((size_t)total + 64, 0);
