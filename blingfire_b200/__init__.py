@@ -11,7 +11,7 @@ raises if lib/libblingfiretokdll.so is missing -- there is no CPU path to fall b
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_int32, c_int64, c_void_p
+from ctypes import c_bool, c_char_p, c_int, c_int32, c_int64, c_void_p
 
 import numpy as np
 
@@ -49,8 +49,20 @@ def lib():
         L.TextToIdsBatch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int]
         L.TextToIdsBatchCsr.restype = c_int64
         L.TextToIdsBatchCsr.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int]
+        L.TextToIdsBatchCsrU16.restype = c_int64
+        L.TextToIdsBatchCsrU16.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int]
         L.TextToIdsBatchDevice.restype = c_int
         L.TextToIdsBatchDevice.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]
+        L.TextToIdsBatchDeviceSized.restype = c_int
+        L.TextToIdsBatchDeviceSized.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]
+        L.BlingFireB200DeviceStatus.restype = c_int
+        L.BlingFireB200DeviceStatus.argtypes = [c_void_p, c_void_p]
+        L.BlingFireB200CompactDevice.restype = c_int64
+        L.BlingFireB200CompactDevice.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+        L.SetNoDummyPrefix.restype = c_int
+        L.SetNoDummyPrefix.argtypes = [c_void_p, c_bool]
+        L.IdsToText.restype = c_int
+        L.IdsToText.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_bool]
         L.BlingFireB200LastError.restype = c_char_p
         L.BlingFireB200KernelLaunches.restype = c_int64
         L.BlingFireB200ModelEngine.restype = c_int
@@ -95,6 +107,24 @@ def text_to_ids(h, s, max_len, unk=0, no_padding=False):
         raise RuntimeError(f"TextToIds failed: {last_error()}")
     out_count = min(max_len, t_count) if no_padding else max_len
     return o.view(np.uint32)[:out_count]
+
+
+def ids_to_text(h, ids, skip_special_tokens=True, output_buffer_size=None):
+    """dist-pypi/blingfire/__init__.py:256-270: the text of a sequence of ids ('' on any failure)."""
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    if output_buffer_size is None:
+        output_buffer_size = len(ids) * 32
+    o = ctypes.create_string_buffer(max(output_buffer_size, 1))
+    o_len = lib().IdsToText(c_void_p(h), ids.ctypes.data if len(ids) else None, len(ids), o, output_buffer_size,
+                            bool(skip_special_tokens))
+    if o_len == -1 or o_len > output_buffer_size:
+        return ""
+    return o.value.decode("utf-8")
+
+
+def change_settings_dummy_prefix(h, add_prefix):
+    """dist-pypi/blingfire/__init__.py:287-288."""
+    lib().SetNoDummyPrefix(c_void_p(h), not add_prefix)
 
 
 def utf8text_to_ids_with_offsets(h, s_bytes, max_len, unk=0, no_padding=False):
@@ -243,25 +273,50 @@ def text_to_ids_batch(h, docs, max_len, unk=0):
     return ids, counts
 
 
-def text_to_ids_batch_csr(h, docs, max_len, unk=0, capacity=None):
-    """Compact batch: returns (ids int32[total], id_offsets int64[n_docs+1])."""
+def text_to_ids_batch_csr(h, docs, max_len, unk=0, capacity=None, dtype=np.int32):
+    """Compact batch: returns (ids[total], id_offsets int64[n_docs+1]).  dtype=np.uint16 asks for 16-bit ids
+    (models whose ids all fit; halves the bytes that come back over PCIe).  The caller's arrays may be ordinary
+    (pageable) numpy memory: the library stages them through its own pinned buffers."""
     buf, offsets = docs if isinstance(docs, tuple) else make_csr(docs)
     n = len(offsets) - 1
     if capacity is None:
-        capacity = int(np.minimum(np.diff(offsets), max_len).clip(min=0).sum())
-    ids = np.empty(max(capacity, 1), dtype=np.int32)
+        # a first guess that fits natural text; the call reports the exact need if it does not
+        capacity = int(np.minimum(np.diff(offsets) + 1, max_len).clip(min=0).sum())
+    fn = lib().TextToIdsBatchCsrU16 if np.dtype(dtype) == np.uint16 else lib().TextToIdsBatchCsr
     id_offsets = np.zeros(n + 1, dtype=np.int64)
     buf = np.ascontiguousarray(buf)
-    r = lib().TextToIdsBatchCsr(c_void_p(h), buf.ctypes.data, offsets.ctypes.data, n, ids.ctypes.data, capacity,
-                                id_offsets.ctypes.data, max_len, unk)
-    if r < 0:
-        raise RuntimeError(f"TextToIdsBatchCsr failed ({r}): {last_error()}")
-    return ids[:r], id_offsets
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    for _ in range(2):
+        ids = np.empty(max(capacity, 1), dtype=dtype)
+        r = fn(c_void_p(h), buf.ctypes.data, offsets.ctypes.data, n, ids.ctypes.data, capacity, id_offsets.ctypes.data, max_len, unk)
+        if r >= 0:
+            return ids[:r], id_offsets
+        if r == -1 and last_error():
+            break
+        capacity = -r            # the batch needs this many ids: a [pos-dict] model can emit more ids than bytes
+    raise RuntimeError(f"TextToIdsBatchCsr failed ({r}): {last_error()}")
 
 
-def text_to_ids_batch_device(h, d_text, d_offsets, n_docs, total_bytes, d_ids, d_counts, max_len, unk=0, stream=0):
-    """Device-pointer entry: all arguments are raw device addresses (ints).  Asynchronous."""
-    r = lib().TextToIdsBatchDevice(c_void_p(h), c_void_p(d_text), c_void_p(d_offsets), n_docs, total_bytes,
-                                   c_void_p(d_ids), c_void_p(d_counts), max_len, unk, c_void_p(stream))
+def text_to_ids_batch_device(h, d_text, d_offsets, n_docs, total_bytes, d_ids, d_counts, max_len, unk=0, stream=0,
+                             max_doc_bytes=0):
+    """Device-pointer entry: all arguments are raw device addresses (ints).  Asynchronous; for [pos-dict]
+    models pass max_doc_bytes (>= the longest document) to keep it so."""
+    r = lib().TextToIdsBatchDeviceSized(c_void_p(h), c_void_p(d_text), c_void_p(d_offsets), n_docs, total_bytes, max_doc_bytes,
+                                        c_void_p(d_ids), c_void_p(d_counts), max_len, unk, c_void_p(stream))
     if r != 0:
         raise RuntimeError(f"TextToIdsBatchDevice failed: {last_error()}")
+
+
+def device_status(h, stream=0):
+    """Synchronises `stream`; raises if a kernel of the device-pointer calls on it reported an error."""
+    r = lib().BlingFireB200DeviceStatus(c_void_p(h), c_void_p(stream))
+    if r != 0:
+        raise RuntimeError(f"device batch failed ({r}): {last_error()}")
+
+
+def compact_device(d_ids, d_counts, n_docs, max_len, d_csr, d_row_off, stream=0):
+    """Row-major device ids -> CSR on the device (raw device addresses).  Asynchronous."""
+    r = lib().BlingFireB200CompactDevice(c_void_p(d_ids), c_void_p(d_counts), n_docs, max_len, c_void_p(d_csr), c_void_p(d_row_off),
+                                         c_void_p(stream))
+    if r != 0:
+        raise RuntimeError(f"BlingFireB200CompactDevice failed: {last_error()}")

@@ -1,24 +1,34 @@
 // capi.cu -- the C ABI (include/blingfiretokdll_b200.h): model lifecycle, device residency of
 // the flattened tables, and the host-side batch pipeline around the kernels.
 //
-// Host code only orchestrates: every tokenizing entry point runs wp_kernel.cu on the GPU.
-// There is deliberately no CPU path; if CUDA is unavailable the calls fail loudly.
+// Host code only orchestrates: every tokenizing entry point runs the kernels of wp_kernel.cu /
+// lex_kernel.cu / sp_kernel.cu on the GPU.  There is deliberately no CPU path; if CUDA is unavailable
+// the calls fail loudly.
+//
+// Concurrency: after LoadModel a model is immutable (SetNoDummyPrefix aside, like the reference,
+// blingfiretokdll.cpp:1670-1679) and every entry point is re-entrant: a call leases a private
+// working context (streams, device and pinned buffers) from the model's pool, so N caller threads on
+// one handle run N pipelines side by side (README.md:105 "can be called from multiple threads").
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/blingfiretokdll_b200.h"
+#include "copy_pool.h"
 #include "ldb.h"
 #include "lex_kernel.cuh"
 #include "lexer_tables.h"
@@ -56,6 +66,11 @@ struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+
+// CPUs of the current model's NUMA node (set by CtxLease for the duration of a call): pinned staging
+// memory is allocated while the calling thread runs there, so that first touch places it next to the GPU
+thread_local const cpu_set_t* g_numa_cpus = nullptr;
+
 template <typename T>
 struct PinBuf {
   T* p = nullptr;
@@ -64,7 +79,12 @@ struct PinBuf {
     if (n <= cap) return true;
     if (p) cudaFreeHost(p);
     p = nullptr; cap = 0;
-    if (!cuda_ok(cudaMallocHost(&p, n * sizeof(T)), "cudaMallocHost")) return false;
+    cpu_set_t saved;
+    const bool moved = g_numa_cpus && n * sizeof(T) >= (1u << 20) && sched_getaffinity(0, sizeof(saved), &saved) == 0 &&
+                       sched_setaffinity(0, sizeof(cpu_set_t), g_numa_cpus) == 0;
+    const bool ok = cuda_ok(cudaMallocHost(&p, n * sizeof(T)), "cudaMallocHost");
+    if (moved) sched_setaffinity(0, sizeof(saved), &saved);
+    if (!ok) return false;
     cap = n;
     return true;
   }
@@ -84,11 +104,12 @@ struct Slot {
   DevBuf<int32_t> ids;
   DevBuf<int32_t> counts;      // ndocs + 1 (trailing zero for the scan)
   DevBuf<int64_t> row_off;     // ndocs + 1
-  DevBuf<int32_t> csr;
+  DevBuf<int32_t> csr;         // compact ids of the chunk (int32, or uint16 packed two per word)
   DevBuf<unsigned long long> counter;
   PinBuf<int64_t> h_row_off;
-  PinBuf<int64_t> h_offsets;
-  PinBuf<int32_t> h_csr;       // only for the row-major host API
+  PinBuf<int64_t> h_offsets;   // staging of the chunk's document offsets when the caller's array is pageable
+  PinBuf<uint8_t> h_text;      // staging of the chunk's text when the caller's buffer is pageable
+  PinBuf<int32_t> h_csr;       // staging of the chunk's ids: row-major API, or a pageable CSR destination
   DevBuf<uint8_t> sp_arena;    // [pos-dict] engine: per-warp scratch for documents beyond the smem window
   DevBuf<uint8_t> sp_overflow; // [pos-dict] BPE: grid-wide arc scratch for segments beyond the private one
   // generic lexer engine scratch
@@ -96,11 +117,12 @@ struct Slot {
   DevBuf<int32_t> lex_ncps, lex_tri, lex_tri_count, lex_boff;
   // bookkeeping of the chunk in flight
   int64_t doc0 = 0, ndocs = 0;
+  int64_t out_base = 0, out_n = 0;      // where the chunk's ids go in the caller's CSR buffer
   void release() {
     lex_cls.release(); lex_ncps.release(); lex_tri.release(); lex_tri_count.release(); lex_boff.release();
     sp_arena.release(); sp_overflow.release();
     text.release(); offsets.release(); ids.release(); counts.release(); row_off.release(); csr.release();
-    counter.release(); h_row_off.release(); h_offsets.release(); h_csr.release();
+    counter.release(); h_row_off.release(); h_offsets.release(); h_text.release(); h_csr.release();
     if (counts_ready) cudaEventDestroy(counts_ready);
     counts_ready = nullptr;
     if (k_begin) cudaEventDestroy(k_begin);
@@ -109,6 +131,26 @@ struct Slot {
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
+};
+
+// everything one host call needs; leased from the model for the duration of the call
+struct Ctx {
+  Slot slots[kSlots];
+  PinBuf<int32_t> h_words;     // single-document calls: [ncps, tri_count, triples...] / ids, starts, ends
+  void release() {
+    for (auto& s : slots) s.release();
+    h_words.release();
+  }
+};
+
+// FAStringArray_pack (FAStringArray_pack.cpp:22-71): count, count+1 offsets, bytes
+struct I2w {
+  bool present = false;
+  std::vector<uint8_t> image;  // private copy of the dump
+  int count = 0;
+  const uint32_t* offsets = nullptr;
+  const uint8_t* data = nullptr;
+  int min_id = 0, max_id = 1000000000;     // FALimits::MaxArrSize (blingfiretokdll.cpp:999-1000)
 };
 
 struct Model {
@@ -129,9 +171,9 @@ struct Model {
   int32_t* d_act_data = nullptr;
   uint32_t* d_fn_ini = nullptr;
   uint16_t* d_cls_words = nullptr;
-  PinBuf<int32_t> h_words;     // TextToWords staging: [ncps, tri_count, triples...]
   // [pos-dict] engine (Unigram-LM / BPE over the Mealy automaton)
   SegTables S;
+  std::atomic<bool> no_dummy_prefix{false};   // SetNoDummyPrefix may flip it after load
   DaEntry* d_da = nullptr;
   uint16_t* d_sym = nullptr;
   SegInfo* d_info = nullptr;
@@ -140,14 +182,30 @@ struct Model {
   int32_t* d_norm_values = nullptr;
   int32_t* d_bpe_ord = nullptr;
   int32_t* d_bpe_id_of_ord = nullptr;
-  std::mutex mu;               // serialises the host-pointer entry points of this handle
-  Slot slots[kSlots];
-  DevBuf<unsigned long long> dev_counter;   // for the device-pointer entry point
+  I2w i2w;
+  int32_t max_tag = 0;         // largest id the model itself can emit (UnkId aside)
+
+  // working contexts of the host-pointer entry points
+  std::mutex pool_mu;
+  std::vector<std::unique_ptr<Ctx>> all_ctx;
+  std::vector<Ctx*> idle_ctx;
+  // device-pointer entry points: scratch per caller stream (work is stream-ordered, so a stream can
+  // reuse its scratch call after call), and a ring of work counters for the scratch-free engine
+  std::mutex dev_mu;
+  std::map<cudaStream_t, std::unique_ptr<Slot>> dev_slots;
+  DevBuf<unsigned long long> dev_counters;
+  std::atomic<uint32_t> dev_counter_next{0};
+  // pageable caller buffers: copy threads on the GPU's NUMA node
+  std::once_flag pool_once;
+  std::unique_ptr<CopyPool> copy_pool;
+  cpu_set_t numa_cpus;
+  bool numa_known = false;
 
   ~Model() {
     cudaSetDevice(device);
-    for (auto& s : slots) s.release();
-    dev_counter.release();
+    for (auto& c : all_ctx) c->release();
+    for (auto& kv : dev_slots) kv.second->release();
+    dev_counters.release();
     if (d_trans) cudaFree(d_trans);
     if (d_tag) cudaFree(d_tag);
     if (d_cls) cudaFree(d_cls);
@@ -165,9 +223,49 @@ struct Model {
     if (d_norm_values) cudaFree(d_norm_values);
     if (d_bpe_ord) cudaFree(d_bpe_ord);
     if (d_bpe_id_of_ord) cudaFree(d_bpe_id_of_ord);
-    h_words.release();
   }
 };
+
+// RAII lease of a working context
+struct CtxLease {
+  Model* m;
+  Ctx* c = nullptr;
+  const cpu_set_t* saved_numa;
+  explicit CtxLease(Model* model) : m(model), saved_numa(g_numa_cpus) {
+    std::lock_guard<std::mutex> l(m->pool_mu);
+    if (m->idle_ctx.empty()) {
+      m->all_ctx.emplace_back(new Ctx());
+      c = m->all_ctx.back().get();
+    } else {
+      c = m->idle_ctx.back();
+      m->idle_ctx.pop_back();
+    }
+    g_numa_cpus = m->numa_known ? &m->numa_cpus : nullptr;
+  }
+  ~CtxLease() {
+    g_numa_cpus = saved_numa;
+    std::lock_guard<std::mutex> l(m->pool_mu);
+    m->idle_ctx.push_back(c);
+  }
+};
+
+CopyPool* copy_pool_of(Model* m) {
+  std::call_once(m->pool_once, [m] {
+    int threads = 12;
+    if (const char* e = std::getenv("BLINGFIRE_B200_COPY_THREADS")) threads = std::max(0, std::atoi(e));
+    if (m->numa_known) threads = std::min(threads, std::max(1, CPU_COUNT(&m->numa_cpus) - 1));
+    m->copy_pool.reset(new CopyPool(threads, m->numa_known ? &m->numa_cpus : nullptr));
+  });
+  return m->copy_pool.get();
+}
+
+// true when the driver would stage a copy from/to this host pointer (plain malloc / numpy memory)
+bool is_pageable(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
 
 template <typename T>
 bool upload(T** dst, const T* src, size_t n, size_t slack_elems = 0) {
@@ -175,11 +273,53 @@ bool upload(T** dst, const T* src, size_t n, size_t slack_elems = 0) {
   return cuda_ok(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy(model)");
 }
 
+// blingfiretokdll.cpp:997-1045: the [i2w] section (string array dump, regular id range)
+bool load_i2w(const LdbImage& ldb, I2w* w) {
+  const std::vector<int>* v = ldb.conf().get(kFuncI2W);
+  if (!v) return true;
+  const int n = (int)v->size();
+  int dump = -1;
+  for (int i = 0; i < n; ++i) {
+    const int p = (*v)[i];
+    if (p == kParamStringArray && i + 1 < n) dump = (*v)[++i];
+    else if (p == kParamTokenIdMin && i + 1 < n) w->min_id = (*v)[++i];
+    else if (p == kParamTokenIdMax && i + 1 < n) w->max_id = (*v)[++i];
+  }
+  if (dump < 0) return true;
+  const Span d = ldb.dump(dump);
+  if (!d.p || d.n < 4) { set_error("[i2w]: bad string-array dump"); return false; }
+  w->image.assign(d.p, d.p + d.n);
+  uint32_t count;
+  std::memcpy(&count, w->image.data(), 4);
+  if (count > 0x7fffffffu || 4 + 4 * ((size_t)count + 1) > w->image.size()) { set_error("[i2w]: truncated string array"); return false; }
+  w->count = (int)count;
+  w->offsets = reinterpret_cast<const uint32_t*>(w->image.data() + 4);
+  w->data = w->image.data() + 4 + 4 * ((size_t)count + 1);
+  const size_t data_bytes = w->image.size() - (4 + 4 * ((size_t)count + 1));
+  for (int i = 0; i < w->count; ++i)
+    if (w->offsets[i + 1] < w->offsets[i] || w->offsets[i + 1] > data_bytes) { set_error("[i2w]: bad offsets"); return false; }
+  w->present = true;
+  return true;
+}
+
 Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
-  if (!cuda_ok(cudaGetDevice(&m->device), "cudaGetDevice")) return nullptr;
   m->has_wbd = ldb.conf().get(kFuncWbd) != nullptr;
   m->has_seg = ldb.conf().get(kFuncPosDict) != nullptr;
-  if (!m->has_wbd && !m->has_seg) { set_error("model has neither a [wbd] nor a [pos-dict] section"); return nullptr; }
+  if (!load_i2w(ldb, &m->i2w)) return nullptr;
+  if (!m->has_wbd && !m->has_seg) {
+    // an *.i2w file holds only the id -> text array (IdsToText); nothing to put on the GPU
+    if (m->i2w.present) return m.release();
+    set_error("model has neither a [wbd], a [pos-dict] nor an [i2w] section");
+    return nullptr;
+  }
+  if (!cuda_ok(cudaGetDevice(&m->device), "cudaGetDevice")) return nullptr;
+  {
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), m->device) == cudaSuccess && !std::getenv("BLINGFIRE_B200_NO_NUMA"))
+      m->numa_known = numa_cpus_of_pci(bus, &m->numa_cpus);
+    else
+      cudaGetLastError();
+  }
   if (m->has_wbd && !m->has_seg) {
     std::string err;
     if (!build_lexer_tables(ldb, &m->T, &err)) { set_error("lexer model: " + err); return nullptr; }
@@ -206,6 +346,8 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
     } else if (m->lex_ok && T.charmap_one_to_one) {
       m->engine = 2;
     }
+    for (int32_t t : T.tag_of_state) m->max_tag = std::max(m->max_tag, t);
+    for (int32_t t : T.act_data) m->max_tag = std::max(m->max_tag, t);
     // the dense table is the bulk of the host footprint; the device copy is the one that serves
     DenseVec<uint16_t>().swap(T.trans16);
     DenseVec<uint32_t>().swap(T.trans32);
@@ -228,6 +370,8 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
       if (!upload(&m->d_bpe_ord, S.bpe_ord.data(), S.bpe_ord.size(), 1)) return nullptr;
       if (!upload(&m->d_bpe_id_of_ord, S.bpe_id_of_ord.data(), S.bpe_id_of_ord.size(), 1)) return nullptr;
     }
+    m->no_dummy_prefix = S.no_dummy_prefix;
+    for (const SegInfo& i : S.info) if (i.id != INT32_MIN) m->max_tag = std::max<int64_t>(m->max_tag, (int64_t)i.id + S.id_offset);
     m->engine = 3;
   }
   return m.release();
@@ -238,7 +382,7 @@ SpModelDev make_sp_model(const Model* m) {
   const SegTables& S = m->S;
   d.da = m->d_da; d.root = S.root; d.sym_of_cp = m->d_sym; d.info = m->d_info; d.info_count = (int)S.info.size();
   d.norm_count = S.has_charmap ? m->d_norm_count : nullptr; d.norm_first = m->d_norm_first; d.norm_values = m->d_norm_values;
-  d.tok_algo = S.tok_algo; d.id_offset = S.id_offset; d.use_raw_bytes = S.use_raw_bytes; d.no_dummy_prefix = S.no_dummy_prefix;
+  d.tok_algo = S.tok_algo; d.id_offset = S.id_offset; d.use_raw_bytes = S.use_raw_bytes; d.no_dummy_prefix = m->no_dummy_prefix.load();
   d.delim_inside_tokens = S.delim_inside_tokens; d.delim_is_token = S.delim_is_token; d.max_arc_len = S.max_arc_len;
   d.bpe_ord = S.bpe_ord_ok ? m->d_bpe_ord : nullptr; d.bpe_id_of_ord = m->d_bpe_id_of_ord;
   d.bpe_singles_first = S.bpe_singles_first;
@@ -272,11 +416,11 @@ LexModelDev make_lex_model(const Model* m) {
 }
 
 // b0 = 4-byte-aligned absolute offset the device text starts at, first_off = offsets[doc0]
-LexLaunch make_lex_launch(const Model*, Slot& s, int64_t first_off, int64_t b0, int64_t b1, int64_t ndocs,
-                          const uint16_t* cls_table, int tri_mul) {
+LexLaunch make_lex_launch(Slot& s, const uint8_t* text_biased, const int64_t* d_offsets, int64_t first_off, int64_t b1,
+                          int64_t ndocs, const uint16_t* cls_table, int tri_mul) {
   LexLaunch X{};
-  X.text = s.text.p - b0;
-  X.offsets = s.offsets.p;
+  X.text = text_biased;
+  X.offsets = d_offsets;
   X.ndocs = ndocs;
   X.text_bytes = b1;
   X.base_offset = first_off;
@@ -296,19 +440,55 @@ bool ensure_stream(Slot& s) {
   return cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
 }
 
-// Enqueue one chunk [doc0, doc0+ndocs) of a host CSR batch on slot s: H2D, tokenize, scan, compact,
-// D2H of the row offsets.  Offsets stay absolute; the device text pointer is biased instead.
-// [pos-dict] engine over the documents already in s.text / s.offsets (absolute bytes [b0, b1)).
-// Documents whose symbols exceed the shared-memory window use a per-warp arena sized for the longest
-// document of the launch; the grid shrinks if the arena would not fit.  With starts/ends the offsets
-// ride in the arena as well.
-bool launch_segmentation(Model* m, Slot& s, int64_t b0, int64_t b1, int64_t ndocs, int64_t max_len, int32_t* d_ids,
-                         int32_t* d_starts, int32_t* d_ends, int max_ids, int unk, int* launches) {
+// ids a document of `len` bytes can produce at most (before the MaxIdsPerDoc cap): one per byte for the
+// lexer engines; the [pos-dict] front end prepends the dummy prefix and its charmap maps one code point
+// to up to two symbols per input symbol on average (blingfiretokdll.cpp:1387-1425: buffers of 2(n+1))
+inline int64_t max_ids_of_doc(const Model* m, int64_t len) {
+  if (len <= 0) return 0;
+  if (m->engine != 3) return len;
+  return m->S.has_charmap ? 2 * (len + 1) + 2 : len + 1;
+}
+
+// ---- small device helpers of the host pipeline (the tokenization itself is in the *_kernel.cu files) ----
+
+// UnkId == INT32_MIN collides with the fused kernel's "no piece starts here" marker: the kernel runs with
+// a stand-in and the ids are patched afterwards (one pass over the written part of the rows)
+__global__ void patch_unk_kernel(int32_t* ids, const int32_t* counts, int64_t ndocs, int max_ids, int32_t from, int32_t to) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t d = warp; d < ndocs; d += nwarps) {
+    const int c = counts[d];
+    int32_t* row = ids + d * (int64_t)max_ids;
+    for (int k = lane; k < c; k += 32) if (row[k] == from) row[k] = to;
+  }
+}
+
+// longest document of a device-resident batch (sizes the [pos-dict] engine's arena)
+__global__ void max_doc_len_kernel(const int64_t* offsets, int64_t ndocs, unsigned long long* out) {
+  unsigned long long mx = 0;
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < ndocs; d += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t len = offsets[d + 1] - offsets[d];
+    if (len > 0 && (unsigned long long)len > mx) mx = (unsigned long long)len;
+  }
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, mx, o); if (v > mx) mx = v; }
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
+}
+
+// ---- engines ----
+
+// [pos-dict] engine over documents already on the device.  Documents whose symbols exceed the
+// shared-memory window use a per-warp arena sized for the longest document of the launch; the grid
+// shrinks if the arena would not fit.  With starts/ends the offsets ride in the arena as well.
+bool launch_segmentation(Model* m, Slot& s, const uint8_t* text_biased, const int64_t* d_offsets, int64_t b1, int64_t ndocs,
+                         int64_t max_len, int32_t* d_ids, int32_t* d_counts, int32_t* d_starts, int32_t* d_ends, int max_ids,
+                         int unk, cudaStream_t stream, int* launches) {
   int64_t cap64 = (m->S.has_charmap ? 2 * (max_len + 1) : max_len + 1) + 2;
   const bool is_bpe = m->S.tok_algo == kTokenizeBpe || m->S.tok_algo == kTokenizeBpeOpt || m->S.tok_algo == kTokenizeBpeOptWithMerges;
-  // the Unigram fast path keeps everything in shared memory when even the worst-case staging fits;
-  // BPE always keeps its arc scratch in the arena
-  if (cap64 <= sp_fast_cap(m->S.tok_algo, m->S.max_arc_len, m->S.use_raw_bytes) && !d_starts) cap64 = 16;
+  // the Unigram fast path keeps everything in shared memory when even the worst-case staging fits
+  // (the same predicate the kernel uses: sp_kernel.cu fast_model); BPE always keeps its arc scratch in the arena
+  const bool unigram_fast = !is_bpe && !m->S.use_raw_bytes && !m->S.delim_inside_tokens && m->S.delim_is_token;
+  if (unigram_fast && cap64 <= sp_fast_cap(m->S.tok_algo, m->S.max_arc_len, m->S.use_raw_bytes) && !d_starts) cap64 = 16;
   if (cap64 > (1ll << 28)) { set_error("document too large for the segmentation engine"); return false; }
   const int cap = (int)cap64;
   const int64_t per_warp = sp_arena_bytes_per_warp(cap, m->S.max_arc_len);
@@ -321,15 +501,66 @@ bool launch_segmentation(Model* m, Slot& s, int64_t b0, int64_t b1, int64_t ndoc
   if (!s.sp_overflow.reserve((size_t)ovf_entries * 16)) return false;
   SpLaunch X{};
   X.overflow = s.sp_overflow.p; X.overflow_cap = ovf_entries;
-  X.text = s.text.p - b0; X.offsets = s.offsets.p; X.ndocs = ndocs; X.text_bytes = b1;
-  X.ids = d_ids; X.counts = s.counts.p; X.starts = d_starts; X.ends = d_ends; X.max_ids = max_ids; X.unk_id = unk;
+  X.text = text_biased; X.offsets = d_offsets; X.ndocs = ndocs; X.text_bytes = b1;
+  X.ids = d_ids; X.counts = d_counts; X.starts = d_starts; X.ends = d_ends; X.max_ids = max_ids; X.unk_id = unk;
   X.work_counter = s.counter.p; X.arena = s.sp_arena.p; X.arena_stride = per_warp; X.arena_cap = cap; X.grid_warps = warps;
-  return cuda_ok(sp_tokenize_launch(X, make_sp_model(m), s.stream, launches), "segmentation launch");
+  return cuda_ok(sp_tokenize_launch(X, make_sp_model(m), stream, launches), "segmentation launch");
 }
 
-bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, int64_t doc0, int64_t ndocs,
-                   int max_ids, int unk) {
+// generic lexer engine (any [wbd] grammar): decode/classify -> Process_int triples -> wp post-pass
+bool launch_lexer_ids(Model* m, Slot& s, const uint8_t* text_biased, const int64_t* d_offsets, int64_t first_off, int64_t b1,
+                      int64_t ndocs, int32_t* d_ids, int32_t* d_counts, int max_ids, int unk, cudaStream_t stream, int* launches) {
+  const size_t span = (size_t)(b1 - first_off) + 8;
+  if (!s.lex_cls.reserve(span) || !s.lex_ncps.reserve((size_t)ndocs) || !s.lex_tri_count.reserve((size_t)ndocs) ||
+      !s.lex_tri.reserve(6 * span))
+    return false;
+  LexLaunch X = make_lex_launch(s, text_biased, d_offsets, first_off, b1, ndocs, m->d_cls, 2);
+  if (!cuda_ok(lex_launch(X, make_lex_model(m), stream, launches), "lexer launch")) return false;
+  return cuda_ok(lex_wp_launch(X, d_ids, d_counts, max_ids, unk, stream, launches), "post-pass launch");
+}
+
+// fused WordPiece kernel.  `counter` = a zeroable device word private to this launch.
+bool launch_wordpiece(Model* m, const uint8_t* text_biased, const int64_t* d_offsets, int64_t b1, int64_t ndocs, int32_t* d_ids,
+                      int32_t* d_counts, int max_ids, int unk, unsigned long long* counter, cudaStream_t stream, int* launches) {
+  WpLaunch L = make_launch(m);
+  L.text = text_biased;            // biased: absolute offsets index it directly
+  L.offsets = d_offsets;
+  L.ndocs = ndocs;
+  L.text_bytes = b1;
+  L.ids = d_ids;
+  L.counts = d_counts;
+  L.max_ids = max_ids;
+  // the kernel marks positions without a piece with INT32_MIN; an UnkId of that value runs under a stand-in
+  // no rule id of the model can equal (rule ids are the model's own, max_tag < INT32_MAX) and is patched back
+  const bool patch = unk == INT32_MIN;
+  L.unk_id = patch ? INT32_MAX : unk;
+  L.work_counter = counter;
+  WpLaunchInfo info{};
+  if (!cuda_ok(wp_tokenize_launch(L, stream, &info), "tokenize launch")) return false;
+  *launches += info.launches;
+  if (patch && ndocs > 0) {
+    patch_unk_kernel<<<(int)std::min<int64_t>((ndocs + 7) / 8, 148 * 16), 256, 0, stream>>>(d_ids, d_counts, ndocs, max_ids, INT32_MAX, INT32_MIN);
+    if (!cuda_ok(cudaGetLastError(), "patch launch")) return false;
+    *launches += 1;
+  }
+  return true;
+}
+
+// how the ids of a host batch travel back
+enum class OutKind { kCsr32, kCsr16 };
+
+struct HostBatch {
+  const char* utf8; const int64_t* offsets; int64_t ndocs; int max_ids; int unk;
+  bool stage_in = false;       // the caller's text/offsets are pageable: stage through pinned chunk buffers
+  OutKind out = OutKind::kCsr32;
+};
+
+// Enqueue one chunk [doc0, doc0+ndocs) of a host CSR batch on slot s: H2D, tokenize, scan, compact,
+// D2H of the row offsets.  Offsets stay absolute; the device text pointer is biased instead.
+bool enqueue_chunk(Model* m, Slot& s, const HostBatch& B, int64_t doc0, int64_t ndocs) {
   if (!ensure_stream(s)) return false;
+  const int64_t* offsets = B.offsets;
+  const int max_ids = B.max_ids;
   const int64_t b0 = offsets[doc0] & ~(int64_t)3;       // keep 32-bit word alignment of absolute offsets
   const int64_t b1 = offsets[doc0 + ndocs];
   const size_t nbytes = (size_t)(b1 - b0);
@@ -337,53 +568,50 @@ bool enqueue_chunk(Model* m, Slot& s, const char* utf8, const int64_t* offsets, 
       !s.row_off.reserve((size_t)ndocs + 1) || !s.ids.reserve((size_t)ndocs * (size_t)max_ids) ||
       !s.counter.reserve(2) || !s.h_row_off.reserve((size_t)ndocs + 2))
     return false;
-  // a document yields at most one id per byte and at most max_ids ids
   size_t csr_cap = 0;
+  int64_t max_len = 0;
   for (int64_t d = doc0; d < doc0 + ndocs; ++d) {
     const int64_t len = offsets[d + 1] - offsets[d];
-    if (len > 0) csr_cap += (size_t)std::min<int64_t>(len, max_ids);
+    max_len = std::max(max_len, len);
+    csr_cap += (size_t)std::min<int64_t>(max_ids_of_doc(m, len), max_ids);
   }
-  if (!s.csr.reserve(csr_cap + 1)) return false;
+  if (!s.csr.reserve(csr_cap + 2)) return false;
 
-  if (nbytes && !cuda_ok(cudaMemcpyAsync(s.text.p, utf8 + b0, nbytes, cudaMemcpyHostToDevice, s.stream), "H2D text")) return false;
-  if (!cuda_ok(cudaMemcpyAsync(s.offsets.p, offsets + doc0, ((size_t)ndocs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream), "H2D offsets")) return false;
+  const char* text_src = B.utf8 + b0;
+  const int64_t* offs_src = offsets + doc0;
+  if (B.stage_in) {
+    if (!s.h_text.reserve(nbytes + 64) || !s.h_offsets.reserve((size_t)ndocs + 1)) return false;
+    copy_pool_of(m)->copy(s.h_text.p, text_src, nbytes);
+    std::memcpy(s.h_offsets.p, offs_src, ((size_t)ndocs + 1) * sizeof(int64_t));
+    text_src = (const char*)s.h_text.p;
+    offs_src = s.h_offsets.p;
+  }
+  if (nbytes && !cuda_ok(cudaMemcpyAsync(s.text.p, text_src, nbytes, cudaMemcpyHostToDevice, s.stream), "H2D text")) return false;
+  if (!cuda_ok(cudaMemcpyAsync(s.offsets.p, offs_src, ((size_t)ndocs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream), "H2D offsets")) return false;
 
-  WpLaunchInfo info{};
+  int nl = 0;
   if (!cuda_ok(cudaEventRecord(s.k_begin, s.stream), "event record")) return false;
+  const uint8_t* text_biased = s.text.p - b0;
   if (m->engine == 3) {
-    int64_t max_len = 0;
-    for (int64_t d = doc0; d < doc0 + ndocs; ++d) max_len = std::max(max_len, offsets[d + 1] - offsets[d]);
-    int nl = 0;
-    if (!launch_segmentation(m, s, b0, b1, ndocs, max_len, s.ids.p, nullptr, nullptr, max_ids, unk, &nl)) return false;
-    info.launches = nl;
-  } else if (m->engine == 2) {
-    // generic lexer: decode/classify -> Process_int triples -> wp post-pass
-    const size_t span = (size_t)(b1 - offsets[doc0]) + 8;
-    if (!s.lex_cls.reserve(span) || !s.lex_ncps.reserve((size_t)ndocs) || !s.lex_tri_count.reserve((size_t)ndocs) ||
-        !s.lex_tri.reserve(6 * span))
+    if (!launch_segmentation(m, s, text_biased, s.offsets.p, b1, ndocs, max_len, s.ids.p, s.counts.p, nullptr, nullptr, max_ids, B.unk,
+                             s.stream, &nl))
       return false;
-    LexLaunch X = make_lex_launch(m, s, offsets[doc0], b0, b1, ndocs, m->d_cls, 2);
-    int nl = 0;
-    if (!cuda_ok(lex_launch(X, make_lex_model(m), s.stream, &nl), "lexer launch")) return false;
-    if (!cuda_ok(lex_wp_launch(X, s.ids.p, s.counts.p, max_ids, unk, s.stream, &nl), "post-pass launch")) return false;
-    info.launches = nl;
+  } else if (m->engine == 2) {
+    if (!launch_lexer_ids(m, s, text_biased, s.offsets.p, offsets[doc0], b1, ndocs, s.ids.p, s.counts.p, max_ids, B.unk, s.stream, &nl))
+      return false;
   } else {
-    WpLaunch L = make_launch(m);
-    L.text = s.text.p - b0;            // biased: absolute offsets index it directly
-    L.offsets = s.offsets.p;
-    L.ndocs = ndocs;
-    L.text_bytes = b1;
-    L.ids = s.ids.p;
-    L.counts = s.counts.p;
-    L.max_ids = max_ids;
-    L.unk_id = unk;
-    L.work_counter = s.counter.p;
-    if (!cuda_ok(wp_tokenize_launch(L, s.stream, &info), "tokenize launch")) return false;
+    if (!launch_wordpiece(m, text_biased, s.offsets.p, b1, ndocs, s.ids.p, s.counts.p, max_ids, B.unk, s.counter.p, s.stream, &nl))
+      return false;
   }
   if (!cuda_ok(cudaEventRecord(s.k_end, s.stream), "event record")) return false;
   if (!cuda_ok(wp_scan_counts(s.counts.p, s.row_off.p, ndocs, s.stream), "scan")) return false;
-  if (!cuda_ok(wp_compact_launch(s.ids.p, s.counts.p, s.row_off.p, ndocs, max_ids, s.csr.p, s.stream), "compact")) return false;
-  g_launches += info.launches + 2;
+  if (B.out == OutKind::kCsr16) {
+    if (!cuda_ok(wp_compact_launch_u16(s.ids.p, s.counts.p, s.row_off.p, ndocs, max_ids, reinterpret_cast<uint16_t*>(s.csr.p), s.stream), "compact"))
+      return false;
+  } else if (!cuda_ok(wp_compact_launch(s.ids.p, s.counts.p, s.row_off.p, ndocs, max_ids, s.csr.p, s.stream), "compact")) {
+    return false;
+  }
+  g_launches += nl + 2;
   if (!cuda_ok(cudaMemcpyAsync(s.h_row_off.p, s.row_off.p, ((size_t)ndocs + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream), "D2H offsets")) return false;
   // the kernel's error word sits right after the work counter (only the [pos-dict] engine sets it)
   s.h_row_off.p[ndocs + 1] = 0;
@@ -419,26 +647,25 @@ int64_t chunk_docs(const int64_t* offsets, int64_t doc0, int64_t ndocs_total, in
   return d - doc0;
 }
 
-// Runs the whole host batch through a three-slot pipeline so that the H2D copy of chunk c, the
+// Runs the whole host batch through a pipeline of kSlots chunks so that the H2D copy of chunk c, the
 // kernels of chunk c-1 and the D2H copy of chunk c-2 overlap (PCIe is full duplex).
 //   issue(slot)   called in chunk order once the chunk's row offsets are on the host
 //                 (slot.h_row_off); enqueues the asynchronous D2H of the ids on slot.stream
 //   finish(slot)  called in chunk order once that D2H has completed (host-side post-processing)
 template <typename Issue, typename Finish>
-bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, int max_ids, int unk,
-                  Issue issue, Finish finish) {
+bool run_pipeline(Model* m, Ctx* ctx, const HostBatch& B, Issue issue, Finish finish) {
   if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return false;
   g_last_kernel_ms = 0.0;
   bool copying[kSlots] = {};
   auto settle = [&](int si) -> bool {   // wait for the ids copy of the chunk that last used slot si
     if (!copying[si]) return true;
     copying[si] = false;
-    Slot& s = m->slots[si];
+    Slot& s = ctx->slots[si];
     if (!cuda_ok(cudaStreamSynchronize(s.stream), "sync")) return false;
     return finish(s);
   };
   auto counts_ready = [&](int si) -> bool {   // kernels of the chunk in slot si are done
-    Slot& s = m->slots[si];
+    Slot& s = ctx->slots[si];
     if (!cuda_ok(cudaEventSynchronize(s.counts_ready), "event sync")) return false;
     float kms = 0.0f;
     if (cudaEventElapsedTime(&kms, s.k_begin, s.k_end) == cudaSuccess) g_last_kernel_ms += kms;
@@ -452,17 +679,18 @@ bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t nd
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_begin = now();
   double t_settle = 0, t_enqueue = 0, t_counts = 0;
-  while (d < ndocs) {
+  bool ok = true;
+  while (ok && d < B.ndocs) {
     const int si = c % kSlots;
     double t0 = now();
-    if (!settle(si)) return false;
+    if (!settle(si)) { ok = false; break; }
     double t1 = now();
-    const int64_t nd = chunk_docs(offsets, d, ndocs, max_ids, m->engine);
-    if (!enqueue_chunk(m, m->slots[si], utf8, offsets, d, nd, max_ids, unk)) return false;
+    const int64_t nd = chunk_docs(B.offsets, d, B.ndocs, B.max_ids, m->engine);
+    if (!enqueue_chunk(m, ctx->slots[si], B, d, nd)) { ok = false; break; }
     double t2 = now();
     // chunk c-kAhead: its kernels had kAhead chunks of queued work behind them, so the copy
     // engines and the SMs never wait for the host
-    if (c >= kAhead && !counts_ready((c - kAhead) % kSlots)) return false;
+    if (c >= kAhead && !counts_ready((c - kAhead) % kSlots)) { ok = false; break; }
     double t3 = now();
     t_settle += t1 - t0; t_enqueue += t2 - t1; t_counts += t3 - t2;
     d += nd; ++c;
@@ -470,19 +698,79 @@ bool run_pipeline(Model* m, const char* utf8, const int64_t* offsets, int64_t nd
   if (trace)
     std::fprintf(stderr, "[bfb200] pipeline: %d chunks, loop %.2f ms (settle %.2f, enqueue %.2f, wait-counts %.2f)\n", c,
                  now() - t_begin, t_settle, t_enqueue, t_counts);
-  for (int k = c >= kAhead ? c - kAhead : 0; k < c; ++k)       // the chunks whose counts were not consumed yet
-    if (!counts_ready(k % kSlots)) return false;
-  for (int k = c >= kSlots ? c - kSlots : 0; k < c; ++k)       // the chunks still copying, oldest first
-    if (!settle(k % kSlots)) return false;
-  return true;
+  if (ok)
+    for (int k = c >= kAhead ? c - kAhead : 0; k < c && ok; ++k)     // the chunks whose counts were not consumed yet
+      ok = counts_ready(k % kSlots);
+  if (ok)
+    for (int k = c >= kSlots ? c - kSlots : 0; k < c && ok; ++k)     // the chunks still copying, oldest first
+      ok = settle(k % kSlots);
+  if (!ok) {
+    // the context goes back to the pool: nothing of this call may still be in flight on its streams
+    const std::string keep = g_last_error;
+    for (auto& s : ctx->slots) if (s.stream) cudaStreamSynchronize(s.stream);
+    cudaGetLastError();
+    g_last_error = keep;
+  }
+  return ok;
 }
 
 bool check_batch_args(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, int max_ids) {
-  g_last_error.clear();
   if (!m) { set_error("null model"); return false; }
-  if (m->engine == 0) { set_error("no GPU engine for this model type yet"); return false; }
+  if (m->engine == 0) { set_error("no GPU engine for this model type"); return false; }
   if (ndocs < 0 || max_ids < 0 || (ndocs > 0 && (!utf8 || !offsets))) { set_error("bad batch arguments"); return false; }
   return true;
+}
+
+// the compact-output batch call behind TextToIdsBatchCsr / TextToIdsBatchCsrU16
+template <typename OutT>
+int64_t batch_csr(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, OutT* ids_csr, int64_t capacity,
+                  int64_t* id_offsets, int max_ids, int unk) {
+  if (!check_batch_args(m, utf8, offsets, ndocs, max_ids)) return -1;
+  if (!id_offsets || (capacity > 0 && !ids_csr)) { set_error("bad output arguments"); return -1; }
+  if (sizeof(OutT) == 2 && (m->max_tag > 0xFFFF || unk < 0 || unk > 0xFFFF)) {
+    set_error("16-bit ids need a model whose ids (and UnkId) fit 16 bits");
+    return -1;
+  }
+  if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
+  CtxLease lease(m);
+  HostBatch B{utf8, offsets, ndocs, max_ids, unk};
+  B.stage_in = ndocs > 0 && is_pageable(utf8);
+  B.out = sizeof(OutT) == 2 ? OutKind::kCsr16 : OutKind::kCsr32;
+  const bool stage_out = capacity > 0 && is_pageable(ids_csr);
+  int64_t total = 0;
+  bool overflow = false;
+  id_offsets[0] = 0;
+  auto issue = [&](Slot& s) -> bool {
+    const int64_t n = s.h_row_off.p[s.ndocs];
+    for (int64_t i = 0; i < s.ndocs; ++i) id_offsets[s.doc0 + i + 1] = total + s.h_row_off.p[i + 1];
+    s.out_base = total; s.out_n = 0;
+    if (total + n > capacity) overflow = true;
+    else if (n > 0) {
+      void* dst = ids_csr + total;
+      if (stage_out) {
+        if (!s.h_csr.reserve(((size_t)n * sizeof(OutT) + 3) / 4 + 1)) return false;
+        dst = s.h_csr.p;
+        s.out_n = n;
+      }
+      if (!cuda_ok(cudaMemcpyAsync(dst, s.csr.p, (size_t)n * sizeof(OutT), cudaMemcpyDeviceToHost, s.stream), "D2H ids")) return false;
+    }
+    total += n;
+    return true;
+  };
+  auto finish = [&](Slot& s) -> bool {
+    if (s.out_n > 0) copy_pool_of(m)->copy(ids_csr + s.out_base, s.h_csr.p, (size_t)s.out_n * sizeof(OutT));
+    return true;
+  };
+  if (!run_pipeline(m, lease.c, B, issue, finish)) return -1;
+  return overflow ? -total : total;
+}
+
+// per-stream scratch of the device-pointer entry points
+Slot* dev_slot_of(Model* m, cudaStream_t stream) {
+  std::lock_guard<std::mutex> l(m->dev_mu);
+  auto& p = m->dev_slots[stream];
+  if (!p) p.reset(new Slot());
+  return p.get();
 }
 
 }  // namespace
@@ -521,57 +809,149 @@ int FreeModel(void* h) {
   return 1;
 }
 
-int TextToIdsBatchDevice(void* h, const char* d_utf8, const int64_t* d_offsets, int64_t ndocs, int64_t total_bytes,
-                         int32_t* d_ids, int32_t* d_counts, int max_ids, int unk, void* stream) {
+// blingfiretokdll.cpp:1669-1679
+int SetNoDummyPrefix(void* h, bool fNoDummyPrefix) {
+  if (!h) return 0;
+  ((Model*)h)->no_dummy_prefix = fNoDummyPrefix;
+  return 1;
+}
+
+// blingfiretokdll.cpp:1689-1745.  A table read on the host, like the reference's: there is no arithmetic
+// to move to the GPU (the id -> text array stays in host memory next to the caller's buffers).
+int IdsToText(void* h, const int32_t* ids, const int count, char* out, const int max_out, bool skip_special) {
+  if (!h) return 0;
+  if (count == 0 || !ids) return 0;
+  const Model* m = (const Model*)h;
+  if (!m->i2w.present) return 0;
+  int len = 0;
+  for (int i = 0; i < count; ++i) {
+    const int id = ids[i];
+    if (skip_special && (id < m->i2w.min_id || id > m->i2w.max_id)) continue;       // :1712
+    if (id < 0 || id >= m->i2w.count) return 0;                                       // unknown id (:1719-1721)
+    const uint8_t* tok = m->i2w.data + m->i2w.offsets[id];
+    int tl = (int)(m->i2w.offsets[id + 1] - m->i2w.offsets[id]);
+    if (len == 0 && tl > 0 && tok[0] == 0x20) { ++tok; --tl; }                       // no leading space (:1724-1727)
+    if (tl > 0 && max_out - len >= tl) std::memcpy(out + len, tok, (size_t)tl);
+    len += tl;
+  }
+  if (max_out > len) out[len] = 0;
+  return len + 1;
+}
+
+int TextToIdsBatchDeviceSized(void* h, const char* d_utf8, const int64_t* d_offsets, int64_t ndocs, int64_t total_bytes,
+                              int64_t max_doc_bytes, int32_t* d_ids, int32_t* d_counts, int max_ids, int unk, void* stream_) {
   try {
+    g_last_error.clear();
     Model* m = (Model*)h;
-    if (!m || m->engine != 1) { set_error(m ? "no GPU engine for this model type yet" : "null model"); return -1; }
+    if (!m || m->engine == 0) { set_error(m ? "no GPU engine for this model type" : "null model"); return -1; }
     if (ndocs == 0) return 0;
     if (ndocs < 0 || !d_utf8 || !d_offsets || !d_ids || !d_counts || max_ids < 0) { set_error("bad arguments"); return -1; }
-    if (!m->dev_counter.reserve(1)) return -1;
-    WpLaunch L = make_launch(m);
-    L.text = (const uint8_t*)d_utf8; L.offsets = d_offsets; L.ndocs = ndocs; L.text_bytes = total_bytes;
-    L.ids = d_ids; L.counts = d_counts; L.max_ids = max_ids; L.unk_id = unk; L.work_counter = m->dev_counter.p;
-    WpLaunchInfo info{};
-    if (!cuda_ok(wp_tokenize_launch(L, (cudaStream_t)stream, &info), "tokenize launch")) return -1;
-    g_launches += info.launches;
+    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int nl = 0;
+    if (m->engine == 1) {
+      // every call takes the next word of a ring: calls on different streams never share a work counter
+      constexpr uint32_t kRing = 1024;
+      {
+        std::lock_guard<std::mutex> l(m->dev_mu);
+        if (!m->dev_counters.reserve(kRing)) return -1;
+      }
+      unsigned long long* counter = m->dev_counters.p + (m->dev_counter_next.fetch_add(1) % kRing);
+      if (!launch_wordpiece(m, (const uint8_t*)d_utf8, d_offsets, total_bytes, ndocs, d_ids, d_counts, max_ids, unk, counter, stream, &nl))
+        return -1;
+    } else {
+      Slot& s = *dev_slot_of(m, stream);      // stream-ordered reuse of the scratch
+      if (m->engine == 3) {
+        if (!s.counter.reserve(4)) return -1;
+        if (max_doc_bytes <= 0) {
+          // size the arena from the batch itself: one small kernel and a 8-byte read back (synchronises the stream)
+          unsigned long long* dmax = s.counter.p + 2;
+          if (!cuda_ok(cudaMemsetAsync(dmax, 0, 8, stream), "memset")) return -1;
+          max_doc_len_kernel<<<(int)std::min<int64_t>((ndocs + 255) / 256, 1184), 256, 0, stream>>>(d_offsets, ndocs, dmax);
+          unsigned long long hmax = 0;
+          if (!cuda_ok(cudaMemcpyAsync(&hmax, dmax, 8, cudaMemcpyDeviceToHost, stream), "D2H") ||
+              !cuda_ok(cudaStreamSynchronize(stream), "sync"))
+            return -1;
+          max_doc_bytes = (int64_t)hmax;
+          ++nl;
+        }
+        if (!launch_segmentation(m, s, (const uint8_t*)d_utf8, d_offsets, total_bytes, ndocs, max_doc_bytes, d_ids, d_counts, nullptr,
+                                 nullptr, max_ids, unk, stream, &nl))
+          return -1;
+      } else {
+        if (!launch_lexer_ids(m, s, (const uint8_t*)d_utf8, d_offsets, 0, total_bytes, ndocs, d_ids, d_counts, max_ids, unk, stream, &nl))
+          return -1;
+      }
+    }
+    g_launches += nl;
     return 0;
   } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
+int TextToIdsBatchDevice(void* h, const char* d_utf8, const int64_t* d_offsets, int64_t ndocs, int64_t total_bytes,
+                         int32_t* d_ids, int32_t* d_counts, int max_ids, int unk, void* stream) {
+  return TextToIdsBatchDeviceSized(h, d_utf8, d_offsets, ndocs, total_bytes, 0, d_ids, d_counts, max_ids, unk, stream);
+}
+
+// the [pos-dict] kernels raise a flag instead of guessing when their scratch cannot hold a document
+int BlingFireB200DeviceStatus(void* h, void* stream_) {
+  try {
+    g_last_error.clear();
+    Model* m = (Model*)h;
+    if (!m) { set_error("null model"); return -1; }
+    if (m->engine != 3) return 0;
+    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Slot& s = *dev_slot_of(m, stream);
+    if (!s.counter.p) return 0;
+    unsigned long long flag = 0;
+    if (!cuda_ok(cudaMemcpyAsync(&flag, s.counter.p + 1, 8, cudaMemcpyDeviceToHost, stream), "D2H") ||
+        !cuda_ok(cudaStreamSynchronize(stream), "sync"))
+      return -1;
+    const int f = (int)(flag & 0xffffffffu);
+    if (f) set_error("segmentation engine: scratch exhausted (code " + std::to_string(f) + ")");
+    return f;
+  } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
+int64_t BlingFireB200CompactDevice(const int32_t* d_ids, const int32_t* d_counts, int64_t ndocs, int max_ids, int32_t* d_csr,
+                                   int64_t* d_row_off, void* stream_) {
+  g_last_error.clear();
+  if (ndocs < 0 || !d_counts || !d_row_off || (ndocs > 0 && (!d_ids || !d_csr))) { set_error("bad arguments"); return -1; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!cuda_ok(wp_scan_counts(d_counts, d_row_off, ndocs, stream), "scan")) return -1;
+  if (!cuda_ok(wp_compact_launch(d_ids, d_counts, d_row_off, ndocs, max_ids, d_csr, stream), "compact")) return -1;
+  g_launches += 2;
+  return 0;
 }
 
 int64_t TextToIdsBatchCsr(void* h, const char* utf8, const int64_t* offsets, int64_t ndocs, int32_t* ids_csr,
                           int64_t capacity, int64_t* id_offsets, int max_ids, int unk) {
   try {
-    Model* m = (Model*)h;
-    if (!check_batch_args(m, utf8, offsets, ndocs, max_ids)) return -1;
-    if (!id_offsets || (capacity > 0 && !ids_csr)) { set_error("bad output arguments"); return -1; }
-    std::lock_guard<std::mutex> lock(m->mu);
-    int64_t total = 0;
-    bool overflow = false;
-    id_offsets[0] = 0;
-    auto issue = [&](Slot& s) -> bool {
-      const int64_t n = s.h_row_off.p[s.ndocs];
-      for (int64_t i = 0; i < s.ndocs; ++i) id_offsets[s.doc0 + i + 1] = total + s.h_row_off.p[i + 1];
-      if (total + n > capacity) overflow = true;
-      else if (n > 0 &&
-               !cuda_ok(cudaMemcpyAsync(ids_csr + total, s.csr.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream), "D2H ids"))
-        return false;
-      total += n;
-      return true;
-    };
-    auto finish = [&](Slot&) -> bool { return true; };
-    if (!run_pipeline(m, utf8, offsets, ndocs, max_ids, unk, issue, finish)) return -1;
-    return overflow ? -total : total;
+    g_last_error.clear();
+    return batch_csr<int32_t>((Model*)h, utf8, offsets, ndocs, ids_csr, capacity, id_offsets, max_ids, unk);
+  } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
+int64_t TextToIdsBatchCsrU16(void* h, const char* utf8, const int64_t* offsets, int64_t ndocs, uint16_t* ids_csr,
+                             int64_t capacity, int64_t* id_offsets, int max_ids, int unk) {
+  try {
+    g_last_error.clear();
+    return batch_csr<uint16_t>((Model*)h, utf8, offsets, ndocs, ids_csr, capacity, id_offsets, max_ids, unk);
   } catch (const std::exception& e) { set_error(e.what()); return -1; }
 }
 
 int64_t TextToIdsBatch(void* h, const char* utf8, const int64_t* offsets, int64_t ndocs, int32_t* ids, int32_t* counts,
                        int max_ids, int unk) {
   try {
+    g_last_error.clear();
     Model* m = (Model*)h;
     if (!check_batch_args(m, utf8, offsets, ndocs, max_ids)) return -1;
     if (ndocs > 0 && (!ids || !counts)) { set_error("bad output arguments"); return -1; }
-    std::lock_guard<std::mutex> lock(m->mu);
+    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
+    CtxLease lease(m);
+    HostBatch B{utf8, offsets, ndocs, max_ids, unk};
+    B.stage_in = ndocs > 16 && is_pageable(utf8);
     int64_t total = 0;
     auto issue = [&](Slot& s) -> bool {
       const int64_t n = s.h_row_off.p[s.ndocs];
@@ -583,23 +963,30 @@ int64_t TextToIdsBatch(void* h, const char* utf8, const int64_t* offsets, int64_
     };
     auto finish = [&](Slot& s) -> bool {
       // rows beyond their count stay untouched, as in the reference (blingfiretokdll.cpp:1098-1101)
-      for (int64_t i = 0; i < s.ndocs; ++i) {
-        const int64_t a = s.h_row_off.p[i], b = s.h_row_off.p[i + 1];
-        counts[s.doc0 + i] = (int32_t)(b - a);
-        if (b > a) std::memcpy(ids + (s.doc0 + i) * (int64_t)max_ids, s.h_csr.p + a, (size_t)(b - a) * sizeof(int32_t));
-      }
+      auto rows = [&](int64_t a0, int64_t a1) {
+        for (int64_t i = a0; i < a1; ++i) {
+          const int64_t a = s.h_row_off.p[i], b = s.h_row_off.p[i + 1];
+          counts[s.doc0 + i] = (int32_t)(b - a);
+          if (b > a) std::memcpy(ids + (s.doc0 + i) * (int64_t)max_ids, s.h_csr.p + a, (size_t)(b - a) * sizeof(int32_t));
+        }
+      };
+      constexpr int64_t kPart = 4096;
+      if (s.ndocs <= 2 * kPart) rows(0, s.ndocs);
+      else copy_pool_of(m)->parallel_for((size_t)((s.ndocs + kPart - 1) / kPart),
+                                         [&](size_t k) { rows((int64_t)k * kPart, std::min<int64_t>(s.ndocs, ((int64_t)k + 1) * kPart)); });
       return true;
     };
-    if (!run_pipeline(m, utf8, offsets, ndocs, max_ids, unk, issue, finish)) return -1;
+    if (!run_pipeline(m, lease.c, B, issue, finish)) return -1;
     return total;
   } catch (const std::exception& e) { set_error(e.what()); return -1; }
 }
 
 int TextToIds(void* h, const char* s, int n, int32_t* ids, const int max_ids, const int unk) {
   // blingfiretokdll.cpp:1619-1646 -> :1121: parameter validation happens before any work
+  g_last_error.clear();
   if (!h || n <= 0 || n > 1000000000 || !s) return 0;
   Model* m = (Model*)h;
-  if (m->engine == 0) { set_error("no GPU engine for this model type yet"); return 0; }
+  if (m->engine == 0) { set_error("no GPU engine for this model type"); return 0; }
   if (max_ids <= 0 || !ids) return 0;
   const int64_t offsets[2] = {0, n};
   int32_t count = 0;
@@ -612,32 +999,35 @@ int TextToIds(void* h, const char* s, int n, int32_t* ids, const int max_ids, co
 // the fused kernel does not carry offsets.  [pos-dict] models: not served yet (returns 0).
 int TextToIdsWithOffsets(void* h, const char* s, int n, int32_t* ids, int* starts, int* ends, const int max_ids, const int unk) {
   try {
+    g_last_error.clear();
     if (!h || n <= 0 || n > 1000000000 || !s) return 0;              // :1121
     if (!starts || !ends) return TextToIds(h, s, n, ids, max_ids, unk);
     Model* m = (Model*)h;
-    g_last_error.clear();
-    if (m->engine == 0) { set_error("no GPU engine for this model type yet"); return 0; }
+    if (m->engine == 0) { set_error("no GPU engine for this model type"); return 0; }
     if (m->engine != 3 && (!m->has_wbd || !m->lex_ok || !m->d_cls)) { set_error("model has no lexer engine with a 1->1 charmap"); return 0; }
     if (max_ids <= 0 || !ids) return 0;
-    std::lock_guard<std::mutex> lock(m->mu);
     if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return 0;
-    Slot& sl = m->slots[0];
+    CtxLease lease(m);
+    Slot& sl = lease.c->slots[0];
+    PinBuf<int32_t>& h_words = lease.c->h_words;
     if (!ensure_stream(sl)) return 0;
     const size_t nb = (size_t)n;
     if (m->engine == 3) {
       // TextToIdsWithOffsets_sp (:1349-1535): the segmentation kernel with the byte offsets of every
       // symbol carried through normalisation and whitespace collapsing
       if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve(2) || !sl.ids.reserve(3 * (size_t)max_ids) || !sl.counts.reserve(2) ||
-          !m->h_words.reserve(3 * (size_t)max_ids + 16))
+          !h_words.reserve(3 * (size_t)max_ids + 16))
         return 0;
       const int64_t offs[2] = {0, n};
       if (!cuda_ok(cudaMemcpyAsync(sl.text.p, s, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return 0;
       if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return 0;
       int32_t* d_ids = sl.ids.p;
       int nl = 0;
-      if (!launch_segmentation(m, sl, 0, n, 1, n, d_ids, d_ids + max_ids, d_ids + 2 * (size_t)max_ids, max_ids, unk, &nl)) return 0;
+      if (!launch_segmentation(m, sl, sl.text.p, sl.offsets.p, n, 1, n, d_ids, sl.counts.p, d_ids + max_ids, d_ids + 2 * (size_t)max_ids,
+                               max_ids, unk, sl.stream, &nl))
+        return 0;
       g_launches += nl;
-      int32_t* hw = m->h_words.p;
+      int32_t* hw = h_words.p;
       if (!cuda_ok(cudaMemcpyAsync(hw, sl.counts.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return 0;
       if (!cuda_ok(cudaMemcpyAsync(hw + 2, sl.counter.p + 1, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H flag")) return 0;
       if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return 0;
@@ -655,12 +1045,12 @@ int TextToIdsWithOffsets(void* h, const char* s, int n, int32_t* ids, int* start
     }
     if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve(2) || !sl.lex_cls.reserve(nb + 8) || !sl.lex_ncps.reserve(1) ||
         !sl.lex_tri_count.reserve(1) || !sl.lex_tri.reserve(6 * nb + 8) || !sl.lex_boff.reserve(nb + 8) ||
-        !sl.ids.reserve(3 * (size_t)max_ids) || !sl.counts.reserve(2) || !m->h_words.reserve(3 * (size_t)max_ids + 16))
+        !sl.ids.reserve(3 * (size_t)max_ids) || !sl.counts.reserve(2) || !h_words.reserve(3 * (size_t)max_ids + 16))
       return 0;
     const int64_t offs[2] = {0, n};
     if (!cuda_ok(cudaMemcpyAsync(sl.text.p, s, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return 0;
     if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return 0;
-    LexLaunch X = make_lex_launch(m, sl, 0, 0, n, 1, m->d_cls, 2);
+    LexLaunch X = make_lex_launch(sl, sl.text.p, sl.offsets.p, 0, n, 1, m->d_cls, 2);
     X.boff_buf = sl.lex_boff.p;
     int nl = 0;
     if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return 0;
@@ -669,7 +1059,7 @@ int TextToIdsWithOffsets(void* h, const char* s, int n, int32_t* ids, int* start
                  "post-pass launch"))
       return 0;
     g_launches += nl;
-    int32_t* hw = m->h_words.p;
+    int32_t* hw = h_words.p;
     if (!cuda_ok(cudaMemcpyAsync(hw, sl.counts.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return 0;
     if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return 0;
     const int count = hw[0];
@@ -738,25 +1128,25 @@ namespace {
 
 // What the host needs to put a lexer's output back into text: the (Tag, From, To) triples and the byte
 // offset of every code point.  The lexer itself (decode, classes, Process_int with every nested call)
-// runs on the GPU.  Caller holds m->mu.  Returns false on any failure (invalid UTF-8 included).
+// runs on the GPU, on the caller's leased context.  Returns false on any failure (invalid UTF-8 included).
 struct LexedText { int ncps = 0, rn = 0; const int32_t* tri = nullptr; std::vector<int> cp_off; };
 
-bool lex_on_gpu(Model* m, const char* s, int n, LexedText* R) {
+bool lex_on_gpu(Model* m, Ctx* ctx, const char* s, int n, LexedText* R) {
   if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return false;
-  Slot& sl = m->slots[0];
+  Slot& sl = ctx->slots[0];
   if (!ensure_stream(sl)) return false;
   const size_t nb = (size_t)n;
   if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve(2) || !sl.lex_cls.reserve(nb + 8) || !sl.lex_ncps.reserve(1) ||
-      !sl.lex_tri_count.reserve(1) || !sl.lex_tri.reserve(3 * nb + 8) || !m->h_words.reserve(3 * nb + 16))
+      !sl.lex_tri_count.reserve(1) || !sl.lex_tri.reserve(3 * nb + 8) || !ctx->h_words.reserve(3 * nb + 16))
     return false;
   const int64_t offs[2] = {0, n};
   if (!cuda_ok(cudaMemcpyAsync(sl.text.p, s, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return false;
   if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return false;
-  LexLaunch X = make_lex_launch(m, sl, 0, 0, n, 1, m->d_cls_words, 1);   // MaxOut = 3 * MaxBuffSize (:492-499, :249-251)
+  LexLaunch X = make_lex_launch(sl, sl.text.p, sl.offsets.p, 0, n, 1, m->d_cls_words, 1);   // MaxOut = 3 * MaxBuffSize (:492-499, :249-251)
   int nl = 0;
   if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return false;
   g_launches += nl;
-  int32_t* hw = m->h_words.p;
+  int32_t* hw = ctx->h_words.p;
   if (!cuda_ok(cudaMemcpyAsync(hw, sl.lex_ncps.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return false;
   if (!cuda_ok(cudaMemcpyAsync(hw + 1, sl.lex_tri_count.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return false;
   if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return false;
@@ -810,6 +1200,7 @@ int finish_text(const std::string& os, char* out, int max_out) {
 // UTF-8 string, like the reference's ostringstream loop (:507-552), and fills the offset arrays.
 int TextToWordsWithOffsetsWithModel(const char* s, int n, char* out, int* starts, int* ends, const int max_out, void* hModel) {
   try {
+    g_last_error.clear();
     Model* m = hModel ? (Model*)hModel : default_model(0);
     if (!m) return -1;
     if (n == 0) return 0;                                           // :446-448
@@ -817,9 +1208,9 @@ int TextToWordsWithOffsetsWithModel(const char* s, int n, char* out, int* starts
     if (!m->has_wbd || !m->lex_ok) { set_error("model has no lexer engine"); return -1; }
     if (starts && max_out > 0) std::memset(starts, 0, (size_t)max_out * sizeof(int));   // :467-472
     if (ends && max_out > 0) std::memset(ends, 0, (size_t)max_out * sizeof(int));
-    std::lock_guard<std::mutex> lock(m->mu);
+    CtxLease lease(m);
     LexedText R;
-    if (!lex_on_gpu(m, s, n, &R)) return -1;
+    if (!lex_on_gpu(m, lease.c, s, n, &R)) return -1;
     std::string os;
     os.reserve((size_t)n + (size_t)R.rn / 3 + 2);
     bool added = false;
@@ -859,6 +1250,7 @@ int TextToWords(const char* s, int n, char* out, const int max_out) { return Tex
 // inside becomes ' ', sentences are joined by '\n'; what follows the last boundary is the last sentence.
 int TextToSentencesWithOffsetsWithModel(const char* s, int n, char* out, int* starts, int* ends, const int max_out, void* hModel) {
   try {
+    g_last_error.clear();
     Model* m = hModel ? (Model*)hModel : default_model(1);
     if (!m) return -1;
     if (n == 0) return 0;                                           // :206-208
@@ -866,9 +1258,9 @@ int TextToSentencesWithOffsetsWithModel(const char* s, int n, char* out, int* st
     if (!m->has_wbd || !m->lex_ok) { set_error("model has no lexer engine"); return -1; }
     if (starts && max_out > 0) std::memset(starts, 0, (size_t)max_out * sizeof(int));   // :227-232
     if (ends && max_out > 0) std::memset(ends, 0, (size_t)max_out * sizeof(int));
-    std::lock_guard<std::mutex> lock(m->mu);
+    CtxLease lease(m);
     LexedText R;
-    if (!lex_on_gpu(m, s, n, &R)) return -1;
+    if (!lex_on_gpu(m, lease.c, s, n, &R)) return -1;
     std::string os;
     os.reserve((size_t)n + 2);
     bool added = false;

@@ -34,7 +34,7 @@ enum : int {
   kParamEop = 45, kParamUseNfst = 46, kParamCharmap = 47, kParamXWord = 51, kParamSeg = 52,
   kParamIgnore = 53, kParamActData = 68, kParamMaxLength = 69, kParamVerifyLdbBin = 70,
   kParamTokenizationType = 71, kParamIdOffset = 72, kParamUseByteEncoding = 73,
-  kParamNoDummyPrefix = 74,
+  kParamNoDummyPrefix = 74, kParamStringArray = 75, kParamTokenIdMin = 76, kParamTokenIdMax = 77,
   kTypeMooreDfa = 3, kTypeMealyDfa = 7,
   kModePackTriv = 1, kModePackMph = 2, kModePackFixed = 3,
   kTokenizeBpe = 3, kTokenizeBpeOpt = 4, kTokenizeBpeOptWithMerges = 5,

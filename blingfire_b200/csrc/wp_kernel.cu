@@ -357,17 +357,18 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
 }
 
 #ifndef BF_SIMT_HOST
+template <typename OutT>
 __global__ void wp_compact_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ counts,
                                   const int64_t* __restrict__ row_off, int64_t ndocs, int max_ids,
-                                  int32_t* __restrict__ csr) {
+                                  OutT* __restrict__ csr) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t d = warp; d < ndocs; d += nwarps) {
     const int c = counts[d];
     const int32_t* src = ids + d * (int64_t)max_ids;
-    int32_t* dst = csr + row_off[d];
-    for (int k = lane; k < c; k += 32) dst[k] = src[k];
+    OutT* dst = csr + row_off[d];
+    for (int k = lane; k < c; k += 32) dst[k] = (OutT)src[k];
   }
 }
 
@@ -448,8 +449,9 @@ cudaError_t wp_tokenize_launch(const WpLaunch& p, cudaStream_t stream, WpLaunchI
   return cudaGetLastError();
 }
 
-cudaError_t wp_compact_launch(const int32_t* ids, const int32_t* counts, const int64_t* row_off, int64_t ndocs,
-                              int max_ids, int32_t* csr, cudaStream_t stream) {
+template <typename OutT>
+static cudaError_t compact_launch(const int32_t* ids, const int32_t* counts, const int64_t* row_off, int64_t ndocs,
+                                  int max_ids, OutT* csr, cudaStream_t stream) {
   if (ndocs <= 0) return cudaSuccess;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -457,8 +459,16 @@ cudaError_t wp_compact_launch(const int32_t* ids, const int32_t* counts, const i
   const int block = 256;
   int64_t grid = (ndocs * 32 + block - 1) / block;
   if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
-  wp_compact_kernel<<<(int)grid, block, 0, stream>>>(ids, counts, row_off, ndocs, max_ids, csr);
+  wp_compact_kernel<OutT><<<(int)grid, block, 0, stream>>>(ids, counts, row_off, ndocs, max_ids, csr);
   return cudaGetLastError();
+}
+cudaError_t wp_compact_launch(const int32_t* ids, const int32_t* counts, const int64_t* row_off, int64_t ndocs,
+                              int max_ids, int32_t* csr, cudaStream_t stream) {
+  return compact_launch<int32_t>(ids, counts, row_off, ndocs, max_ids, csr, stream);
+}
+cudaError_t wp_compact_launch_u16(const int32_t* ids, const int32_t* counts, const int64_t* row_off, int64_t ndocs,
+                                  int max_ids, uint16_t* csr, cudaStream_t stream) {
+  return compact_launch<uint16_t>(ids, counts, row_off, ndocs, max_ids, csr, stream);
 }
 
 cudaError_t wp_scan_counts(const int32_t* counts, int64_t* row_off, int64_t ndocs, cudaStream_t stream) {

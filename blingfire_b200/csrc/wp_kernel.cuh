@@ -44,6 +44,10 @@ cudaError_t wp_tokenize_launch(const WpLaunch& p, cudaStream_t stream, WpLaunchI
 cudaError_t wp_compact_launch(const int32_t* ids, const int32_t* counts, const int64_t* row_off,
                               int64_t ndocs, int max_ids, int32_t* csr, cudaStream_t stream);
 
+// Same, 16-bit ids (the caller guarantees every id fits): halves the device->host bytes of a host batch call.
+cudaError_t wp_compact_launch_u16(const int32_t* ids, const int32_t* counts, const int64_t* row_off,
+                                  int64_t ndocs, int max_ids, uint16_t* csr, cudaStream_t stream);
+
 // Exclusive prefix sum of counts[0..ndocs) into int64 row offsets row_off[0..ndocs].
 cudaError_t wp_scan_counts(const int32_t* counts, int64_t* row_off, int64_t ndocs, cudaStream_t stream);
 

@@ -25,6 +25,7 @@
 #ifndef BLINGFIRETOKDLL_B200_H
 #define BLINGFIRETOKDLL_B200_H
 
+#include <stdbool.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -52,8 +53,7 @@ int FreeModel(void* ModelPtr);
 /* blingfiretokdll.h:93-100, blingfiretokdll.cpp:1619-1646.  Writes at most MaxIdsArrLength
  * ids, leaves the rest of pIdsArr untouched, returns the number written.  Returns 0 for a
  * NULL model/text, InUtf8StrByteCount <= 0 or > 1e9, invalid UTF-8 anywhere in the input,
- * or normalisation overflow -- exactly like the reference.  (UnkId may be any int except INT32_MIN,
- * which the WordPiece kernel uses as its "no piece starts here" marker.) */
+ * or normalisation overflow -- exactly like the reference.  UnkId may be any int. */
 int TextToIds(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
                     int32_t* pIdsArr, const int MaxIdsArrLength, const int UnkId);
 
@@ -78,6 +78,21 @@ int TextToIdsWithOffsets_wp(void* ModelPtr, const char* pInUtf8Str, int InUtf8St
 int TextToIdsWithOffsets_sp(void* ModelPtr, const char* pInUtf8Str, int InUtf8StrByteCount,
                             int32_t* pIdsArr, int* pStartOffsets, int* pEndOffsets,
                             const int MaxIdsArrLength, const int UnkId);
+
+/* blingfiretokdll.cpp:1669-1679 (exported through blingfiretokdll.def; dist-pypi/blingfire/__init__.py:287-288).
+ * Turns the dummy U+2581 prefix of a [pos-dict] model off (true) or on (false) for all later calls on the
+ * handle.  Like the reference's, the switch is a plain store: do not flip it while other threads tokenize.
+ * Returns 0 for a NULL handle, else 1. */
+int SetNoDummyPrefix(void* ModelPtr, bool fNoDummyPrefix);
+
+/* blingfiretokdll.cpp:1689-1745 (dist-pypi/blingfire/__init__.py:256-270).  Concatenates the texts of the ids
+ * (model with an [i2w] section, or a separate *.i2w file loaded with LoadModel); with SkipSpecialTokens ids
+ * outside the model's regular range are dropped; a space leading the output is dropped.  Returns the length
+ * including the trailing NUL (the minimum buffer size that holds the whole output); 0 for a NULL handle, no
+ * ids, a model without [i2w] or an id outside the array.  If the return value exceeds
+ * MaxOutUtf8StrByteCount the buffer content is undefined, as in the reference.  A table read on the host. */
+int IdsToText(void* ModelPtr, const int32_t* pIdsArr, const int IdsCount, char* pOutUtf8Str,
+              const int MaxOutUtf8StrByteCount, bool SkipSpecialTokens);
 
 /* blingfiretokdll.h:41, blingfiretokdll.cpp:610-614.  Default word breaker.  Returns -1 on
  * error, 0 for empty input, else the required output size including the trailing NUL (the
@@ -124,20 +139,45 @@ int64_t TextToIdsBatch(void* ModelPtr, const char* pUtf8, const int64_t* pOffset
                        int32_t* pIds, int32_t* pCounts, int MaxIdsPerDoc, int UnkId);
 
 /* Same contract, compact output: ids of document i are pIdsCsr[pIdOffsets[i] .. pIdOffsets[i+1]),
- * pIdOffsets has DocCount+1 entries.  pIdsCsr must hold CsrCapacity ids; if the batch
- * produces more, nothing is copied and the required capacity is returned negated.
- * HOST pointers.  This is the call bench.py times end to end. */
+ * pIdOffsets has DocCount+1 entries (always complete on a non-error return).  pIdsCsr must hold CsrCapacity
+ * ids (a document of n bytes yields at most n ids for lexer models, n+1 for [pos-dict] models, 2n+4 for
+ * [pos-dict] models with a charmap; never more than MaxIdsPerDoc).  If the batch produces more, the required
+ * capacity is returned negated and the content of pIdsCsr is undefined (the chunks that still fitted have
+ * been copied).  HOST pointers, pinned or pageable: pageable buffers are staged through library-owned
+ * pinned memory by a few copy threads on the GPU's NUMA node.  This is the call bench.py times end to end. */
 int64_t TextToIdsBatchCsr(void* ModelPtr, const char* pUtf8, const int64_t* pOffsets, int64_t DocCount,
                           int32_t* pIdsCsr, int64_t CsrCapacity, int64_t* pIdOffsets,
                           int MaxIdsPerDoc, int UnkId);
 
+/* Same with 16-bit ids, for models whose ids all fit (every shipped WordPiece/BPE model below 65 536 entries)
+ * and 0 <= UnkId <= 65535: halves the device->host bytes.  -1 if the model or UnkId does not qualify. */
+int64_t TextToIdsBatchCsrU16(void* ModelPtr, const char* pUtf8, const int64_t* pOffsets, int64_t DocCount,
+                             uint16_t* pIdsCsr, int64_t CsrCapacity, int64_t* pIdOffsets,
+                             int MaxIdsPerDoc, int UnkId);
+
 /* DEVICE pointers on the model's device, no copies, asynchronous on `cudaStream` (a
  * cudaStream_t, NULL = legacy default stream).  dUtf8 must be 4-byte aligned with at least
- * 8 readable bytes of slack after TotalBytes (any cudaMalloc'ed buffer qualifies).
- * dIds is [DocCount][MaxIdsPerDoc] row-major.  Returns 0 on success, -1 on error. */
+ * 8 readable bytes of slack after TotalBytes (any cudaMalloc'ed buffer qualifies); for the generic-lexer
+ * engine dOffsets[0] must be 0.  dIds is [DocCount][MaxIdsPerDoc] row-major.  Calls on different streams may
+ * overlap (each call has its own work counter; [pos-dict] scratch is kept per stream).  For [pos-dict]
+ * models this form reads the longest document back from the device first (one stream synchronisation);
+ * TextToIdsBatchDeviceSized takes it from the caller (MaxDocBytes >= every document's byte length) and
+ * stays asynchronous.  Returns 0 on success, -1 on error. */
 int TextToIdsBatchDevice(void* ModelPtr, const char* dUtf8, const int64_t* dOffsets, int64_t DocCount,
                          int64_t TotalBytes, int32_t* dIds, int32_t* dCounts,
                          int MaxIdsPerDoc, int UnkId, void* cudaStream);
+int TextToIdsBatchDeviceSized(void* ModelPtr, const char* dUtf8, const int64_t* dOffsets, int64_t DocCount,
+                              int64_t TotalBytes, int64_t MaxDocBytes, int32_t* dIds, int32_t* dCounts,
+                              int MaxIdsPerDoc, int UnkId, void* cudaStream);
+
+/* After device-pointer calls on `cudaStream`: synchronises the stream and returns 0, or the error code a
+ * [pos-dict] kernel raised because its scratch could not hold a document (it never guesses); -1 on a CUDA error. */
+int BlingFireB200DeviceStatus(void* ModelPtr, void* cudaStream);
+
+/* Row-major device ids -> CSR on the device: dRowOff[DocCount+1] = exclusive prefix sum of dCounts,
+ * dCsr[dRowOff[i] + k] = dIds[i*MaxIdsPerDoc + k] for k < dCounts[i].  Asynchronous.  0 / -1. */
+int64_t BlingFireB200CompactDevice(const int32_t* dIds, const int32_t* dCounts, int64_t DocCount, int MaxIdsPerDoc,
+                                   int32_t* dCsr, int64_t* dRowOff, void* cudaStream);
 
 /* Last error of the calling thread ("" if none).  Never NULL. */
 const char* BlingFireB200LastError(void);

@@ -25,7 +25,7 @@ enum {
     IW_ANY = 0, IW_L_ANCHOR = 1, IW_R_ANCHOR = 2, IW_EPSILON = 3,
     DFA_DEAD_STATE = -2,
     TRS_NONE = 0, TRS_RANGE = 1, TRS_IMPL = 2, TRS_PARA = 4, TRS_IWIA = 6,
-    FUNC_POS_DICT = 12, FUNC_WBD = 19, FUNC_GLOBAL = 20,
+    FUNC_POS_DICT = 12, FUNC_WBD = 19, FUNC_GLOBAL = 20, FUNC_I2W = 35,
     PARAM_FSM = 2, PARAM_REVERSE = 10, PARAM_DIRECTION = 11, PARAM_MAP_MODE = 16,
     PARAM_NO_TR = 18, PARAM_IGNORE_CASE = 22, PARAM_ARRAY = 24, PARAM_MULTI_MAP = 25,
     PARAM_FSM_TYPE = 26, PARAM_DICT_MODE = 31, PARAM_NORMALIZE = 35, PARAM_DO_W2B = 37,
@@ -34,7 +34,7 @@ enum {
     PARAM_CHARMAP = 47, PARAM_XWORD = 51, PARAM_SEG = 52, PARAM_IGNORE = 53,
     PARAM_ACT_DATA = 68, PARAM_MAX_LENGTH = 69, PARAM_VERIFY_LDB_BIN = 70,
     PARAM_TOKENIZATION_TYPE = 71, PARAM_ID_OFFSET = 72, PARAM_USE_BYTE_ENCODING = 73,
-    PARAM_NO_DUMMY_PREFIX = 74,
+    PARAM_NO_DUMMY_PREFIX = 74, PARAM_STRING_ARRAY = 75, PARAM_TOKENID_MIN = 76, PARAM_TOKENID_MAX = 77,
     TYPE_MOORE_DFA = 3, TYPE_MEALY_DFA = 7,
     MODE_PACK_TRIV = 1, MODE_PACK_MPH = 2, MODE_PACK_FIXED = 3,
     TOKENIZE_BPE = 3, TOKENIZE_BPE_OPT = 4, TOKENIZE_BPE_OPT_WITH_MERGES = 5,
@@ -79,6 +79,8 @@ struct bfo_model {
     int has_seg; dfa_t seg_dfa; mmap_fixed_t i2info_fixed; mmap_t i2info_triv; int i2info_mode;
     mmap_fixed_t seg_charmap; int has_seg_charmap;
     int tok_algo, id_offset, use_raw_bytes, no_dummy_prefix;
+    /* [i2w] (blingfiretokdll.cpp:997-1045): FAStringArray_pack image, regular id range */
+    int has_i2w; int i2w_count; const u8* i2w_offsets; const u8* i2w_data; int min_token_id, max_token_id;
 };
 
 static int rd_i32(const u8* p) { int v; memcpy(&v, p, 4); return v; }
@@ -503,7 +505,45 @@ bfo_model* bfo_load_model(const char* path) {
     if (n != -1) { if (!init_wbd(m, vals, n)) { bfo_free_model(m); return NULL; } m->has_wbd = 1; }
     vals = NULL; n = mmap_get(&m->conf, FUNC_POS_DICT, &vals);
     if (n != -1) { if (!init_seg(m, vals, n)) { bfo_free_model(m); return NULL; } m->has_seg = 1; }
+    /* blingfiretokdll.cpp:997-1045 */
+    m->min_token_id = 0; m->max_token_id = 1000000000;   /* FALimits::MaxArrSize */
+    vals = NULL; n = mmap_get(&m->conf, FUNC_I2W, &vals);
+    if (n != -1) {
+        for (int i = 0; i < n; ++i) {
+            if (vals[i] == PARAM_STRING_ARRAY && i + 1 < n) {
+                const u8* d = m->dumps[vals[++i]];
+                m->i2w_count = rd_i32(d);                    /* FAStringArray_pack.cpp:22-52 */
+                m->i2w_offsets = d + 4; m->i2w_data = d + 4 + 4L * (m->i2w_count + 1);
+                m->has_i2w = 1;
+            } else if (vals[i] == PARAM_TOKENID_MIN && i + 1 < n) m->min_token_id = vals[++i];
+            else if (vals[i] == PARAM_TOKENID_MAX && i + 1 < n) m->max_token_id = vals[++i];
+        }
+    }
     return m;
+}
+
+/* blingfiretokdll.cpp:1669-1679 */
+int bfo_set_no_dummy_prefix(bfo_model* m, int flag) { if (!m) return 0; m->no_dummy_prefix = flag ? 1 : 0; return 1; }
+
+/* blingfiretokdll.cpp:1689-1745 over FAStringArray_pack::GetAt (FAStringArray_pack.cpp:55-71) */
+int bfo_ids_to_text(const bfo_model* m, const int32_t* ids, int count, char* out, int max_out, int skip_special) {
+    if (!m) return 0;
+    if (count == 0 || !ids) return 0;
+    if (!m->has_i2w) return 0;
+    int len = 0;
+    for (int i = 0; i < count; ++i) {
+        const int id = ids[i];
+        if (skip_special && (id < m->min_token_id || id > m->max_token_id)) continue;
+        if (id < 0 || id >= m->i2w_count) return 0;
+        const unsigned b = rd_u32(m->i2w_offsets + 4L * id), e = rd_u32(m->i2w_offsets + 4L * (id + 1));
+        const u8* tok = m->i2w_data + b;
+        int tl = (int)(e - b);
+        if (len == 0 && tl > 0 && tok[0] == 0x20) { ++tok; --tl; }
+        if (tl > 0 && max_out - len >= tl) memcpy(out + len, tok, (size_t)tl);
+        len += tl;
+    }
+    if (max_out > len) out[len] = 0;
+    return len + 1;
 }
 
 /* ---- UTF-8: FAUtf8Utils.cpp ---- */
@@ -1076,4 +1116,78 @@ int64_t bfo_text_to_ids_batch(const bfo_model* m, const char* utf8, const int64_
     }
     for (int t = 0; t < threads; ++t) { pthread_join(th[t], NULL); total += jobs[t].total; }
     return total;
+}
+
+/* ---- per-document digests for full-size parity (bench.py, tests/): FNV-1a-64 over the uint32 id
+ * stream of a document (SURVEY 8c recipe), computed without materialising an [ndocs][max_ids] matrix ---- */
+static uint64_t fnv_ids(const int32_t* ids, int n) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (int i = 0; i < n; ++i) { h ^= (uint32_t)ids[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+typedef struct { const bfo_model* m; const char* utf8; const int64_t* offs; int64_t ndocs; uint64_t* dig; int32_t* counts;
+                 int max_ids, unk, tid, nthreads; int64_t total; } dig_job_t;
+static void* dig_worker(void* arg) {
+    dig_job_t* j = (dig_job_t*)arg;
+    int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)(j->max_ids > 0 ? j->max_ids : 1));
+    int64_t tot = 0;
+    for (int64_t d = j->tid; d < j->ndocs; d += j->nthreads) {
+        int c = bfo_text_to_ids(j->m, j->utf8 + j->offs[d], (int)(j->offs[d + 1] - j->offs[d]), ids, j->max_ids, j->unk);
+        if (c > j->max_ids) c = j->max_ids;
+        j->counts[d] = c; j->dig[d] = fnv_ids(ids, c); tot += c;
+    }
+    j->total = tot; free(ids);
+    return NULL;
+}
+/* digests[d], counts[d] of the oracle's TextToIds on every document; returns the total id count */
+int64_t bfo_text_to_ids_digests(const bfo_model* m, const char* utf8, const int64_t* offsets, int64_t ndocs,
+                                uint64_t* digests, int32_t* counts, int max_ids, int unk_id, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 512) threads = 512;
+    dig_job_t* jobs = (dig_job_t*)calloc((size_t)threads, sizeof(dig_job_t));
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 0; t < threads; ++t) {
+        dig_job_t j = { m, utf8, offsets, ndocs, digests, counts, max_ids, unk_id, t, threads, 0 };
+        jobs[t] = j; pthread_create(&th[t], NULL, dig_worker, &jobs[t]);
+    }
+    int64_t tot = 0;
+    for (int t = 0; t < threads; ++t) { pthread_join(th[t], NULL); tot += jobs[t].total; }
+    free(jobs); free(th);
+    return tot;
+}
+/* the same digests of ids given in CSR form (what the product's batch call returned); elem_size 4 or 2 */
+typedef struct { const void* ids; int elem; const int64_t* off; int64_t ndocs; uint64_t* dig; int tid, nthreads; } csr_job_t;
+static void* csr_worker(void* arg) {
+    csr_job_t* j = (csr_job_t*)arg;
+    for (int64_t d = j->tid; d < j->ndocs; d += j->nthreads) {
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (int64_t k = j->off[d]; k < j->off[d + 1]; ++k) {
+            const uint32_t v = j->elem == 2 ? (uint32_t)((const uint16_t*)j->ids)[k] : (uint32_t)((const int32_t*)j->ids)[k];
+            h ^= v; h *= 0x100000001b3ull;
+        }
+        j->dig[d] = h;
+    }
+    return NULL;
+}
+void bfo_csr_digests(const void* ids, int elem_size, const int64_t* id_offsets, int64_t ndocs, uint64_t* digests, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 512) threads = 512;
+    csr_job_t* jobs = (csr_job_t*)calloc((size_t)threads, sizeof(csr_job_t));
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 0; t < threads; ++t) {
+        csr_job_t j = { ids, elem_size, id_offsets, ndocs, digests, t, threads };
+        jobs[t] = j; pthread_create(&th[t], NULL, csr_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    free(jobs); free(th);
+}
+/* one number for a whole batch: FNV-1a-64 over the per-document (count, digest) pairs in document order */
+uint64_t bfo_fold_digests(const uint64_t* digests, const int64_t* id_offsets, const int32_t* counts, int64_t ndocs) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (int64_t d = 0; d < ndocs; ++d) {
+        const uint64_t c = id_offsets ? (uint64_t)(id_offsets[d + 1] - id_offsets[d]) : (uint64_t)counts[d];
+        h ^= c; h *= 0x100000001b3ull;
+        h ^= digests[d]; h *= 0x100000001b3ull;
+    }
+    return h;
 }

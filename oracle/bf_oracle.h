@@ -35,6 +35,10 @@ void bfo_free_model(bfo_model* m);
 int bfo_text_to_ids(const bfo_model* m, const char* utf8, int nbytes,
                     int32_t* ids, int max_ids, int unk_id);
 
+/* blingfiretokdll.cpp:1669-1679 (SetNoDummyPrefix) and :1689-1745 (IdsToText) */
+int bfo_set_no_dummy_prefix(bfo_model* m, int flag);
+int bfo_ids_to_text(const bfo_model* m, const int32_t* ids, int count, char* out, int max_out, int skip_special);
+
 /* blingfiretokdll.cpp:1108-1314 / :1349-1535 with offsets (NULL to skip). */
 int bfo_text_to_ids_with_offsets(const bfo_model* m, const char* utf8, int nbytes,
                                  int32_t* ids, int* starts, int* ends,
@@ -67,6 +71,12 @@ int bfo_has_seg(const bfo_model* m);
 int64_t bfo_text_to_ids_batch(const bfo_model* m, const char* utf8, const int64_t* offsets,
                               int64_t ndocs, int32_t* ids, int32_t* counts,
                               int max_ids, int unk_id, int threads);
+
+/* Full-size parity without an [ndocs][max_ids] matrix: FNV-1a-64 (SURVEY 8c recipe) of every document's ids. */
+int64_t bfo_text_to_ids_digests(const bfo_model* m, const char* utf8, const int64_t* offsets, int64_t ndocs,
+                                uint64_t* digests, int32_t* counts, int max_ids, int unk_id, int threads);
+void bfo_csr_digests(const void* ids, int elem_size, const int64_t* id_offsets, int64_t ndocs, uint64_t* digests, int threads);
+uint64_t bfo_fold_digests(const uint64_t* digests, const int64_t* id_offsets, const int32_t* counts, int64_t ndocs);
 
 #ifdef __cplusplus
 }

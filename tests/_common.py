@@ -53,6 +53,15 @@ class Oracle:
         for fn in ("bfo_text_to_words_with_offsets", "bfo_text_to_sentences_with_offsets"):
             getattr(L, fn).argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int]
+        L.bfo_set_no_dummy_prefix.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.bfo_ids_to_text.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.bfo_text_to_ids_digests.restype = ctypes.c_int64
+        L.bfo_text_to_ids_digests.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.bfo_csr_digests.restype = None
+        L.bfo_csr_digests.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]
+        L.bfo_fold_digests.restype = ctypes.c_uint64
+        L.bfo_fold_digests.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         L.bfo_text_to_ids_batch.restype = ctypes.c_int64
         L.bfo_text_to_ids_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -72,6 +81,38 @@ class Oracle:
 
     def free(self, h):
         self.lib.bfo_free_model(h)
+
+    def set_no_dummy_prefix(self, h, flag):
+        return self.lib.bfo_set_no_dummy_prefix(h, int(bool(flag)))
+
+    def ids_to_text(self, h, ids, max_out, skip_special):
+        return ids_to_text_call(self.lib.bfo_ids_to_text, h, ids, max_out, skip_special)
+
+    def digests(self, h, buf, offsets, max_ids, unk, threads=None):
+        """Per-document (FNV-1a-64 digest, count) of the oracle's TextToIds over a CSR batch, threaded in C."""
+        n = len(offsets) - 1
+        dig = np.zeros(n, np.uint64)
+        counts = np.zeros(n, np.int32)
+        buf = np.ascontiguousarray(buf)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        tot = self.lib.bfo_text_to_ids_digests(h, buf.ctypes.data, offsets.ctypes.data, n, dig.ctypes.data, counts.ctypes.data,
+                                               max_ids, unk, threads or (os.cpu_count() or 1))
+        return int(tot), dig, counts
+
+    def csr_digests(self, ids, id_offsets, threads=None):
+        """The same per-document digests of ids already in CSR form (int32 or uint16)."""
+        ids = np.ascontiguousarray(ids)
+        id_offsets = np.ascontiguousarray(id_offsets, dtype=np.int64)
+        n = len(id_offsets) - 1
+        dig = np.zeros(n, np.uint64)
+        self.lib.bfo_csr_digests(ids.ctypes.data, ids.dtype.itemsize, id_offsets.ctypes.data, n, dig.ctypes.data,
+                                 threads or (os.cpu_count() or 1))
+        return dig
+
+    def fold(self, dig, id_offsets=None, counts=None):
+        n = len(dig)
+        return int(self.lib.bfo_fold_digests(dig.ctypes.data, id_offsets.ctypes.data if id_offsets is not None else None,
+                                             counts.ctypes.data if counts is not None else None, n))
 
     def text_to_ids(self, h, data: bytes, max_ids=512, unk=0):
         ids = np.full(max_ids, -7, np.int32)
@@ -133,6 +174,9 @@ class Ref:
             getattr(L, fn).argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_int, ctypes.c_void_p]
 
+        L.SetNoDummyPrefix.argtypes = [ctypes.c_void_p, ctypes.c_bool]
+        L.IdsToText.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_bool]
+
     def split(self, kind, data: bytes, model=None, max_out=None):
         return split_call(getattr(self.lib, "TextToWordsWithOffsetsWithModel" if kind == "words" else
                                   "TextToSentencesWithOffsetsWithModel"), data, model, max_out)
@@ -141,6 +185,12 @@ class Ref:
         h = self.lib.LoadModel(path.encode())
         assert h
         return h
+
+    def set_no_dummy_prefix(self, h, flag):
+        return self.lib.SetNoDummyPrefix(h, bool(flag))
+
+    def ids_to_text(self, h, ids, max_out, skip_special):
+        return ids_to_text_call(self.lib.IdsToText, h, ids, max_out, skip_special)
 
     def free(self, h):
         self.lib.FreeModel(h)
@@ -165,6 +215,14 @@ class Ref:
         else:
             n = self.lib.TextToWordsWithModel(data, len(data), out, max_out, ctypes.c_void_p(model))
         return n, out.raw[: max(n, 0)] if n <= max_out else b""
+
+
+def ids_to_text_call(fn, h, ids, max_out, skip_special):
+    """Calls an IdsToText-shaped function: (ret, bytes written incl. the NUL when it fitted, else b"")."""
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    out = ctypes.create_string_buffer(max(max_out, 1))
+    n = fn(ctypes.c_void_p(h), ids.ctypes.data if len(ids) else None, len(ids), out, max_out, bool(skip_special))
+    return n, (out.raw[:n] if 0 < n <= max_out else b"")
 
 
 def split_call(fn, data: bytes, model, max_out=None):

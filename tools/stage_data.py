@@ -22,6 +22,9 @@ MODELS = [
     "bert_base_tok.bin", "bert_base_cased_tok.bin", "bert_multi_cased.bin", "bert_chinese.bin",
     "wbd.bin", "wbd_chuni.bin", "sbd.bin", "gpt2.bin", "roberta.bin", "xlm_roberta_base.bin",
     "xlnet.bin", "xlnet_nonorm.bin", "bpe_example.bin", "laser100k.bin", "uri100k.bin",
+    # id -> text arrays for IdsToText (separate LDB files with only an [i2w] section)
+    "bert_base_tok.i2w", "bert_base_cased_tok.i2w", "bert_chinese.i2w", "gpt2.i2w", "roberta.i2w",
+    "xlm_roberta_base.i2w", "laser100k.i2w", "uri100k.i2w",
 ]
 CORPORA = [("ldbsrc/bert_base_tok/test.txt", "test.txt")]
 ZIPS = [("ldbsrc/bert_multi_cased/test.multi.txt.zip", "test.multi.txt")]
