@@ -169,10 +169,11 @@ def test_device_entry_point_matches_host(bf, oracle):
 
 
 def test_full_size_properties(bf, oracle):
-    """cfg 2 at full size (1 M docs x ~512 B): properties that do not need the oracle on every doc.
+    """cfg 2 at full size (1 M docs x ~512 B): size-independent properties (every document against the reference is
+    tests/test_gpu_fullsize.py).
       * replica / rotation invariance: rotating the document order rotates the result rows
       * concatenation: per-document counts sum to the CSR total
-      * a strided sample is checked id-for-id against the oracle."""
+      * a strided sample is checked id-for-id against the oracle port (the full-size test uses oracle/_ref)."""
     import corpus
     n = 1_000_000
     h = gpu_model(bf, "bert_base_tok.bin")
