@@ -164,6 +164,8 @@ struct Model {
   int32_t* d_tag = nullptr;
   uint16_t* d_cls = nullptr;
   uint8_t* d_blob = nullptr;
+  uint32_t* d_clsx = nullptr;
+  WpWordSlot* d_words = nullptr;
   // generic lexer engine (any [wbd] model)
   bool lex_ok = false;
   int32_t* d_ow = nullptr;
@@ -210,6 +212,8 @@ struct Model {
     if (d_tag) cudaFree(d_tag);
     if (d_cls) cudaFree(d_cls);
     if (d_blob) cudaFree(d_blob);
+    if (d_clsx) cudaFree(d_clsx);
+    if (d_words) cudaFree(d_words);
     if (d_ow) cudaFree(d_ow);
     if (d_act_begin) cudaFree(d_act_begin);
     if (d_act_data) cudaFree(d_act_data);
@@ -342,6 +346,11 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
       build_wp_blob(T, &m->blob);
       if (!upload(&m->d_tag, T.tag_of_state.data(), T.tag_of_state.size())) return nullptr;
       if (!upload(&m->d_blob, m->blob.bytes.data(), m->blob.bytes.size())) return nullptr;
+      if (!upload(&m->d_clsx, T.clsx_of_cp.data(), T.clsx_of_cp.size())) return nullptr;
+      if (!upload(&m->d_words, m->blob.word_slots.data(), m->blob.word_slots.size())) return nullptr;
+      m->blob.words.slots = m->d_words;
+      std::vector<WpWordSlot>().swap(m->blob.word_slots);
+      std::vector<uint32_t>().swap(T.clsx_of_cp);
       m->engine = 1;
     } else if (m->lex_ok && T.charmap_one_to_one) {
       m->engine = 2;
@@ -396,7 +405,8 @@ WpLaunch make_launch(const Model* m) {
   L.trans = m->d_trans;
   L.wide = m->T.wide_states;
   L.tag_of_state = m->d_tag;
-  L.cls_of_cp = m->d_cls;
+  L.clsx_of_cp = m->d_clsx;
+  L.words = m->blob.words;
   L.NC1 = (uint32_t)m->T.NC + 1;
   L.first_final = m->T.first_final;
   L.cls_caret = m->T.cls_caret;

@@ -162,6 +162,26 @@ bool build_lexer_tables(const LdbImage& ldb, LexerTables* T, std::string* err) {
   };
   if (T->wide_states) fill_rows(T->trans32.data(), (uint32_t)kNoState); else fill_rows(T->trans16.data(), (uint16_t)0xFFFF);
 
+  // ---- the stored arcs in the new numbering ----
+  {
+    std::vector<int32_t> old_of(T->NS, -1);
+    for (int s = 0; s < n; ++s) old_of[newid[s]] = s;
+    T->arc_begin.assign((size_t)T->NS + 1, 0);
+    T->arc_label.clear(); T->arc_dst.clear();
+    for (int ns = 0; ns < T->NS; ++ns) {
+      T->arc_begin[ns] = (int64_t)T->arc_label.size();
+      const int s = old_of[ns];
+      if (s < 0) continue;
+      for (int64_t k = A.arc_begin[s]; k < A.arc_begin[s + 1]; ++k) {
+        const Arc& a = A.arcs[k];
+        if (a.label < 0 || a.label >= NC) continue;
+        T->arc_label.push_back((uint32_t)a.label);
+        T->arc_dst.push_back(a.dst == kDeadState ? T->dead : newid[a.dst]);
+      }
+    }
+    T->arc_begin[T->NS] = (int64_t)T->arc_label.size();
+  }
+
   // ---- rule ids, actions ----
   T->ow_of_state.assign((size_t)T->NS, -1);
   T->orig_offset.assign((size_t)T->NS, -1);
@@ -376,6 +396,11 @@ bool build_lexer_tables(const LdbImage& ldb, LexerTables* T, std::string* err) {
     }
   }
   F.ok = true;
+  if (T->charmap_one_to_one) {
+    T->clsx_of_cp.resize(T->cls_of_cp.size());
+    for (size_t cp = 0; cp < T->cls_of_cp.size(); ++cp)
+      T->clsx_of_cp[cp] = (uint32_t)T->cls_of_cp[cp] | ((uint32_t)F.tc_of_class[T->cls_of_cp[cp]] << 16);
+  }
   return true;
 }
 

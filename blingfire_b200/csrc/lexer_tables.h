@@ -80,6 +80,8 @@ struct LexerTables {
   int NC = 0;                          // number of real classes; class NC = "unmapped"
   uint32_t cls_caret = 0, cls_dollar = 0;   // classes of IW_L_ANCHOR / IW_R_ANCHOR (NC if unmapped)
   std::vector<uint16_t> cls_of_cp;     // [0x110000] combined charmap+clamp+class (1->1 charmaps only)
+  std::vector<uint32_t> clsx_of_cp;    // [0x110000] cls_of_cp | top-level class << 16 (FastPath models only): one gather
+                                       //            per code point in the fused kernel
   std::vector<uint16_t> cls_of_iw;     // [max_iw+1] plain class map (general path)
   // TextToWords' view of a code point (blingfiretokdll.cpp:475-482): NO charmap, U+0000 -> U+0020,
   // then the lexer's clamp and the class map
@@ -100,6 +102,11 @@ struct LexerTables {
   DenseVec<uint32_t> trans32;          // [NS*(NC+1)] when wide_states, kNoState = none
   std::vector<int32_t> ow_of_state;    // [NS] rule id for finals, -1 otherwise
   std::vector<int32_t> orig_offset;    // [NS] the state's id in the packed image (byte offset), -1 for the sink
+  // the stored arcs in the new numbering (CSR over states): the load-time enumeration of the vocabulary
+  // (wp_model.cpp, whole-word table) walks these instead of scanning dense rows
+  std::vector<int64_t> arc_begin;      // [NS+1]
+  std::vector<uint32_t> arc_label;     // class
+  std::vector<uint32_t> arc_dst;
 
   // actions: rule id -> ints (FAMultiMap_pack rows), validated like FALexTools_t::Validate
   std::vector<int32_t> act_begin;      // [num_acts+1]

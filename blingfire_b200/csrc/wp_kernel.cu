@@ -29,9 +29,22 @@ constexpr int kWarpsPerCta = 16;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kWin = 576;            // window capacity in code points (per warp)
 constexpr int kBlockBytes = 128;     // bytes consumed per decode step (32 lanes x uchar4)
-constexpr int kWarpSmem = kWin * (2 + 4 + 1 + 2 + 2);   // cls u16, ids_at i32, top class u8, starts u16, order u16
+constexpr int kPad = 4;              // the window starts (lo & 3) entries into its arrays, so that a lane's 4 ASCII bytes land on
+                                     // a 4-entry boundary and go out as one vector store per array
+constexpr int kRing = 64;            // entries per work ring (a round consumes 32; at most 63 are ever queued)
+constexpr int kEvRing = 128;         // the event ring: a round needs 34 queued (every event looks at its two successors)
+// per-warp shared memory: ids_at i32 | cls u16 (+ slack for the key reads past a chunk) | top class u8 | event ring u16 |
+// fast ring u32 | slow ring u32
+constexpr int kOffCls = (kWin + kPad) * 4;
+constexpr int kOffMeta = kOffCls + (kWin + kPad + kMaxFastLen + 4) * 2;
+constexpr int kOffEvq = (kOffMeta + kWin + kPad + 15) & ~15;
+constexpr int kOffFastq = kOffEvq + kEvRing * 2;
+constexpr int kOffSlowq = kOffFastq + kRing * 4;
+constexpr int kWarpSmem = kOffSlowq + kRing * 4;
 
 static_assert(kWin % 32 == 0, "window must be a multiple of the warp size");
+static_assert(kOffCls % 16 == 0 && kOffMeta % 4 == 0 && kWarpSmem % 16 == 0, "vector stores need aligned arrays");
+static_assert(kWin + kPad < 0x8000, "event entries keep the position in 15 bits");
 
 __device__ __forceinline__ unsigned lanemask_lt() {
 #ifdef BF_SIMT_HOST                        // tests/simt: the kernel source on the CPU
@@ -117,9 +130,111 @@ __device__ __forceinline__ LaneDecode decode_lane(uint32_t w0, uint32_t w1, int6
   return r;
 }
 
-__device__ __forceinline__ void load_words(const uint32_t* text32, int64_t pos0, int64_t padded_bytes, uint32_t* w0, uint32_t* w1) {
-  *w0 = pos0 < padded_bytes ? __ldg(text32 + (pos0 >> 2)) : 0u;
-  *w1 = pos0 + 4 < padded_bytes ? __ldg(text32 + (pos0 >> 2) + 1) : 0u;
+// The per-warp working set: one window of the current document and the three work rings.
+struct WarpWin {
+  int32_t* ids_at;     // [kWin] id of the piece starting at a position, kNoPiece elsewhere
+  uint16_t* cls;       // [kWin] class of every position
+  uint8_t* meta;       // [kWin] top-level class of every position
+  uint16_t* evq;       // ring of events: position | 0x8000 when a chunk may start there (else: only the class changes)
+  uint32_t* fastq;     // ring of word runs for the whole-word table: start | length << 16
+  uint32_t* slowq;     // ring of chunks for the lexer loops: start | end << 16
+  int nev, evh, nfast, fh, nslow, sh;   // ring counts and heads (warp-uniform)
+  int carry;           // per lane: largest position known to be a finished chunk boundary
+};
+
+// Events -> chunks: every lane takes one event and its two successors.  A chunk start followed by another chunk
+// start is a run inside ONE group of top-level classes (a change of group would be an event of its own); a chunk
+// start, a change to the DEAD group, and the next chunk start is such a run followed by positions that match
+// nothing ("word" + white space in bert_*).  The per-group memo says whether the run emits nothing, is one word for
+// the table, or needs the loops -- as does every chunk of another shape.
+template <typename TE>
+__device__ __forceinline__ void classify_round(WarpWin& w, const WpTop& top, const WpWords& words, int cnt, int lane, int m,
+                                               bool at_end, int limit, bool first) {
+  int action = 0;      // 1 = table, 2 = loops
+  int s = 0, we = 0, e = 0;
+  if (lane < cnt) {
+    const unsigned e0 = w.evq[(w.evh + lane) & (kEvRing - 1)], e1 = w.evq[(w.evh + lane + 1) & (kEvRing - 1)];
+    s = (int)(e0 & 0x7FFFu);
+    if (e0 & 0x8000u) {
+      bool shaped = true;
+      we = e = (int)(e1 & 0x7FFFu);
+      if (!(e1 & 0x8000u)) {
+        const unsigned e2 = w.evq[(w.evh + lane + 2) & (kEvRing - 1)];
+        e = (int)(e2 & 0x7FFFu);
+        shaped = (e2 & 0x8000u) && (top.kind_of_tc[w.meta[we]] & kKindDead);
+        if (!shaped) {
+          // some other mix of groups: find where the chunk really ends
+          int p = we + 1;
+          while (p < m && !(top.sync_start[((unsigned)w.meta[p - 1] << top.sync_shift) | (unsigned)w.meta[p]] & kSyncStart)) ++p;
+          e = p;
+        }
+      }
+      if (!shaped || (!at_end && e > limit)) {
+        action = 2;                                  // (a chunk that is not final in this window: the loops clip it)
+      } else {
+        const int r = wp_classify_run(top.kind_of_tc[w.meta[s]], we - s, words.max_len, first && s == 0, at_end && we == m);
+        if (r == 0) action = 2;
+        else { action = r == 2 ? 1 : 0; w.carry = max(w.carry, e); }
+      }
+    }
+  }
+  const unsigned lt = lanemask_lt();
+  const unsigned bf = __ballot_sync(0xffffffffu, action == 1), bs = __ballot_sync(0xffffffffu, action == 2);
+  if (action == 1) w.fastq[(w.fh + w.nfast + __popc(bf & lt)) & (kRing - 1)] = (uint32_t)s | ((uint32_t)(we - s) << 16);
+  if (action == 2) w.slowq[(w.sh + w.nslow + __popc(bs & lt)) & (kRing - 1)] = (uint32_t)s | ((uint32_t)e << 16);
+  w.nfast += __popc(bf); w.nslow += __popc(bs);
+  w.evh = (w.evh + cnt) & (kEvRing - 1); w.nev -= cnt;
+  __syncwarp();
+}
+
+// One word per lane through the whole-word table; what the table does not hold goes to the loops.
+__device__ __forceinline__ void fast_round(WarpWin& w, const WpWords& words, int cnt, int lane) {
+  int s = 0, L = 0;
+  if (lane < cnt) {
+    const uint32_t ent = w.fastq[(w.fh + lane) & (kRing - 1)];
+    s = (int)(ent & 0xFFFFu); L = (int)(ent >> 16);
+  }
+  const int lcap = __reduce_max_sync(0xffffffffu, L);
+  uint32_t kw[4];
+  wp_pack_key_any(words.cpw, w.cls + s, L, lcap, words.cb, kw);
+  const int32_t id = wp_words_find(words, kw);
+  const bool hit = lane < cnt && id != kNoPiece;
+  if (hit) w.ids_at[s] = id;
+  const bool miss = lane < cnt && !hit;
+  const unsigned bm = __ballot_sync(0xffffffffu, miss);
+  if (miss) w.slowq[(w.sh + w.nslow + __popc(bm & lanemask_lt())) & (kRing - 1)] = (uint32_t)s | ((uint32_t)(s + L) << 16);
+  w.nslow += __popc(bm);
+  w.fh = (w.fh + cnt) & (kRing - 1); w.nfast -= cnt;
+  __syncwarp();
+}
+
+// One chunk per lane through the reference's loops (wp_core.cuh).
+template <typename TE>
+__device__ __forceinline__ void slow_round(WarpWin& w, const WpTop& top, const WpGlobal<TE>& g, int cnt, int lane, int m, bool at_end,
+                                           int limit, bool first, int unk_id) {
+  if (lane < cnt) {
+    const uint32_t ent = w.slowq[(w.sh + lane) & (kRing - 1)];
+    const int s = (int)(ent & 0xFFFFu);
+    int fe = (int)(ent >> 16);
+    if (fe > limit) fe = limit;
+    const int fb = (s == 0 && first) ? -1 : s;
+    if (fb < fe) w.carry = max(w.carry, wp_chunk<TE>(top, g, w.cls, m, at_end, fb, fe, unk_id, w.ids_at, w.meta));
+  }
+  w.sh = (w.sh + cnt) & (kRing - 1); w.nslow -= cnt;
+  __syncwarp();
+}
+
+template <typename TE>
+__device__ __forceinline__ void drain_rounds(WarpWin& w, const WpTop& top, const WpGlobal<TE>& g, const WpWords& words, int lane, int m,
+                                             bool at_end, int limit, bool first, int unk_id, bool all) {
+  // a ring holds at most 63 entries: the loops' ring is emptied before the table round can add 32 more
+  if (w.nslow >= 32) slow_round<TE>(w, top, g, 32, lane, m, at_end, limit, first, unk_id);
+  if (w.nfast >= 32) fast_round(w, words, 32, lane);
+  if (w.nslow >= 32) slow_round<TE>(w, top, g, 32, lane, m, at_end, limit, first, unk_id);
+  if (all) {
+    if (w.nfast > 0) fast_round(w, words, w.nfast, lane);
+    while (w.nslow > 0) slow_round<TE>(w, top, g, w.nslow < 32 ? w.nslow : 32, lane, m, at_end, limit, first, unk_id);
+  }
 }
 
 template <typename TE>
@@ -151,16 +266,15 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
   WpGlobal<TE> g;
   g.trans = reinterpret_cast<const TE*>(p.trans);
   g.tag_of_state = p.tag_of_state;
-  g.cls_of_cp = p.cls_of_cp;
   g.NC1 = p.NC1; g.first_final = p.first_final; g.cls_caret = p.cls_caret; g.cls_dollar = p.cls_dollar;
   g.max_token_length = p.max_token_length;
+  const WpWords words = p.words;
 
   uint8_t* wbase = smem + blob_bytes + (size_t)warp * kWarpSmem;
-  int32_t* ids_at = reinterpret_cast<int32_t*>(wbase);
-  uint16_t* cls = reinterpret_cast<uint16_t*>(wbase + kWin * 4);
-  uint16_t* starts = reinterpret_cast<uint16_t*>(wbase + kWin * 6);
-  uint8_t* meta = wbase + kWin * 8;          // top-level class of every position
-  uint16_t* order = reinterpret_cast<uint16_t*>(wbase + kWin * 9 + (kWin & 1));
+  WarpWin w;
+  w.evq = reinterpret_cast<uint16_t*>(wbase + kOffEvq);
+  w.fastq = reinterpret_cast<uint32_t*>(wbase + kOffFastq);
+  w.slowq = reinterpret_cast<uint32_t*>(wbase + kOffSlowq);
 
   const uint32_t* text32 = reinterpret_cast<const uint32_t*>(p.text);
   const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
@@ -196,8 +310,8 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
       for (int64_t bpos = lo0; bpos < hi;) {
         const int64_t bs = bpos & ~(int64_t)3;
         const int64_t pos0 = bs + lane * 4;
-        uint32_t w0, w1;
-        load_words(text32, pos0, padded_bytes, &w0, &w1);
+        const uint32_t w0 = pos0 < padded_bytes ? __ldg(text32 + (pos0 >> 2)) : 0u;
+        const uint32_t w1 = pos0 + 4 < padded_bytes ? __ldg(text32 + (pos0 >> 2) + 1) : 0u;
         const LaneDecode dcd = decode_lane(w0, w1, pos0, bpos, hi);
         bad |= dcd.bad; sumlen += dcd.sumlen;
         bpos = bs + kBlockBytes;
@@ -209,13 +323,20 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
     }
 
     if (run) {
+      // the window starts (lo0 & 3) entries into its arrays: a lane's 4 bytes of ASCII text then land on a
+      // 4-entry boundary, as long as everything before them was ASCII too
+      const int pad = (int)(lo0 & 3);
+      w.ids_at = reinterpret_cast<int32_t*>(wbase) + pad;
+      w.cls = reinterpret_cast<uint16_t*>(wbase + kOffCls) + pad;
+      w.meta = wbase + kOffMeta + pad;
       int m = 0, out = 0;
       int64_t bpos = lo0;
       bool first = true, ok = true;
-      unsigned sumlen = 0;
+      unsigned sumlen = 0;          // per lane: bytes covered by the sequences decoded here
+      int ulen = 0;                 // uniform: bytes of the all-ASCII blocks
       int32_t* row = p.ids + doc * (int64_t)p.max_ids;
       for (;;) {
-        // ---- fill the window: decode, validate, classify, compact ----
+        // ---- fill the window: decode, validate, classify ----
         unsigned bad = 0;
         while (bpos < hi) {
           const int64_t bs = bpos & ~(int64_t)3;
@@ -223,30 +344,52 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
           const int64_t blk_end = bs + kBlockBytes < hi ? bs + kBlockBytes : hi;
           if (m + (int)(blk_end - bpos) > kWin) break;
           const int64_t pos0 = bs + lane * 4;
-          uint32_t w0, w1;
-          load_words(text32, pos0, padded_bytes, &w0, &w1);
-          const LaneDecode dcd = decode_lane(w0, w1, pos0, bpos, hi);
-          bad |= dcd.bad; sumlen += dcd.sumlen;
-          const int cnt = __popc(dcd.start_mask);
-          int incl = cnt;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-          }
-          int idx = m + incl - cnt;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (dcd.start_mask & (1u << k)) {
-              const uint32_t cp = dcd.cp[k];
-              const uint16_t c = cp < 128 ? top.ascii_cls[cp] : __ldg(g.cls_of_cp + cp);
-              cls[idx] = c;
-              meta[idx] = top.tc_of_class[c];
-              ids_at[idx] = kNoPiece;
-              ++idx;
+          const uint32_t w0 = pos0 < padded_bytes ? __ldg(text32 + (pos0 >> 2)) : 0u;
+          const int vfirst = (int)(bpos - pos0), vlast = (int)(blk_end - pos0);   // this lane's bytes [vfirst, vlast) belong to the block
+          uint32_t vmask = vlast >= 4 ? 0xFFFFFFFFu : (vlast <= 0 ? 0u : (1u << (8 * vlast)) - 1u);
+          if (vfirst > 0) vmask &= ~((1u << (8 * vfirst)) - 1u);
+          if (!__any_sync(0xffffffffu, (w0 & 0x80808080u & vmask) != 0)) {
+            // all ASCII: position = byte offset, classes from the shared-memory table
+            const int idx = m + (int)(pos0 - bpos);
+            const uint32_t x0 = top.ascii_clsx[w0 & 0x7F], x1 = top.ascii_clsx[(w0 >> 8) & 0x7F];
+            const uint32_t x2 = top.ascii_clsx[(w0 >> 16) & 0x7F], x3 = top.ascii_clsx[(w0 >> 24) & 0x7F];
+            if (vmask == 0xFFFFFFFFu && ((pad + idx) & 3) == 0) {
+              *reinterpret_cast<uint2*>(w.cls + idx) = make_uint2(__byte_perm(x0, x1, 0x5410), __byte_perm(x2, x3, 0x5410));
+              *reinterpret_cast<uint32_t*>(w.meta + idx) = __byte_perm(__byte_perm(x0, x1, 0x0062), __byte_perm(x2, x3, 0x0062), 0x5410);
+              *reinterpret_cast<int4*>(w.ids_at + idx) = make_int4(kNoPiece, kNoPiece, kNoPiece, kNoPiece);
+            } else {
+              if (vmask & 0xFFu) { w.cls[idx] = (uint16_t)x0; w.meta[idx] = (uint8_t)(x0 >> 16); w.ids_at[idx] = kNoPiece; }
+              if (vmask & 0xFF00u) { w.cls[idx + 1] = (uint16_t)x1; w.meta[idx + 1] = (uint8_t)(x1 >> 16); w.ids_at[idx + 1] = kNoPiece; }
+              if (vmask & 0xFF0000u) { w.cls[idx + 2] = (uint16_t)x2; w.meta[idx + 2] = (uint8_t)(x2 >> 16); w.ids_at[idx + 2] = kNoPiece; }
+              if (vmask & 0xFF000000u) { w.cls[idx + 3] = (uint16_t)x3; w.meta[idx + 3] = (uint8_t)(x3 >> 16); w.ids_at[idx + 3] = kNoPiece; }
             }
+            m += (int)(blk_end - bpos);
+            ulen += (int)(blk_end - bpos);
+          } else {
+            const uint32_t w1 = pos0 + 4 < padded_bytes ? __ldg(text32 + (pos0 >> 2) + 1) : 0u;
+            const LaneDecode dcd = decode_lane(w0, w1, pos0, bpos, hi);
+            bad |= dcd.bad; sumlen += dcd.sumlen;
+            const int cnt = __popc(dcd.start_mask);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += v;
+            }
+            int idx = m + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (dcd.start_mask & (1u << k)) {
+                const uint32_t cp = dcd.cp[k];
+                const uint32_t x = cp < 128 ? top.ascii_clsx[cp] : __ldg(p.clsx_of_cp + cp);
+                w.cls[idx] = (uint16_t)x;
+                w.meta[idx] = (uint8_t)(x >> 16);
+                w.ids_at[idx] = kNoPiece;
+                ++idx;
+              }
+            }
+            m += __shfl_sync(0xffffffffu, incl, 31);
           }
-          m += __shfl_sync(0xffffffffu, incl, 31);
           bpos = bs + kBlockBytes;
         }
         const bool at_end = bpos >= hi;
@@ -255,79 +398,54 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
           unsigned tot = sumlen;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-          if (__any_sync(0xffffffffu, bad != 0) || (at_end && (int64_t)tot != hi - lo0)) { ok = false; break; }
+          if (__any_sync(0xffffffffu, bad != 0) || (at_end && (int64_t)tot + ulen != hi - lo0)) { ok = false; break; }
         }
         if (m == 0) break;
         __syncwarp();
 
-        // ---- sync points -> chunk starts ----
-        int nst = 0;
+        // ---- events: positions where a chunk may start (sync points) or the top-level class changes ----
+        const int limit = at_end ? m : m - max_tok;
+        w.nev = w.evh = w.nfast = w.fh = w.nslow = w.sh = 0;
+        w.carry = 0;
         for (int p0 = 0; p0 < m; p0 += 32) {
           const int q = p0 + lane;
-          bool flag = false;
+          bool ev = false;
+          unsigned entry = 0;
           if (q < m) {
-            flag = q == 0 || top.sync_start[((unsigned)meta[q - 1] << top.sync_shift) | (unsigned)meta[q]] != 0;
+            const unsigned tc = w.meta[q];
+            const unsigned tp = q > 0 ? (unsigned)w.meta[q - 1] : tc;
+            const unsigned sv = q == 0 ? (unsigned)kSyncStart : (unsigned)top.sync_start[(tp << top.sync_shift) | tc];
+            ev = sv != 0;
+            entry = (unsigned)q | ((sv & kSyncStart) ? 0x8000u : 0u);
           }
-          const unsigned bal = __ballot_sync(0xffffffffu, flag);
-          if (flag) starts[nst + __popc(bal & lanemask_lt())] = (uint16_t)q;
-          nst += __popc(bal);
+          const unsigned bal = __ballot_sync(0xffffffffu, ev);
+          if (ev) w.evq[(w.evh + w.nev + __popc(bal & lanemask_lt())) & (kEvRing - 1)] = (uint16_t)entry;
+          w.nev += __popc(bal);
+          __syncwarp();
+          if (w.nev >= 34) {         // 32 events with their successors
+            classify_round<TE>(w, top, words, 32, lane, m, at_end, limit, first);
+            drain_rounds<TE>(w, top, g, words, lane, m, at_end, limit, first, p.unk_id, false);
+          }
         }
+        // the end of the window closes the last chunk (twice: every event looks at two successors)
+        if (lane < 2) w.evq[(w.evh + w.nev + lane) & (kEvRing - 1)] = (uint16_t)((unsigned)m | 0x8000u);
+        w.nev += 2;
         __syncwarp();
-
-        // ---- order the chunks by length class (counting sort over the chunk list), so that the 32
-        // chunks of a round cost about the same and the lanes of the warp stay together ----
-        const int limit = at_end ? m : m - max_tok;
-        int carry = at_end ? m : 0;
-        {
-          int cnt0 = 0, cnt1 = 0, cnt2 = 0;     // chunks of length <= 2, 3..4, 5..7 (the rest is class 3)
-          for (int base = 0; base < nst; base += 32) {
-            const int i = base + lane;
-            int cl = 4;
-            if (i < nst) { const int len = (i + 1 < nst ? (int)starts[i + 1] : m) - (int)starts[i]; cl = len <= 2 ? 0 : len <= 4 ? 1 : len <= 7 ? 2 : 3; }
-            cnt0 += __popc(__ballot_sync(0xffffffffu, cl == 0));
-            cnt1 += __popc(__ballot_sync(0xffffffffu, cl == 1));
-            cnt2 += __popc(__ballot_sync(0xffffffffu, cl == 2));
-          }
-          int o0 = 0, o1 = cnt0, o2 = cnt0 + cnt1, o3 = cnt0 + cnt1 + cnt2;
-          for (int base = 0; base < nst; base += 32) {
-            const int i = base + lane;
-            int cl = 4;
-            if (i < nst) { const int len = (i + 1 < nst ? (int)starts[i + 1] : m) - (int)starts[i]; cl = len <= 2 ? 0 : len <= 4 ? 1 : len <= 7 ? 2 : 3; }
-            const unsigned b0 = __ballot_sync(0xffffffffu, cl == 0), b1 = __ballot_sync(0xffffffffu, cl == 1);
-            const unsigned b2 = __ballot_sync(0xffffffffu, cl == 2), b3 = __ballot_sync(0xffffffffu, cl == 3);
-            const unsigned lt = lanemask_lt();
-            if (cl == 0) order[o0 + __popc(b0 & lt)] = (uint16_t)i;
-            else if (cl == 1) order[o1 + __popc(b1 & lt)] = (uint16_t)i;
-            else if (cl == 2) order[o2 + __popc(b2 & lt)] = (uint16_t)i;
-            else if (cl == 3) order[o3 + __popc(b3 & lt)] = (uint16_t)i;
-            o0 += __popc(b0); o1 += __popc(b1); o2 += __popc(b2); o3 += __popc(b3);
-          }
+        while (w.nev >= 3) {
+          classify_round<TE>(w, top, words, w.nev - 2 < 32 ? w.nev - 2 : 32, lane, m, at_end, limit, first);
+          drain_rounds<TE>(w, top, g, words, lane, m, at_end, limit, first, p.unk_id, w.nev < 3);
         }
-        __syncwarp();
-
-        // ---- one lane per chunk: the reference's loops, verbatim in structure ----
-        for (int base = 0; base < nst; base += 32) {
-          const int k = base + lane;
-          if (k < nst) {
-            const int i = order[k];
-            int fb = starts[i];
-            int fe = i + 1 < nst ? (int)starts[i + 1] : m;
-            if (fe > limit) fe = limit;
-            if (i == 0 && first) fb = -1;
-            if (fb < fe) {
-              const int r = wp_chunk<TE>(top, g, cls, m, at_end, fb, fe, p.unk_id, ids_at, meta);
-              carry = max(carry, r);
-            }
-          }
-        }
+        int carry = at_end ? m : w.carry;
+        if (!at_end) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) carry = max(carry, __shfl_xor_sync(0xffffffffu, carry, o));
+          for (int o = 16; o > 0; o >>= 1) carry = max(carry, __shfl_xor_sync(0xffffffffu, carry, o));
+        }
         __syncwarp();
 
         // ---- ordered compaction of the ids of positions [0, carry) ----
         for (int p0 = 0; p0 < carry; p0 += 32) {
           const int q = p0 + lane;
-          const int32_t id = q < carry ? ids_at[q] : kNoPiece;
+          const int32_t id = q < carry ? w.ids_at[q] : kNoPiece;
           const bool f = id != kNoPiece;
           const unsigned bal = __ballot_sync(0xffffffffu, f);
           const int rank = out + __popc(bal & lanemask_lt());
@@ -340,10 +458,10 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
         const int rest = m - carry;
         for (int k0 = 0; k0 < rest; k0 += 32) {
           const int k = k0 + lane;
-          const uint16_t v = k < rest ? cls[carry + k] : (uint16_t)0;
-          const uint8_t mt = k < rest ? meta[carry + k] : (uint8_t)0;
+          const uint16_t v = k < rest ? w.cls[carry + k] : (uint16_t)0;
+          const uint8_t mt = k < rest ? w.meta[carry + k] : (uint8_t)0;
           __syncwarp();
-          if (k < rest) { cls[k] = v; meta[k] = mt; ids_at[k] = kNoPiece; }
+          if (k < rest) { w.cls[k] = v; w.meta[k] = mt; w.ids_at[k] = kNoPiece; }
         }
         __syncwarp();
         m = rest;

@@ -25,7 +25,8 @@ struct WpLaunch {
   const void* trans;           // dense table, uint16_t or uint32_t entries
   bool wide;
   const int32_t* tag_of_state;
-  const uint16_t* cls_of_cp;
+  const uint32_t* clsx_of_cp;  // [0x110000] class | top-level class << 16
+  WpWords words;               // whole-word table (slots in global memory)
   uint32_t NC1, first_final, cls_caret, cls_dollar;
   int max_token_length;
   unsigned long long* work_counter;   // device scalar, zeroed by the launcher

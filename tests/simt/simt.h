@@ -33,6 +33,8 @@ struct uint2 { unsigned x, y; };
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 inline int2 make_int2(int a, int b) { return int2{a, b}; }
+inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
+inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, d}; }
 struct dim3s { unsigned x = 0, y = 0, z = 0; };
 
 typedef void* cudaStream_t;
@@ -91,6 +93,12 @@ inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst
 inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {     // PRMT, default mode (selectors 0..7, no sign replication)
+  const uint64_t v = ((uint64_t)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+  return r;
+}
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline float __int_as_float(int v) { return simt::unpack<float>((uint64_t)(uint32_t)v); }

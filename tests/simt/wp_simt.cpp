@@ -54,7 +54,9 @@ int wpsim_batch(void* h, const char* text, const int64_t* offsets, int64_t ndocs
   L.wide = T.wide_states;
   L.trans = T.wide_states ? (const void*)T.trans32.data() : (const void*)T.trans16.data();
   L.tag_of_state = T.tag_of_state.data();
-  L.cls_of_cp = T.cls_of_cp.data();
+  L.clsx_of_cp = T.clsx_of_cp.data();
+  L.words = t->blob.words;
+  L.words.slots = t->blob.word_slots.data();
   L.blob = t->blob.bytes.data();
   L.layout = t->blob.layout;
   L.NC1 = (uint32_t)T.NC + 1; L.first_final = T.first_final; L.cls_caret = T.cls_caret; L.cls_dollar = T.cls_dollar;

@@ -59,7 +59,9 @@ int twin_info(void* h, int what) {
     case 10: return t->T.max_depth;
     case 11: return t->T.max_token_length;
     case 12: return (int)t->blob.layout.total_bytes;
-    case 13: return t->blob.layout.num_rows;
+    case 13: return (int)t->blob.word_count;
+    case 14: return (int)t->blob.words.log2_size;
+    case 15: return (int)t->blob.words.max_len;
     default: return -1;
   }
 }
@@ -106,7 +108,13 @@ int twin_wp_postpass(const int32_t* res, int rn, int32_t* ids, int max_ids, int 
 
 // One document through the mirrored warp algorithm.  `window` plays the role of the
 // kernel's per-warp window capacity (in code points); small values stress the carry logic.
+int twin_text_to_ids_ex(void* h, const char* s, int n, int32_t* ids, int max_ids, int unk, int window, int use_memo, int64_t* stats);
 int twin_text_to_ids(void* h, const char* s, int n, int32_t* ids, int max_ids, int unk, int window) {
+  return twin_text_to_ids_ex(h, s, n, ids, max_ids, unk, window, 1, nullptr);
+}
+// use_memo = 0: every chunk through the lexer loops (the memo must not change a single id);
+// stats[0..2] += words found in the table, words the table did not hold, chunks that emit nothing
+int twin_text_to_ids_ex(void* h, const char* s, int n, int32_t* ids, int max_ids, int unk, int window, int use_memo, int64_t* stats) {
   Twin* t = (Twin*)h;
   if (!twin_fast_ok(h)) return -2;
   if (n <= 0 || n > 1000000000 || !s) return 0;
@@ -140,18 +148,21 @@ int twin_text_to_ids(void* h, const char* s, int n, int32_t* ids, int max_ids, i
     }
   }
 
-  std::vector<uint16_t> cls((size_t)window + 8);
+  std::vector<uint16_t> cls((size_t)window + 32);
   std::vector<int32_t> ids_at((size_t)window + 8);
-  std::vector<uint8_t> has_id((size_t)window + 8);
-  std::vector<int> starts;
+  std::vector<uint8_t> tcs((size_t)window + 8);
+  std::vector<unsigned> events;
   WpGlobal<uint16_t> g16{};
   WpGlobal<uint32_t> g32{};
   auto fill_g = [&](auto& g, const auto* trans) {
-    g.trans = trans; g.tag_of_state = T.tag_of_state.data(); g.cls_of_cp = T.cls_of_cp.data();
+    g.trans = trans; g.tag_of_state = T.tag_of_state.data();
     g.NC1 = (uint32_t)T.NC + 1; g.first_final = T.first_final; g.cls_caret = T.cls_caret; g.cls_dollar = T.cls_dollar;
     g.max_token_length = max_tok;
   };
   if (T.wide_states) fill_g(g32, T.trans32.data()); else fill_g(g16, T.trans16.data());
+  WpWords words = t->blob.words;
+  words.slots = t->blob.word_slots.data();
+  if (!use_memo) words.max_len = 0;
 
   int m = 0, bpos = lo, out = 0;
   bool first = true;
@@ -162,39 +173,73 @@ int twin_text_to_ids(void* h, const char* s, int n, int32_t* ids, int max_ids, i
       int len = c < 0x80 ? 1 : (c & 0xE0) == 0xC0 ? 2 : (c & 0xF0) == 0xE0 ? 3 : 4;
       int cp = c < 0x80 ? c : len == 2 ? c & 0x1F : len == 3 ? c & 0x0F : c & 0x07;
       for (int k = 1; k < len; ++k) cp = (cp << 6) | (b[bpos + k] & 0x3F);
-      cls[m++] = cp < 128 ? top.ascii_cls[cp] : T.cls_of_cp[cp];
+      const uint32_t x = cp < 128 ? top.ascii_clsx[cp] : T.clsx_of_cp[cp];
+      cls[m] = (uint16_t)x; tcs[m] = (uint8_t)(x >> 16); ids_at[m] = kNoPiece;
+      ++m;
       bpos += len;
     }
     const bool at_end = bpos >= hi;
     if (m == 0) break;
-    for (int p = 0; p < m; ++p) { has_id[p] = top.tc_of_class[cls[p]]; ids_at[p] = kNoPiece; }   // top-level class of every position; no piece yet
-    // chunk starts: sync points whose first class can start a match; position 0 always
-    starts.clear();
-    starts.push_back(0);
-    for (int p = 1; p < m; ++p) {
-      const uint8_t t1 = top.tc_of_class[cls[p - 1]], t2 = top.tc_of_class[cls[p]];
-      const bool sync = !((top.cross[t1] >> t2) & 1ull);
-      if (sync && top.ttop[t2] != 0xFF) starts.push_back(p);
+    // events: chunk starts (sync points whose class can start a match; position 0 always) and changes of group
+    events.clear();
+    for (int p = 0; p < m; ++p) {
+      const unsigned tc = tcs[p], tp = p > 0 ? tcs[p - 1] : tc;
+      const unsigned sv = p == 0 ? (unsigned)kSyncStart : (unsigned)top.sync_start[(tp << top.sync_shift) | tc];
+      if (sv) events.push_back((unsigned)p | ((sv & kSyncStart) ? 0x8000u : 0u));
     }
+    events.push_back((unsigned)m | 0x8000u);
+    events.push_back((unsigned)m | 0x8000u);
     const int limit = at_end ? m : m - max_tok;
     int carry = at_end ? m : 0;
-    for (size_t i = 0; i < starts.size(); ++i) {
-      int fb = (i == 0 && first) ? -1 : starts[i];
-      int fe = i + 1 < starts.size() ? starts[i + 1] : m;
-      if (fb >= limit) break;
-      if (fe > limit) fe = limit;
+    auto loops = [&](int s, int e) -> int {
+      int fe = e > limit ? limit : e;
+      const int fb = (s == 0 && first) ? -1 : s;
+      if (fb >= fe) return 0;
       int r;
-      if (T.wide_states) r = wp_chunk<uint32_t>(top, g32, cls.data(), m, at_end, fb, fe, unk, ids_at.data(), has_id.data());
-      else r = wp_chunk<uint16_t>(top, g16, cls.data(), m, at_end, fb, fe, unk, ids_at.data(), has_id.data());
+      if (T.wide_states) r = wp_chunk<uint32_t>(top, g32, cls.data(), m, at_end, fb, fe, unk, ids_at.data(), tcs.data());
+      else r = wp_chunk<uint16_t>(top, g16, cls.data(), m, at_end, fb, fe, unk, ids_at.data(), tcs.data());
       if (r > carry) carry = r;
-      // exactness guard of the sync-point argument: a chunk must end exactly on the next start
-      if (i + 1 < starts.size() && starts[i + 1] <= limit && r != starts[i + 1]) return -3;
+      return 0;
+    };
+    for (size_t i = 0; i + 2 < events.size(); ++i) {
+      if (!(events[i] & 0x8000u)) continue;
+      const int s = (int)(events[i] & 0x7FFFu);
+      int we = (int)(events[i + 1] & 0x7FFFu), e = we;
+      bool shaped = true;
+      if (!(events[i + 1] & 0x8000u)) {
+        e = (int)(events[i + 2] & 0x7FFFu);
+        shaped = (events[i + 2] & 0x8000u) && (top.kind_of_tc[tcs[we]] & kKindDead);
+        if (!shaped) {
+          int p = we + 1;
+          while (p < m && !(top.sync_start[((unsigned)tcs[p - 1] << top.sync_shift) | (unsigned)tcs[p]] & kSyncStart)) ++p;
+          e = p;
+        }
+      }
+      if (!shaped || (!at_end && e > limit)) {
+        const int c0 = carry;
+        if (loops(s, e)) return -3;
+        // exactness guard of the sync-point argument: a chunk must end exactly on the next start
+        if (e < m && e <= limit && carry > c0 && carry != e && carry > e) return -3;
+        continue;
+      }
+      const int r = wp_classify_run(top.kind_of_tc[tcs[s]], we - s, words.max_len, first && s == 0, at_end && we == m);
+      if (r == 0) { if (loops(s, e)) return -3; continue; }
+      if (e > carry) carry = e;
+      if (r == 2) {
+        uint32_t kw[4];
+        wp_pack_key_any(words.cpw, cls.data() + s, we - s, we - s, words.cb, kw);
+        const int32_t id = wp_words_find(words, kw);
+        if (id != kNoPiece) { ids_at[s] = id; if (stats) ++stats[0]; }
+        else { if (stats) ++stats[1]; if (loops(s, we)) return -3; }
+      } else if (stats) ++stats[2];
     }
     for (int p = 0; p < carry && p < m; ++p)
       if (ids_at[p] != kNoPiece) { if (out < max_ids) ids[out] = ids_at[p]; ++out; }
     if (at_end) break;
     std::memmove(cls.data(), cls.data() + carry, sizeof(uint16_t) * (size_t)(m - carry));
+    std::memmove(tcs.data(), tcs.data() + carry, (size_t)(m - carry));
     m -= carry;
+    for (int p = 0; p < m; ++p) ids_at[p] = kNoPiece;
     first = false;
   }
   return out < max_ids ? out : max_ids;
