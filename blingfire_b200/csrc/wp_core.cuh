@@ -39,29 +39,42 @@ constexpr uint32_t kKindInert = 1u;      // a run of this class, of any length, 
 constexpr uint32_t kKindCaretOk = 2u;    // the left anchor (run at the start of the document) does not change the outcome
 constexpr uint32_t kKindDollarOk = 4u;   // the right anchor (run at the end of the document) does not change the outcome
 constexpr uint32_t kKindDead = 8u;       // positions of this class match nothing and start nothing (white space in bert_*)
-constexpr int kKindLenShift = 8;         // bit (kKindLenShift + L): a run of L positions is ONE WORD token over [0, L) calling
-                                         // the class's function pair; L = 1..kMaxFastLen
-constexpr int kMaxFastLen = 12;
+constexpr uint32_t kKindWordRun = 16u;   // a run of any length is ONE WORD token over the run, calling the group's function pair
+constexpr uint32_t kKindWordOne = 32u;   // ... a run of length 1 is
+constexpr int kMaxFastLen = 24;          // longest word the table's key holds (two halves of 12 classes at 10 bits)
 // sync_start entries
 constexpr uint8_t kSyncStart = 1;        // a chunk may start at the second position of the pair
 constexpr uint8_t kSyncGroupChange = 2;  // the two positions belong to different groups of top-level classes (wp_model.cpp)
 
-// One slot of the whole-word table: the packed class sequence (with its length) and the piece id.
-struct alignas(16) WpWordSlot {
+// One slot of the word table: the packed class sequence of a word (with its length) and its pieces.  Two 32-byte
+// sectors; a word of at most half the maximal length with at most 3 pieces is served from the first one alone.
+//   meta == 0            empty
+//   meta == kSlotBusy    being written (run-time insertion)
+//   meta & kSlotValid    n = meta & 7 pieces (0: the word is one UnkId), ids in id[0..3) and id_hi[0..3); piece 1 starts
+//                        (meta >> 4) & 31 positions into the word, piece 2 (meta >> 9) & 31, pieces 3..5 at the bytes of offs_hi
+struct alignas(32) WpWordSlot {
   uint32_t kw[4];
-  int32_t id;
-  uint32_t pad[3];
+  int32_t id[3];
+  uint32_t meta;
+  uint32_t kw_hi[4];
+  int32_t id_hi[3];
+  uint32_t offs_hi;
 };
-static_assert(sizeof(WpWordSlot) == 32, "one 32-byte sector per slot");
+static_assert(sizeof(WpWordSlot) == 64, "two 32-byte sectors per slot");
+constexpr uint32_t kSlotBusy = 1u, kSlotValid = 0x80000000u;
+constexpr int kMaxLearnPieces = 6;
 
-// Cuckoo table: slot h1(key) of the first half or slot h2(key) of the second half.
+// Two-choice table: slot h1(key) of the first half or slot h2(key) of the second half.  The single-piece words of the
+// vocabulary are placed at load time (cuckoo, wp_model.cpp); words with several pieces (and words that are one
+// UnkId) are added at RUN time by the warp that has just sent one through the lexer loops -- into an EMPTY candidate
+// slot only, never over an entry, so a slot is written once and a reader can trust what it matches (wp_words_insert).
 struct WpWords {
-  const WpWordSlot* slots;   // [2 << log2_size]
+  WpWordSlot* slots;         // [2 << log2_size]
   uint32_t log2_size;        // slots per half (power of two)
   uint32_t cb;               // bits per class in the key
   uint32_t cpw;              // classes per 32-bit key word: 3, 2 or 1
-  uint32_t max_len;          // longest run the key holds: min(kMaxFastLen, 4 * cpw); 0 = no table
-  uint32_t mul[8];           // odd multipliers of the two hash functions
+  uint32_t max_len;          // longest run the key holds: min(kMaxFastLen, 8 * cpw); 0 = no table
+  uint32_t mul[9];           // odd multipliers of the hash
 };
 
 // Small, read-mostly part of the model.  On the device every pointer below addresses shared
@@ -77,6 +90,8 @@ struct WpTop {
                                   //           here (no walk crosses the pair, and some match starts with the class);
                                   //           kSyncGroupChange: the classes belong to different groups
   const uint32_t* kind_of_tc;     // [NT] kKind* bits
+  const uint32_t* fn_root_of_tc;  // [NT] function entry states of the class's group (word runs), or none
+  const uint32_t* fn_caret_of_tc; // [NT]
   int K, NT;
   uint8_t tc_caret, tc_dollar, tc_none, sync_shift;
 };
@@ -208,13 +223,14 @@ BF_HD int wp_chunk(const WpTop& t, const WpGlobal<TE>& g, const uint16_t* cls, i
 
 // ---- the whole-word memo ----
 
-// Packs the class sequence cls[0..L) and its length into four 32-bit words, CPW classes of `cb` bits per
-// word (CPW * cb <= 30; bits 30-31 of words 0 and 1 hold L).  `lcap` >= L bounds the unrolled loop (on
-// the device: the warp-wide maximum, so the lanes stay together).  Injective for L <= 4 * CPW.
+// Packs the class sequence cls[0..L) and its length into eight 32-bit words, CPW classes of `cb` bits per word
+// (CPW * cb <= 30; bits 30-31 of words 0..2 hold L).  Words 4..7 are only needed (and only computed) for words longer
+// than 4 * CPW classes.  `lcap` >= L bounds the unrolled loop (on the device: the warp-wide maximum, so the lanes stay
+// together).  Injective for L <= 8 * CPW.
 template <int CPW>
-BF_HD void wp_pack_key(const uint16_t* cls, int L, int lcap, uint32_t cb, uint32_t kw[4]) {
+BF_HD void wp_pack_key(const uint16_t* cls, int L, int lcap, uint32_t cb, uint32_t kw[8]) {
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
+  for (int w = 0; w < 8; ++w) {
     uint32_t v = 0;
     if (w * CPW < lcap) {
 #pragma unroll
@@ -226,40 +242,127 @@ BF_HD void wp_pack_key(const uint16_t* cls, int L, int lcap, uint32_t cb, uint32
     kw[w] = v;
   }
   kw[0] |= ((uint32_t)L & 3u) << 30;
-  kw[1] |= ((uint32_t)L >> 2) << 30;
+  kw[1] |= (((uint32_t)L >> 2) & 3u) << 30;
+  kw[2] |= ((uint32_t)L >> 4) << 30;
 }
-BF_HD void wp_pack_key_any(uint32_t cpw, const uint16_t* cls, int L, int lcap, uint32_t cb, uint32_t kw[4]) {
+BF_HD void wp_pack_key_any(uint32_t cpw, const uint16_t* cls, int L, int lcap, uint32_t cb, uint32_t kw[8]) {
   if (cpw == 3) wp_pack_key<3>(cls, L, lcap, cb, kw);
   else if (cpw == 2) wp_pack_key<2>(cls, L, lcap, cb, kw);
   else wp_pack_key<1>(cls, L, lcap, cb, kw);
 }
 
-BF_HD uint32_t wp_key_hash(const uint32_t kw[4], const uint32_t* mul, uint32_t log2_size) {
+// 32-bit mix of the key; the two slot indices are different bit ranges of two products of it.  `wide`: some word of
+// the round is longer than half the maximum (the upper key words of the others are zero).
+BF_HD uint32_t wp_key_hash(const uint32_t kw[8], const uint32_t* mul, bool wide) {
   uint32_t h = kw[0] * mul[0] + kw[1] * mul[1] + kw[2] * mul[2] + kw[3] * mul[3];
+  if (wide) h += kw[4] * mul[5] + kw[5] * mul[6] + kw[6] * mul[7] + kw[7] * mul[8];
   h ^= h >> 16;
   h *= 0x85EBCA6Bu;
-  return h >> (32u - log2_size);
+  h ^= h >> 13;
+  return h;
+}
+BF_HD uint32_t wp_slot1(const WpWords& W, uint32_t h) { return h >> (32u - W.log2_size); }
+BF_HD uint32_t wp_slot2(const WpWords& W, uint32_t h) { return ((h * W.mul[4]) >> (32u - W.log2_size)) + (1u << W.log2_size); }
+
+struct WpWordHit {
+  uint32_t meta;       // 0: not in the table
+  uint32_t offs_hi;
+  int32_t id[6];
+};
+
+BF_HD bool wp_slot_matches(const WpWordSlot& a, const uint32_t kw[8], bool wide) {
+  bool m = a.kw[0] == kw[0] && a.kw[1] == kw[1] && a.kw[2] == kw[2] && a.kw[3] == kw[3];
+  if (wide) m = m && a.kw_hi[0] == kw[4] && a.kw_hi[1] == kw[5] && a.kw_hi[2] == kw[6] && a.kw_hi[3] == kw[7];
+  return m;
 }
 
-// The piece id of the word with this key, or kNoPiece when the table does not hold it.
-BF_HD int32_t wp_words_find(const WpWords& W, const uint32_t kw[4]) {
-  const uint32_t h1 = wp_key_hash(kw, W.mul, W.log2_size);
-  const uint32_t h2 = wp_key_hash(kw, W.mul + 4, W.log2_size) + (1u << W.log2_size);
+// Looks a word up.  Slots are written once (meta goes 0 -> busy -> valid, the key and the ids are in place before
+// it turns valid), so a valid slot whose key matches is complete; a slot seen half-way is simply "not found".
+BF_HD WpWordHit wp_words_find(const WpWords& W, const uint32_t kw[8], bool wide) {
+  const uint32_t h = wp_key_hash(kw, W.mul, wide);
+  const uint32_t h1 = wp_slot1(W, h), h2 = wp_slot2(W, h);
+  WpWordHit r;
 #if defined(__CUDA_ARCH__)
   const uint4* s1 = reinterpret_cast<const uint4*>(W.slots + h1);
   const uint4* s2 = reinterpret_cast<const uint4*>(W.slots + h2);
-  const uint4 a = __ldg(s1), b = __ldg(s2);
-  const uint4 ai = __ldg(s1 + 1), bi = __ldg(s2 + 1);
-  const bool m1 = ((a.x ^ kw[0]) | (a.y ^ kw[1]) | (a.z ^ kw[2]) | (a.w ^ kw[3])) == 0;
-  const bool m2 = ((b.x ^ kw[0]) | (b.y ^ kw[1]) | (b.z ^ kw[2]) | (b.w ^ kw[3])) == 0;
-  return m1 ? (int32_t)ai.x : (m2 ? (int32_t)bi.x : kNoPiece);
+  const uint4 a = s1[0], b = s2[0];
+  const uint4 ai = s1[1], bi = s2[1];
+  bool m1 = (((a.x ^ kw[0]) | (a.y ^ kw[1]) | (a.z ^ kw[2]) | (a.w ^ kw[3])) == 0) && (ai.w & kSlotValid);
+  bool m2 = (((b.x ^ kw[0]) | (b.y ^ kw[1]) | (b.z ^ kw[2]) | (b.w ^ kw[3])) == 0) && (bi.w & kSlotValid);
+  const uint4* sm = m1 ? s1 : s2;
+  if (wide) {                    // (warp-uniform) the upper halves of the keys
+    const uint4 c = s1[2], d = s2[2];
+    m1 = m1 && (((c.x ^ kw[4]) | (c.y ^ kw[5]) | (c.z ^ kw[6]) | (c.w ^ kw[7])) == 0);
+    m2 = m2 && (((d.x ^ kw[4]) | (d.y ^ kw[5]) | (d.z ^ kw[6]) | (d.w ^ kw[7])) == 0);
+    sm = m1 ? s1 : s2;
+  }
+  r.meta = m1 ? ai.w : (m2 ? bi.w : 0u);
+  r.id[0] = (int32_t)(m1 ? ai.x : bi.x); r.id[1] = (int32_t)(m1 ? ai.y : bi.y); r.id[2] = (int32_t)(m1 ? ai.z : bi.z);
+  r.offs_hi = 0; r.id[3] = r.id[4] = r.id[5] = 0;
+  if ((r.meta & 7u) > 3u) {      // rare: more than three pieces
+    const uint4 e = sm[3];
+    r.id[3] = (int32_t)e.x; r.id[4] = (int32_t)e.y; r.id[5] = (int32_t)e.z; r.offs_hi = e.w;
+  }
 #else
-  const WpWordSlot& a = W.slots[h1];
-  const WpWordSlot& b = W.slots[h2];
-  if (a.kw[0] == kw[0] && a.kw[1] == kw[1] && a.kw[2] == kw[2] && a.kw[3] == kw[3]) return a.id;
-  if (b.kw[0] == kw[0] && b.kw[1] == kw[1] && b.kw[2] == kw[2] && b.kw[3] == kw[3]) return b.id;
-  return kNoPiece;
+  r.meta = 0; r.offs_hi = 0;
+  for (int i = 0; i < 6; ++i) r.id[i] = 0;
+  const uint32_t hs[2] = {h1, h2};
+  for (int k = 0; k < 2 && !r.meta; ++k) {
+    const WpWordSlot& a = W.slots[hs[k]];
+    const uint32_t meta = __atomic_load_n(&a.meta, __ATOMIC_ACQUIRE);
+    if ((meta & kSlotValid) && wp_slot_matches(a, kw, wide)) {
+      r.meta = meta; r.offs_hi = a.offs_hi;
+      for (int i = 0; i < 3; ++i) { r.id[i] = a.id[i]; r.id[3 + i] = a.id_hi[i]; }
+    }
+  }
 #endif
+  return r;
+}
+
+// Adds a word the lexer loops have just resolved (n pieces, n <= kMaxLearnPieces; n = 0: one UnkId) to an empty
+// candidate slot.  Another warp may be adding the same word: whoever claims the slot first writes it, the other
+// one finds it busy and leaves.  Nothing is ever overwritten.
+BF_HD void wp_words_insert(const WpWords& W, const uint32_t kw[8], bool wide, int n, const int32_t* ids, const int* offs) {
+  const uint32_t h = wp_key_hash(kw, W.mul, wide);
+  const uint32_t hs[2] = {wp_slot1(W, h), wp_slot2(W, h)};
+  const uint32_t meta = kSlotValid | (uint32_t)n | ((uint32_t)(n > 1 ? offs[1] : 0) << 4) | ((uint32_t)(n > 2 ? offs[2] : 0) << 9);
+  const uint32_t offs_hi = (uint32_t)(n > 3 ? offs[3] : 0) | ((uint32_t)(n > 4 ? offs[4] : 0) << 8) | ((uint32_t)(n > 5 ? offs[5] : 0) << 16);
+  for (int k = 0; k < 2; ++k) {
+    WpWordSlot* s = W.slots + hs[k];
+#if defined(__CUDA_ARCH__)
+    const uint32_t old = atomicCAS(&s->meta, 0u, kSlotBusy);
+#else
+    uint32_t old = 0;
+    __atomic_compare_exchange_n(&s->meta, &old, kSlotBusy, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+#endif
+    if (old == 0u) {
+      for (int i = 0; i < 4; ++i) { s->kw[i] = kw[i]; s->kw_hi[i] = wide ? kw[4 + i] : 0u; }
+      for (int i = 0; i < 3; ++i) { s->id[i] = n > i ? ids[i] : 0; s->id_hi[i] = n > 3 + i ? ids[3 + i] : 0; }
+      s->offs_hi = offs_hi;
+#if defined(__CUDA_ARCH__)
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(&s->meta) = meta;
+#else
+      __atomic_store_n(&s->meta, meta, __ATOMIC_RELEASE);
+#endif
+      return;
+    }
+    // taken: by this very word (then it is in the table) or by another one (try the other slot)
+    if ((old & kSlotValid) && wp_slot_matches(*s, kw, wide)) return;
+  }
+}
+
+// Writes a table hit for the word starting at window position s.
+BF_HD void wp_apply_hit(const WpWordHit& h, int s, int unk_id, int32_t* ids_at) {
+  const uint32_t n = h.meta & 7u;
+  ids_at[s] = n == 0 ? unk_id : h.id[0];
+  if (n > 1) ids_at[s + (int)((h.meta >> 4) & 31u)] = h.id[1];
+  if (n > 2) ids_at[s + (int)((h.meta >> 9) & 31u)] = h.id[2];
+  if (n > 3) {
+    ids_at[s + (int)(h.offs_hi & 255u)] = h.id[3];
+    if (n > 4) ids_at[s + (int)((h.offs_hi >> 8) & 255u)] = h.id[4];
+    if (n > 5) ids_at[s + (int)((h.offs_hi >> 16) & 255u)] = h.id[5];
+  }
 }
 
 // May the run [s, e) -- every position in one group of top-level classes, kind `kind` -- be served by the memo?  Returns
@@ -268,7 +371,7 @@ BF_HD int wp_classify_run(uint32_t kind, int len, uint32_t max_len, bool at_doc_
   if (kind & kKindInert) return 1;       // established over the closure with both anchors
   if (at_doc_start && !(kind & kKindCaretOk)) return 0;
   if (at_doc_end && !(kind & kKindDollarOk)) return 0;
-  if (len <= (int)max_len && ((kind >> (kKindLenShift + len)) & 1u)) return 2;
+  if (len <= (int)max_len && ((kind & kKindWordRun) || (len == 1 && (kind & kKindWordOne)))) return 2;
   return 0;
 }
 

@@ -29,21 +29,20 @@ constexpr int kWarpsPerCta = 16;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kWin = 576;            // window capacity in code points (per warp)
 constexpr int kBlockBytes = 128;     // bytes consumed per decode step (32 lanes x uchar4)
-constexpr int kPad = 4;              // the window starts (lo & 3) entries into its arrays, so that a lane's 4 ASCII bytes land on
-                                     // a 4-entry boundary and go out as one vector store per array
+constexpr int kPad = 4;              // the window starts (offset & 3) entries into its arrays, so that a lane's 4 ASCII bytes land
+                                     // on a 4-entry boundary and go out as one vector store per array
 constexpr int kRing = 64;            // entries per work ring (a round consumes 32; at most 63 are ever queued)
-constexpr int kEvRing = 128;         // the event ring: a round needs 34 queued (every event looks at its two successors)
-// per-warp shared memory: ids_at i32 | cls u16 (+ slack for the key reads past a chunk) | top class u8 | event ring u16 |
-// fast ring u32 | slow ring u32
+// per-warp shared memory: ids_at i32 | cls u16 (+ slack for the key reads past a chunk) | top class u8 | events u16 |
+// table ring u32 | loops ring u32
 constexpr int kOffCls = (kWin + kPad) * 4;
 constexpr int kOffMeta = kOffCls + (kWin + kPad + kMaxFastLen + 4) * 2;
-constexpr int kOffEvq = (kOffMeta + kWin + kPad + 15) & ~15;
-constexpr int kOffFastq = kOffEvq + kEvRing * 2;
+constexpr int kOffEv = (kOffMeta + kWin + kPad + 15) & ~15;
+constexpr int kOffFastq = kOffEv + (kWin + 8) * 2;
 constexpr int kOffSlowq = kOffFastq + kRing * 4;
 constexpr int kWarpSmem = kOffSlowq + kRing * 4;
 
 static_assert(kWin % 32 == 0, "window must be a multiple of the warp size");
-static_assert(kOffCls % 16 == 0 && kOffMeta % 4 == 0 && kWarpSmem % 16 == 0, "vector stores need aligned arrays");
+static_assert(kOffCls % 16 == 0 && kOffMeta % 4 == 0 && kOffFastq % 4 == 0 && kWarpSmem % 16 == 0, "vector stores need aligned arrays");
 static_assert(kWin + kPad < 0x8000, "event entries keep the position in 15 bits");
 
 __device__ __forceinline__ unsigned lanemask_lt() {
@@ -90,6 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 // ---- UTF-8: decode the (up to 4) sequences that START in this lane's word ----
 // Strictness follows FAUtf8ToInt (FAUtf8Utils.cpp:121-196): shortest form, no surrogates,
 // <= U+10FFFF, continuation bytes 10xxxxxx, no truncation at the end of the document.
+// Offsets are relative to the 4-byte-aligned word the document starts in: the document is [ulo, uhi).
 struct LaneDecode {
   uint32_t cp[4];
   unsigned start_mask;   // bit k: a sequence starts at byte k of the lane's word
@@ -97,17 +97,17 @@ struct LaneDecode {
   unsigned sumlen;       // total length of the sequences that start here
 };
 
-__device__ __forceinline__ LaneDecode decode_lane(uint32_t w0, uint32_t w1, int64_t pos0, int64_t bpos, int64_t hi) {
+__device__ __forceinline__ LaneDecode decode_lane(uint32_t w0, uint32_t w1, int u0, int ulo, int uhi) {
   LaneDecode r;
   r.start_mask = 0; r.bad = 0; r.sumlen = 0;
   const uint64_t x = ((uint64_t)w1 << 32) | w0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int64_t pos = pos0 + k;
+    const int pos = u0 + k;
     const uint32_t y = (uint32_t)(x >> (8 * k));
     const uint32_t b0 = y & 0xFF, b1 = (y >> 8) & 0xFF, b2 = (y >> 16) & 0xFF, b3 = y >> 24;
     r.cp[k] = 0;
-    if (pos >= bpos && pos < hi && (b0 & 0xC0) != 0x80) {
+    if (pos >= ulo && pos < uhi && (b0 & 0xC0) != 0x80) {
       uint32_t cp, len, bad = 0;
       if (b0 < 0x80) { cp = b0; len = 1; }
       else if ((b0 & 0xE0) == 0xC0) {
@@ -120,7 +120,7 @@ __device__ __forceinline__ LaneDecode decode_lane(uint32_t w0, uint32_t w1, int6
         len = 4; cp = ((b0 & 0x07) << 18) | ((b1 & 0x3F) << 12) | ((b2 & 0x3F) << 6) | (b3 & 0x3F);
         bad = ((b1 & 0xC0) != 0x80) | ((b2 & 0xC0) != 0x80) | ((b3 & 0xC0) != 0x80) | (cp < 0x10000) | (cp > 0x10FFFF);
       } else { cp = 0; len = 1; bad = 1; }
-      bad |= (pos + len > hi);
+      bad |= (pos + (int)len > uhi);
       r.bad |= bad;
       r.sumlen += len;
       r.cp[k] = bad ? 0u : cp;
@@ -130,36 +130,57 @@ __device__ __forceinline__ LaneDecode decode_lane(uint32_t w0, uint32_t w1, int6
   return r;
 }
 
-// The per-warp working set: one window of the current document and the three work rings.
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// The per-warp working set: one window of the current document, its events, and the two work rings.
 struct WarpWin {
   int32_t* ids_at;     // [kWin] id of the piece starting at a position, kNoPiece elsewhere
   uint16_t* cls;       // [kWin] class of every position
   uint8_t* meta;       // [kWin] top-level class of every position
-  uint16_t* evq;       // ring of events: position | 0x8000 when a chunk may start there (else: only the class changes)
-  uint32_t* fastq;     // ring of word runs for the whole-word table: start | length << 16
-  uint32_t* slowq;     // ring of chunks for the lexer loops: start | end << 16
-  int nev, evh, nfast, fh, nslow, sh;   // ring counts and heads (warp-uniform)
+  uint16_t* ev;        // events in position order: position | 0x8000 when a chunk may start there (else: only the group
+                       // of top-level classes changes)
+  uint32_t* fastq;     // ring of word runs for the table: start | length << 16
+  uint32_t* slowq;     // ring of chunks for the lexer loops: start | end << 16; bit 15: a word run the table did not hold
+  int nev, nfast, fh, nslow, sh;   // counts and ring heads (warp-uniform)
   int carry;           // per lane: largest position known to be a finished chunk boundary
 };
+
+// Events of the positions [pb, pe), one position per lane (the all-ASCII blocks make theirs in registers).
+__device__ __forceinline__ void gen_events(WarpWin& w, const WpTop& top, int pb, int pe, int lane) {
+  for (int p0 = pb; p0 < pe; p0 += 32) {
+    const int q = p0 + lane;
+    unsigned sv = 0;
+    if (q < pe) sv = q == 0 ? (unsigned)kSyncStart : (unsigned)top.sync_start[((unsigned)w.meta[q - 1] << top.sync_shift) | (unsigned)w.meta[q]];
+    const unsigned bal = __ballot_sync(0xffffffffu, sv != 0);
+    if (sv) w.ev[w.nev + __popc(bal & lanemask_lt())] = (uint16_t)((unsigned)q | ((sv & kSyncStart) ? 0x8000u : 0u));
+    w.nev += __popc(bal);
+  }
+}
 
 // Events -> chunks: every lane takes one event and its two successors.  A chunk start followed by another chunk
 // start is a run inside ONE group of top-level classes (a change of group would be an event of its own); a chunk
 // start, a change to the DEAD group, and the next chunk start is such a run followed by positions that match
 // nothing ("word" + white space in bert_*).  The per-group memo says whether the run emits nothing, is one word for
 // the table, or needs the loops -- as does every chunk of another shape.
-template <typename TE>
-__device__ __forceinline__ void classify_round(WarpWin& w, const WpTop& top, const WpWords& words, int cnt, int lane, int m,
+__device__ __forceinline__ void classify_round(WarpWin& w, const WpTop& top, const WpWords& words, int i0, int cnt, int lane, int m,
                                                bool at_end, int limit, bool first) {
   int action = 0;      // 1 = table, 2 = loops
   int s = 0, we = 0, e = 0;
   if (lane < cnt) {
-    const unsigned e0 = w.evq[(w.evh + lane) & (kEvRing - 1)], e1 = w.evq[(w.evh + lane + 1) & (kEvRing - 1)];
+    const unsigned e0 = w.ev[i0 + lane], e1 = w.ev[i0 + lane + 1];
     s = (int)(e0 & 0x7FFFu);
     if (e0 & 0x8000u) {
       bool shaped = true;
       we = e = (int)(e1 & 0x7FFFu);
       if (!(e1 & 0x8000u)) {
-        const unsigned e2 = w.evq[(w.evh + lane + 2) & (kEvRing - 1)];
+        const unsigned e2 = w.ev[i0 + lane + 2];
         e = (int)(e2 & 0x7FFFu);
         shaped = (e2 & 0x8000u) && (top.kind_of_tc[w.meta[we]] & kKindDead);
         if (!shaped) {
@@ -183,57 +204,81 @@ __device__ __forceinline__ void classify_round(WarpWin& w, const WpTop& top, con
   if (action == 1) w.fastq[(w.fh + w.nfast + __popc(bf & lt)) & (kRing - 1)] = (uint32_t)s | ((uint32_t)(we - s) << 16);
   if (action == 2) w.slowq[(w.sh + w.nslow + __popc(bs & lt)) & (kRing - 1)] = (uint32_t)s | ((uint32_t)e << 16);
   w.nfast += __popc(bf); w.nslow += __popc(bs);
-  w.evh = (w.evh + cnt) & (kEvRing - 1); w.nev -= cnt;
   __syncwarp();
 }
 
-// One word per lane through the whole-word table; what the table does not hold goes to the loops.
-__device__ __forceinline__ void fast_round(WarpWin& w, const WpWords& words, int cnt, int lane) {
+// One word per lane through the table; what it does not hold goes to the loops (and from there into the table).
+__device__ __forceinline__ void fast_round(WarpWin& w, const WpWords& words, int cnt, int lane, int unk_id) {
   int s = 0, L = 0;
   if (lane < cnt) {
     const uint32_t ent = w.fastq[(w.fh + lane) & (kRing - 1)];
     s = (int)(ent & 0xFFFFu); L = (int)(ent >> 16);
   }
   const int lcap = __reduce_max_sync(0xffffffffu, L);
-  uint32_t kw[4];
+  const bool wide = lcap > (int)(4 * words.cpw);     // some word of the round needs the upper half of the key
+  uint32_t kw[8];
   wp_pack_key_any(words.cpw, w.cls + s, L, lcap, words.cb, kw);
-  const int32_t id = wp_words_find(words, kw);
-  const bool hit = lane < cnt && id != kNoPiece;
-  if (hit) w.ids_at[s] = id;
-  const bool miss = lane < cnt && !hit;
+  const WpWordHit hit = wp_words_find(words, kw, wide);
+  const bool found = lane < cnt && hit.meta != 0;
+  if (found) wp_apply_hit(hit, s, unk_id, w.ids_at);
+  const bool miss = lane < cnt && !found;
   const unsigned bm = __ballot_sync(0xffffffffu, miss);
-  if (miss) w.slowq[(w.sh + w.nslow + __popc(bm & lanemask_lt())) & (kRing - 1)] = (uint32_t)s | ((uint32_t)(s + L) << 16);
+  if (miss) w.slowq[(w.sh + w.nslow + __popc(bm & lanemask_lt())) & (kRing - 1)] = (uint32_t)s | 0x8000u | ((uint32_t)(s + L) << 16);
   w.nslow += __popc(bm);
   w.fh = (w.fh + cnt) & (kRing - 1); w.nfast -= cnt;
   __syncwarp();
 }
 
-// One chunk per lane through the reference's loops (wp_core.cuh).
+// One chunk per lane through the reference's loops (wp_core.cuh).  A word run the table did not hold is resolved by
+// the function sub-grammar alone -- its top-level outcome is the memo's -- and then added to the table.
 template <typename TE>
-__device__ __forceinline__ void slow_round(WarpWin& w, const WpTop& top, const WpGlobal<TE>& g, int cnt, int lane, int m, bool at_end,
-                                           int limit, bool first, int unk_id) {
+__device__ __forceinline__ void slow_round(WarpWin& w, const WpTop& top, const WpGlobal<TE>& g, const WpWords& words, int cnt, int lane,
+                                           int m, bool at_end, int limit, bool first, int unk_id) {
   if (lane < cnt) {
     const uint32_t ent = w.slowq[(w.sh + lane) & (kRing - 1)];
-    const int s = (int)(ent & 0xFFFFu);
+    const int s = (int)(ent & 0x7FFFu);
     int fe = (int)(ent >> 16);
-    if (fe > limit) fe = limit;
-    const int fb = (s == 0 && first) ? -1 : s;
-    if (fb < fe) w.carry = max(w.carry, wp_chunk<TE>(top, g, w.cls, m, at_end, fb, fe, unk_id, w.ids_at, w.meta));
+    if (ent & 0x8000u) {
+      const unsigned tc = w.meta[s];
+      const int tiled = wp_word<TE>(g, w.cls, s, fe - 1, top.fn_root_of_tc[tc], top.fn_caret_of_tc[tc], w.ids_at);
+      int n = 0, offs[kMaxLearnPieces];
+      int32_t ids[kMaxLearnPieces];
+      if (!tiled) {                      // not covered without gaps -> one UnkId (blingfiretokdll.cpp:1282-1301)
+        for (int p = s + 1; p < fe; ++p) w.ids_at[p] = kNoPiece;
+        w.ids_at[s] = unk_id;
+      } else {
+        for (int p = s; p < fe; ++p) {
+          const int32_t id = w.ids_at[p];
+          if (id != kNoPiece) { if (n < kMaxLearnPieces) { ids[n] = id; offs[n] = p - s; } ++n; }
+        }
+      }
+      if (n <= kMaxLearnPieces) {
+        uint32_t kw[8];
+        wp_pack_key_any(words.cpw, w.cls + s, fe - s, fe - s, words.cb, kw);
+        wp_words_insert(words, kw, fe - s > (int)(4 * words.cpw), n, ids, offs);
+      }
+    } else {
+      if (fe > limit) fe = limit;
+      const int fb = (s == 0 && first) ? -1 : s;
+      if (fb < fe) w.carry = max(w.carry, wp_chunk<TE>(top, g, w.cls, m, at_end, fb, fe, unk_id, w.ids_at, w.meta));
+    }
   }
   w.sh = (w.sh + cnt) & (kRing - 1); w.nslow -= cnt;
   __syncwarp();
 }
 
+// Runs full rounds (32 entries) of the two rings; with `all`, empties them.  A ring holds at most 63 entries: the
+// loops' ring is brought below 32 before a table round can add its misses.
 template <typename TE>
 __device__ __forceinline__ void drain_rounds(WarpWin& w, const WpTop& top, const WpGlobal<TE>& g, const WpWords& words, int lane, int m,
                                              bool at_end, int limit, bool first, int unk_id, bool all) {
-  // a ring holds at most 63 entries: the loops' ring is emptied before the table round can add 32 more
-  if (w.nslow >= 32) slow_round<TE>(w, top, g, 32, lane, m, at_end, limit, first, unk_id);
-  if (w.nfast >= 32) fast_round(w, words, 32, lane);
-  if (w.nslow >= 32) slow_round<TE>(w, top, g, 32, lane, m, at_end, limit, first, unk_id);
-  if (all) {
-    if (w.nfast > 0) fast_round(w, words, w.nfast, lane);
-    while (w.nslow > 0) slow_round<TE>(w, top, g, w.nslow < 32 ? w.nslow : 32, lane, m, at_end, limit, first, unk_id);
+  for (;;) {
+    if (w.nslow >= 32 || (all && w.nslow > 0 && w.nfast == 0))
+      slow_round<TE>(w, top, g, words, w.nslow < 32 ? w.nslow : 32, lane, m, at_end, limit, first, unk_id);
+    else if (w.nfast >= 32 || (all && w.nfast > 0))
+      fast_round(w, words, w.nfast < 32 ? w.nfast : 32, lane, unk_id);
+    else
+      break;
   }
 }
 
@@ -272,13 +317,13 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
 
   uint8_t* wbase = smem + blob_bytes + (size_t)warp * kWarpSmem;
   WarpWin w;
-  w.evq = reinterpret_cast<uint16_t*>(wbase + kOffEvq);
+  w.ev = reinterpret_cast<uint16_t*>(wbase + kOffEv);
   w.fastq = reinterpret_cast<uint32_t*>(wbase + kOffFastq);
   w.slowq = reinterpret_cast<uint32_t*>(wbase + kOffSlowq);
 
   const uint32_t* text32 = reinterpret_cast<const uint32_t*>(p.text);
-  const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
   const int max_tok = p.max_token_length;
+  const unsigned sh = top.sync_shift;
 
   for (;;) {
     unsigned long long d64 = 0;
@@ -286,96 +331,120 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
     d64 = __shfl_sync(0xffffffffu, d64, 0);
     if ((int64_t)d64 >= p.ndocs) break;
     const int64_t doc = (int64_t)d64;
-    int64_t lo = __ldg(p.offsets + doc);
-    const int64_t hi = __ldg(p.offsets + doc + 1);
-    const int64_t n = hi - lo;
+    const int64_t lo = __ldg(p.offsets + doc);
+    const int64_t n64 = __ldg(p.offsets + doc + 1) - lo;
     int result = 0;
 
-    // parameter validation (blingfiretokdll.cpp:1121) and the BOM (FAUtf8Utils.cpp:247-252)
-    bool run = n > 0 && n <= 1000000000;
-    if (run && n >= 3) {
-      const uint32_t b0 = __ldg(p.text + lo), b1 = __ldg(p.text + lo + 1), b2 = __ldg(p.text + lo + 2);
-      if (b0 == 0xEF && b1 == 0xBB && b2 == 0xBF) lo += 3;
+    // parameter validation (blingfiretokdll.cpp:1121).  From here on offsets are relative to the aligned word the
+    // document starts in: the document is the bytes [a, uend) of the words tw[0..].
+    bool run = n64 > 0 && n64 <= 1000000000;
+    const uint32_t* tw = text32 + (lo >> 2);
+    int a = (int)(lo & 3);
+    const int uend = a + (int)(run ? n64 : 0);
+    if (run && n64 >= 3) {                 // the BOM (FAUtf8Utils.cpp:247-252)
+      const uint32_t f0 = __ldg(tw), f1 = a + 3 > 4 ? __ldg(tw + 1) : 0u;
+      const uint32_t b = (uint32_t)((((uint64_t)f1 << 32) | f0) >> (8 * a)) & 0xFFFFFFu;
+      if (b == 0xBFBBEFu) a += 3;
     }
-    run = run && lo < hi;
-    const int64_t lo0 = lo;
+    run = run && a < uend;
 
     // Documents that may not fit one window are validated up front, because ids are
     // emitted window by window and an invalid byte anywhere must yield 0 ids.
-    // a document of up to kWin-3 bytes always fits one window (its code points <= its bytes; the
-    // first decode block may start up to 3 bytes before the document)
-    const bool multi = run && (hi - lo0) > (kWin - 4);
+    // a document of up to kWin-3 bytes always fits one window (its code points <= its bytes)
+    const bool multi = run && (uend - a) > (kWin - 4);
     if (multi) {
       unsigned bad = 0, sumlen = 0;
-      for (int64_t bpos = lo0; bpos < hi;) {
-        const int64_t bs = bpos & ~(int64_t)3;
-        const int64_t pos0 = bs + lane * 4;
-        const uint32_t w0 = pos0 < padded_bytes ? __ldg(text32 + (pos0 >> 2)) : 0u;
-        const uint32_t w1 = pos0 + 4 < padded_bytes ? __ldg(text32 + (pos0 >> 2) + 1) : 0u;
-        const LaneDecode dcd = decode_lane(w0, w1, pos0, bpos, hi);
+      for (int ub = 0; ub < uend; ub += kBlockBytes) {
+        const int u0 = ub + lane * 4;
+        const uint32_t w0 = u0 < uend ? __ldg(tw + (u0 >> 2)) : 0u;
+        const uint32_t w1 = u0 + 4 < uend ? __ldg(tw + (u0 >> 2) + 1) : 0u;
+        const LaneDecode dcd = decode_lane(w0, w1, u0, a, uend);
         bad |= dcd.bad; sumlen += dcd.sumlen;
-        bpos = bs + kBlockBytes;
       }
-      bad = __any_sync(0xffffffffu, bad != 0);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sumlen += __shfl_xor_sync(0xffffffffu, sumlen, o);
-      if (bad || (int64_t)sumlen != hi - lo0) run = false;
+      if (__any_sync(0xffffffffu, bad != 0) || (int)__reduce_add_sync(0xffffffffu, sumlen) != uend - a) run = false;
     }
 
     if (run) {
-      // the window starts (lo0 & 3) entries into its arrays: a lane's 4 bytes of ASCII text then land on a
+      // the window starts (a & 3) entries into its arrays: a lane's 4 bytes of ASCII text then land on a
       // 4-entry boundary, as long as everything before them was ASCII too
-      const int pad = (int)(lo0 & 3);
+      const int pad = a & 3;
       w.ids_at = reinterpret_cast<int32_t*>(wbase) + pad;
       w.cls = reinterpret_cast<uint16_t*>(wbase + kOffCls) + pad;
       w.meta = wbase + kOffMeta + pad;
-      int m = 0, out = 0;
-      int64_t bpos = lo0;
+      int m = 0, out = 0, ub = 0;
       bool first = true, ok = true;
       unsigned sumlen = 0;          // per lane: bytes covered by the sequences decoded here
       int ulen = 0;                 // uniform: bytes of the all-ASCII blocks
       int32_t* row = p.ids + doc * (int64_t)p.max_ids;
       for (;;) {
-        // ---- fill the window: decode, validate, classify ----
+        // ---- fill the window: decode, validate, classify, and list the events ----
         unsigned bad = 0;
-        while (bpos < hi) {
-          const int64_t bs = bpos & ~(int64_t)3;
-          // the block [bpos, min(bs+128, hi)) yields at most that many code points
-          const int64_t blk_end = bs + kBlockBytes < hi ? bs + kBlockBytes : hi;
-          if (m + (int)(blk_end - bpos) > kWin) break;
-          const int64_t pos0 = bs + lane * 4;
-          const uint32_t w0 = pos0 < padded_bytes ? __ldg(text32 + (pos0 >> 2)) : 0u;
-          const int vfirst = (int)(bpos - pos0), vlast = (int)(blk_end - pos0);   // this lane's bytes [vfirst, vlast) belong to the block
-          uint32_t vmask = vlast >= 4 ? 0xFFFFFFFFu : (vlast <= 0 ? 0u : (1u << (8 * vlast)) - 1u);
-          if (vfirst > 0) vmask &= ~((1u << (8 * vfirst)) - 1u);
+        unsigned prev_tc = 0;
+        w.nev = 0;
+        if (m > 0) {                // the tail kept from the previous window
+          __syncwarp();
+          gen_events(w, top, 0, m, lane);
+          prev_tc = w.meta[m - 1];
+        }
+        while (ub < uend) {
+          const int blo = ub > a ? ub : a, bhi = ub + kBlockBytes < uend ? ub + kBlockBytes : uend;
+          const int nvalid = bhi - blo;        // the block yields at most that many code points
+          if (m + nvalid > kWin) break;
+          const int u0 = ub + lane * 4;
+          const bool full = ub >= a && ub + kBlockBytes <= uend;
+          const uint32_t w0 = (full || (u0 < uend && u0 + 4 > a)) ? __ldg(tw + (u0 >> 2)) : 0u;
+          uint32_t vmask = 0xFFFFFFFFu;        // this lane's bytes that belong to the document
+          if (!full) {
+            const int vfirst = a - u0, vlast = uend - u0;
+            vmask = vlast >= 4 ? 0xFFFFFFFFu : (vlast <= 0 ? 0u : (1u << (8 * vlast)) - 1u);
+            if (vfirst > 0) vmask = vfirst >= 4 ? 0u : (vmask & ~((1u << (8 * vfirst)) - 1u));
+          }
           if (!__any_sync(0xffffffffu, (w0 & 0x80808080u & vmask) != 0)) {
-            // all ASCII: position = byte offset, classes from the shared-memory table
-            const int idx = m + (int)(pos0 - bpos);
+            // all ASCII: position = byte offset; classes from the shared-memory table; events in registers
+            const int p0 = m + (u0 - blo);     // window position of this lane's first byte
             const uint32_t x0 = top.ascii_clsx[w0 & 0x7F], x1 = top.ascii_clsx[(w0 >> 8) & 0x7F];
             const uint32_t x2 = top.ascii_clsx[(w0 >> 16) & 0x7F], x3 = top.ascii_clsx[(w0 >> 24) & 0x7F];
-            if (vmask == 0xFFFFFFFFu && ((pad + idx) & 3) == 0) {
-              *reinterpret_cast<uint2*>(w.cls + idx) = make_uint2(__byte_perm(x0, x1, 0x5410), __byte_perm(x2, x3, 0x5410));
-              *reinterpret_cast<uint32_t*>(w.meta + idx) = __byte_perm(__byte_perm(x0, x1, 0x0062), __byte_perm(x2, x3, 0x0062), 0x5410);
-              *reinterpret_cast<int4*>(w.ids_at + idx) = make_int4(kNoPiece, kNoPiece, kNoPiece, kNoPiece);
-            } else {
-              if (vmask & 0xFFu) { w.cls[idx] = (uint16_t)x0; w.meta[idx] = (uint8_t)(x0 >> 16); w.ids_at[idx] = kNoPiece; }
-              if (vmask & 0xFF00u) { w.cls[idx + 1] = (uint16_t)x1; w.meta[idx + 1] = (uint8_t)(x1 >> 16); w.ids_at[idx + 1] = kNoPiece; }
-              if (vmask & 0xFF0000u) { w.cls[idx + 2] = (uint16_t)x2; w.meta[idx + 2] = (uint8_t)(x2 >> 16); w.ids_at[idx + 2] = kNoPiece; }
-              if (vmask & 0xFF000000u) { w.cls[idx + 3] = (uint16_t)x3; w.meta[idx + 3] = (uint8_t)(x3 >> 16); w.ids_at[idx + 3] = kNoPiece; }
+            const unsigned t0 = x0 >> 16, t1 = x1 >> 16, t2 = x2 >> 16, t3 = x3 >> 16;
+            unsigned tp = __shfl_up_sync(0xffffffffu, t3, 1);
+            if (lane == 0) tp = prev_tc;
+            unsigned s0 = top.sync_start[(tp << sh) | t0], s1 = top.sync_start[(t0 << sh) | t1];
+            unsigned s2 = top.sync_start[(t1 << sh) | t2], s3 = top.sync_start[(t2 << sh) | t3];
+            if (m == 0) {                      // the first position of a window is a chunk start
+              const int k = blo - u0;
+              if (k == 0) s0 = kSyncStart; else if (k == 1) s1 = kSyncStart; else if (k == 2) s2 = kSyncStart; else if (k == 3) s3 = kSyncStart;
             }
-            m += (int)(blk_end - bpos);
-            ulen += (int)(blk_end - bpos);
+            if (full && ((pad + m) & 3) == 0) {
+              *reinterpret_cast<uint2*>(w.cls + p0) = make_uint2(__byte_perm(x0, x1, 0x5410), __byte_perm(x2, x3, 0x5410));
+              *reinterpret_cast<uint32_t*>(w.meta + p0) = __byte_perm(__byte_perm(x0, x1, 0x0062), __byte_perm(x2, x3, 0x0062), 0x5410);
+              *reinterpret_cast<int4*>(w.ids_at + p0) = make_int4(kNoPiece, kNoPiece, kNoPiece, kNoPiece);
+            } else if (full) {
+              w.cls[p0] = (uint16_t)x0; w.cls[p0 + 1] = (uint16_t)x1; w.cls[p0 + 2] = (uint16_t)x2; w.cls[p0 + 3] = (uint16_t)x3;
+              w.meta[p0] = (uint8_t)t0; w.meta[p0 + 1] = (uint8_t)t1; w.meta[p0 + 2] = (uint8_t)t2; w.meta[p0 + 3] = (uint8_t)t3;
+              w.ids_at[p0] = kNoPiece; w.ids_at[p0 + 1] = kNoPiece; w.ids_at[p0 + 2] = kNoPiece; w.ids_at[p0 + 3] = kNoPiece;
+            } else {
+              if (vmask & 0xFFu) { w.cls[p0] = (uint16_t)x0; w.meta[p0] = (uint8_t)t0; w.ids_at[p0] = kNoPiece; } else s0 = 0;
+              if (vmask & 0xFF00u) { w.cls[p0 + 1] = (uint16_t)x1; w.meta[p0 + 1] = (uint8_t)t1; w.ids_at[p0 + 1] = kNoPiece; } else s1 = 0;
+              if (vmask & 0xFF0000u) { w.cls[p0 + 2] = (uint16_t)x2; w.meta[p0 + 2] = (uint8_t)t2; w.ids_at[p0 + 2] = kNoPiece; } else s2 = 0;
+              if (vmask & 0xFF000000u) { w.cls[p0 + 3] = (uint16_t)x3; w.meta[p0 + 3] = (uint8_t)t3; w.ids_at[p0 + 3] = kNoPiece; } else s3 = 0;
+            }
+            const unsigned sx = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+            const int cnt = __popc((sx | (sx >> 1)) & 0x01010101u);
+            const int incl = warp_incl_scan(cnt, lane);
+            int ei = w.nev + incl - cnt;
+            if (s0) w.ev[ei++] = (uint16_t)((unsigned)p0 | ((s0 & kSyncStart) << 15));
+            if (s1) w.ev[ei++] = (uint16_t)((unsigned)(p0 + 1) | ((s1 & kSyncStart) << 15));
+            if (s2) w.ev[ei++] = (uint16_t)((unsigned)(p0 + 2) | ((s2 & kSyncStart) << 15));
+            if (s3) w.ev[ei++] = (uint16_t)((unsigned)(p0 + 3) | ((s3 & kSyncStart) << 15));
+            w.nev += __shfl_sync(0xffffffffu, incl, 31);
+            prev_tc = __shfl_sync(0xffffffffu, t3, 31);   // (a block that ends before its lane 31 is the document's last)
+            m += nvalid;
+            ulen += nvalid;
           } else {
-            const uint32_t w1 = pos0 + 4 < padded_bytes ? __ldg(text32 + (pos0 >> 2) + 1) : 0u;
-            const LaneDecode dcd = decode_lane(w0, w1, pos0, bpos, hi);
+            const uint32_t w1 = u0 + 4 < uend ? __ldg(tw + (u0 >> 2) + 1) : 0u;
+            const LaneDecode dcd = decode_lane(w0, w1, u0, blo, uend);
             bad |= dcd.bad; sumlen += dcd.sumlen;
             const int cnt = __popc(dcd.start_mask);
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const int v = __shfl_up_sync(0xffffffffu, incl, o);
-              if (lane >= o) incl += v;
-            }
+            const int incl = warp_incl_scan(cnt, lane);
             int idx = m + incl - cnt;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -388,69 +457,53 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
                 ++idx;
               }
             }
-            m += __shfl_sync(0xffffffffu, incl, 31);
+            const int m1 = m + __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            gen_events(w, top, m, m1, lane);
+            if (m1 > 0) prev_tc = w.meta[m1 - 1];
+            m = m1;
           }
-          bpos = bs + kBlockBytes;
+          ub += kBlockBytes;
         }
-        const bool at_end = bpos >= hi;
+        const bool at_end = ub >= uend;
         if (!multi) {
           // single-window document: validity is known only now, before anything is emitted
-          unsigned tot = sumlen;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-          if (__any_sync(0xffffffffu, bad != 0) || (at_end && (int64_t)tot + ulen != hi - lo0)) { ok = false; break; }
+          if (__any_sync(0xffffffffu, bad != 0) || (at_end && (int)__reduce_add_sync(0xffffffffu, sumlen) + ulen != uend - a)) { ok = false; break; }
         }
         if (m == 0) break;
-        __syncwarp();
-
-        // ---- events: positions where a chunk may start (sync points) or the top-level class changes ----
-        const int limit = at_end ? m : m - max_tok;
-        w.nev = w.evh = w.nfast = w.fh = w.nslow = w.sh = 0;
-        w.carry = 0;
-        for (int p0 = 0; p0 < m; p0 += 32) {
-          const int q = p0 + lane;
-          bool ev = false;
-          unsigned entry = 0;
-          if (q < m) {
-            const unsigned tc = w.meta[q];
-            const unsigned tp = q > 0 ? (unsigned)w.meta[q - 1] : tc;
-            const unsigned sv = q == 0 ? (unsigned)kSyncStart : (unsigned)top.sync_start[(tp << top.sync_shift) | tc];
-            ev = sv != 0;
-            entry = (unsigned)q | ((sv & kSyncStart) ? 0x8000u : 0u);
-          }
-          const unsigned bal = __ballot_sync(0xffffffffu, ev);
-          if (ev) w.evq[(w.evh + w.nev + __popc(bal & lanemask_lt())) & (kEvRing - 1)] = (uint16_t)entry;
-          w.nev += __popc(bal);
-          __syncwarp();
-          if (w.nev >= 34) {         // 32 events with their successors
-            classify_round<TE>(w, top, words, 32, lane, m, at_end, limit, first);
-            drain_rounds<TE>(w, top, g, words, lane, m, at_end, limit, first, p.unk_id, false);
-          }
-        }
         // the end of the window closes the last chunk (twice: every event looks at two successors)
-        if (lane < 2) w.evq[(w.evh + w.nev + lane) & (kEvRing - 1)] = (uint16_t)((unsigned)m | 0x8000u);
-        w.nev += 2;
-        __syncwarp();
-        while (w.nev >= 3) {
-          classify_round<TE>(w, top, words, w.nev - 2 < 32 ? w.nev - 2 : 32, lane, m, at_end, limit, first);
-          drain_rounds<TE>(w, top, g, words, lane, m, at_end, limit, first, p.unk_id, w.nev < 3);
-        }
-        int carry = at_end ? m : w.carry;
-        if (!at_end) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) carry = max(carry, __shfl_xor_sync(0xffffffffu, carry, o));
-        }
+        if (lane < 2) w.ev[w.nev + lane] = (uint16_t)((unsigned)m | 0x8000u);
         __syncwarp();
 
-        // ---- ordered compaction of the ids of positions [0, carry) ----
-        for (int p0 = 0; p0 < carry; p0 += 32) {
-          const int q = p0 + lane;
-          const int32_t id = q < carry ? w.ids_at[q] : kNoPiece;
-          const bool f = id != kNoPiece;
-          const unsigned bal = __ballot_sync(0xffffffffu, f);
-          const int rank = out + __popc(bal & lanemask_lt());
-          if (f && rank < p.max_ids) row[rank] = id;
-          out += __popc(bal);
+        // ---- events -> chunks -> ids ----
+        const int limit = at_end ? m : m - max_tok;
+        w.nfast = w.fh = w.nslow = w.sh = 0;
+        w.carry = 0;
+        for (int i0 = 0; i0 < w.nev; i0 += 32) {
+          const int cnt = w.nev - i0 < 32 ? w.nev - i0 : 32;
+          classify_round(w, top, words, i0, cnt, lane, m, at_end, limit, first);
+          drain_rounds<TE>(w, top, g, words, lane, m, at_end, limit, first, p.unk_id, i0 + 32 >= w.nev);
+        }
+        int carry = at_end ? m : __reduce_max_sync(0xffffffffu, w.carry);
+        __syncwarp();
+
+        // ---- ordered compaction of the ids of positions [0, carry), four (array-aligned) entries per lane ----
+        const int32_t* ids_base = w.ids_at - pad;
+        for (int pp = 0; pp < pad + carry; pp += 128) {
+          const int ph = pp + 4 * lane;
+          int4 v = make_int4(kNoPiece, kNoPiece, kNoPiece, kNoPiece);
+          if (ph < pad + carry) v = *reinterpret_cast<const int4*>(ids_base + ph);
+          const int q = ph - pad;                // window position of v.x
+          const bool f0 = v.x != kNoPiece && q >= 0 && q < carry, f1 = v.y != kNoPiece && q + 1 >= 0 && q + 1 < carry;
+          const bool f2 = v.z != kNoPiece && q + 2 >= 0 && q + 2 < carry, f3 = v.w != kNoPiece && q + 3 < carry;
+          const int cnt = (int)f0 + (int)f1 + (int)f2 + (int)f3;
+          const int incl = warp_incl_scan(cnt, lane);
+          const int r0 = out + incl - cnt, r1 = r0 + (int)f0, r2 = r1 + (int)f1, r3 = r2 + (int)f2;
+          if (f0 && r0 < p.max_ids) row[r0] = v.x;
+          if (f1 && r1 < p.max_ids) row[r1] = v.y;
+          if (f2 && r2 < p.max_ids) row[r2] = v.z;
+          if (f3 && r3 < p.max_ids) row[r3] = v.w;
+          out += __shfl_sync(0xffffffffu, incl, 31);
         }
         if (at_end) break;
 

@@ -129,25 +129,29 @@ uint64_t splitmix(uint64_t* s) {
 }
 
 bool cuckoo_build(const std::vector<WpWordSlot>& keys, WpWords* W, std::vector<WpWordSlot>* slots) {
-  uint32_t log2 = 4;
-  while (((size_t)1 << log2) * 4 < keys.size() * 5 + 16) ++log2;     // each half >= 1.25 x the keys
+  // each half holds >= 16 x the vocabulary's words: the rest of the slots take the words learned at run time, and a new
+  // word finds one of its two slots free as long as the table stays sparse (64 MB for bert_base_tok; what is touched
+  // is a sector or two per distinct word of the corpus)
+  uint32_t log2 = 12;
+  while (((size_t)1 << log2) < keys.size() * 16 + 16) ++log2;
   uint64_t seed = 0x5EEDB200ull;
   for (; log2 <= 26; ++log2) {
     const uint32_t S = 1u << log2;
     for (int attempt = 0; attempt < 16; ++attempt) {
-      for (int i = 0; i < 8; ++i) W->mul[i] = (uint32_t)splitmix(&seed) | 1u;
+      for (int i = 0; i < 9; ++i) W->mul[i] = (uint32_t)splitmix(&seed) | 1u;
       W->log2_size = log2;
-      WpWordSlot empty{};
-      empty.id = kNoPiece;
-      slots->assign((size_t)2 * S, empty);
+      slots->assign((size_t)2 * S, WpWordSlot{});
       bool ok = true;
       for (const WpWordSlot& k : keys) {
         WpWordSlot cur = k;
         int side = 0, kick = 0;
         for (; kick < 2000; ++kick) {
-          const uint32_t idx = side == 0 ? wp_key_hash(cur.kw, W->mul, log2) : S + wp_key_hash(cur.kw, W->mul + 4, log2);
+          uint32_t k8[8];
+          for (int i = 0; i < 4; ++i) { k8[i] = cur.kw[i]; k8[4 + i] = cur.kw_hi[i]; }
+          const uint32_t h = wp_key_hash(k8, W->mul, true);
+          const uint32_t idx = side == 0 ? wp_slot1(*W, h) : wp_slot2(*W, h);
           WpWordSlot& dst = (*slots)[idx];
-          if (dst.id == kNoPiece && (dst.kw[0] | dst.kw[1]) == 0) { dst = cur; break; }
+          if (dst.meta == 0) { dst = cur; break; }
           std::swap(cur, dst);
           side ^= 1;
         }
@@ -172,10 +176,10 @@ void build_words(const LexerTables& T, const TE* trans, const TopGroups& G, cons
   g.NC1 = (uint32_t)T.NC + 1; g.first_final = T.first_final; g.cls_caret = T.cls_caret; g.cls_dollar = T.cls_dollar;
   g.max_token_length = T.max_token_length;
 
-  std::map<std::array<uint32_t, 4>, int32_t> found;
+  std::map<std::array<uint32_t, 8>, int32_t> found;
   const int max_len = (int)W.max_len;
   for (int grp = 2; grp < (int)G.members.size(); ++grp) {
-    if (!(kind_of_group[grp] >> (kKindLenShift + 1))) continue;        // no length bit
+    if (!(kind_of_group[grp] & (kKindWordRun | kKindWordOne))) continue;
     const uint32_t root = F.top_fn_root[G.state_of_group[grp]], caret = F.top_fn_caret[G.state_of_group[grp]];
     const uint32_t entries[2] = {caret, root};
     for (uint32_t entry : entries) {
@@ -195,19 +199,19 @@ void build_words(const LexerTables& T, const TE* trans, const TopGroups& G, cons
         if (G.group_of_tc[F.tc_of_class[c]] != grp || d == T.dead) continue;
         const int depth = (int)st.size();                   // length of the sequence with c appended
         seq[depth - 1] = (uint16_t)c;
-        if (((kind_of_group[grp] >> (kKindLenShift + depth)) & 1u) &&
+        if (((kind_of_group[grp] & kKindWordRun) || depth == 1) &&
             (T.is_final(d) || T.is_final(T.next(d, T.cls_dollar)))) {
           for (int i = 0; i < depth; ++i) ids[i] = kNoPiece;
           const int n = wp_word<TE>(g, seq, 0, depth - 1, root, caret, ids);
           bool single = n == 1 && ids[0] != kNoPiece;
           for (int i = 1; i < depth && single; ++i) single = ids[i] == kNoPiece;
           if (single) {
-            std::array<uint32_t, 4> kw;
+            std::array<uint32_t, 8> kw;
             wp_pack_key_any(W.cpw, seq, depth, depth, W.cb, kw.data());
             found[kw] = ids[0];
           }
         }
-        if (depth < max_len) st.push_back(Frame{d, T.arc_begin[d]});
+        if (depth < max_len && (kind_of_group[grp] & kKindWordRun)) st.push_back(Frame{d, T.arc_begin[d]});
       }
     }
   }
@@ -215,16 +219,15 @@ void build_words(const LexerTables& T, const TE* trans, const TopGroups& G, cons
   keys.reserve(found.size());
   for (const auto& kv : found) {
     WpWordSlot s{};
-    for (int i = 0; i < 4; ++i) s.kw[i] = kv.first[i];
-    s.id = kv.second;
+    for (int i = 0; i < 4; ++i) { s.kw[i] = kv.first[i]; s.kw_hi[i] = kv.first[4 + i]; }
+    s.id[0] = kv.second;
+    s.meta = kSlotValid | 1u;
     keys.push_back(s);
   }
   out->word_count = (int64_t)keys.size();
   if (!cuckoo_build(keys, &W, &out->word_slots)) {   // cannot happen below 2^26 slots; serve without the table
     W.max_len = 0; W.log2_size = 4;
-    WpWordSlot empty{};
-    empty.id = kNoPiece;
-    out->word_slots.assign(32, empty);
+    out->word_slots.assign(32, WpWordSlot{});
     out->word_count = 0;
   }
 }
@@ -244,7 +247,7 @@ void build_wp_blob(const LexerTables& T, WpBlob* out) {
   W.cb = 1;
   while ((1u << W.cb) < (uint32_t)T.NC + 1) ++W.cb;
   W.cpw = std::max(1u, std::min(3u, 30u / W.cb));
-  W.max_len = (uint32_t)std::max(0, std::min({kMaxFastLen, (int)(4 * W.cpw), T.max_token_length - 1}));
+  W.max_len = (uint32_t)std::max(0, std::min({kMaxFastLen, (int)(8 * W.cpw), T.max_token_length - 1}));
   const TopGroups G = make_groups(F);
   std::vector<uint32_t> kind_of_group(G.members.size(), 0);
   const uint8_t c0 = F.ttop[F.tc_caret];                      // delta(initial, ^)
@@ -255,8 +258,7 @@ void build_wp_blob(const LexerTables& T, WpBlob* out) {
     const int s = G.state_of_group[grp];
     if (s >= 0 && F.top_tag[s] == 1 && F.top_fn_root[s] != kNoState) {
       // one WORD token over the whole run, final state s whatever the mix of the group's classes
-      const int max_run = G.closed[grp] ? (int)W.max_len : std::min(1, (int)W.max_len);
-      for (int len = 1; len <= max_run; ++len) k |= 1u << (kKindLenShift + len);
+      k |= G.closed[grp] ? kKindWordRun : kKindWordOne;
       // at the start of the document the walk begins in delta(initial, ^) (FALexTools_t.h:244-252): same outcome iff that
       // state does not exist, or takes every class of the group to s as well
       bool caret_ok = true;
@@ -286,7 +288,7 @@ void build_wp_blob(const LexerTables& T, WpBlob* out) {
           for (const TopTok& x : a) if (F.top_tag[x.fq] == 1) ++words;
           bool good = true;
           if (k & kKindInert) good = words == 0;
-          else if ((k >> (kKindLenShift + len)) & 1u) {
+          else if ((k & kKindWordRun) || (len == 1 && (k & kKindWordOne))) {
             const int s = G.state_of_group[G.group_of_tc[t]];
             good = words == 1;
             for (const TopTok& x : a)
@@ -302,7 +304,7 @@ void build_wp_blob(const LexerTables& T, WpBlob* out) {
   if (T.wide_states) build_words<uint32_t>(T, T.trans32.data(), G, kind_of_group, out);
   else build_words<uint16_t>(T, T.trans16.data(), G, kind_of_group, out);
   if (W.max_len == 0)
-    for (uint32_t& k : kind_of_group) k &= (1u << kKindLenShift) - 1;
+    for (uint32_t& k : kind_of_group) k &= ~(kKindWordRun | kKindWordOne);
   std::vector<uint32_t> kind((size_t)F.NT, 0);
   for (int t = 0; t < F.NT; ++t) kind[t] = kind_of_group[G.group_of_tc[t]];
 
@@ -318,6 +320,8 @@ void build_wp_blob(const LexerTables& T, WpBlob* out) {
   while ((1 << L.sync_shift) < F.NT) ++L.sync_shift;
   L.off_sync = place(1u << (2 * L.sync_shift), 16);
   L.off_kind = place((uint32_t)F.NT * 4, 16);
+  L.off_fn_root = place((uint32_t)F.NT * 4, 16);
+  L.off_fn_caret = place((uint32_t)F.NT * 4, 16);
   L.total_bytes = (off + 15) / 16 * 16;
 
   out->bytes.assign(L.total_bytes, 0);
@@ -337,6 +341,11 @@ void build_wp_blob(const LexerTables& T, WpBlob* out) {
   std::memcpy(bp + L.off_root, F.top_fn_root.data(), (size_t)F.K * 4);
   std::memcpy(bp + L.off_caret, F.top_fn_caret.data(), (size_t)F.K * 4);
   std::memcpy(bp + L.off_kind, kind.data(), (size_t)F.NT * 4);
+  for (int t = 0; t < F.NT; ++t) {
+    const int st = G.state_of_group[G.group_of_tc[t]];
+    reinterpret_cast<uint32_t*>(bp + L.off_fn_root)[t] = st >= 0 ? F.top_fn_root[st] : kNoState;
+    reinterpret_cast<uint32_t*>(bp + L.off_fn_caret)[t] = st >= 0 ? F.top_fn_caret[st] : kNoState;
+  }
 }
 
 }  // namespace bfb200

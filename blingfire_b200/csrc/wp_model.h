@@ -16,7 +16,7 @@ namespace bfb200 {
 // Byte offsets inside the blob.  Plain data: passed to the kernel by value.
 struct WpBlobLayout {
   uint32_t total_bytes;       // multiple of 16 (cp.async.bulk granularity)
-  uint32_t off_ascii, off_ttop, off_tag, off_root, off_caret, off_sync, off_kind;
+  uint32_t off_ascii, off_ttop, off_tag, off_root, off_caret, off_sync, off_kind, off_fn_root, off_fn_caret;
   int32_t K, NT;
   uint8_t tc_caret, tc_dollar, tc_none;
   uint8_t sync_shift;         // sync_start is [1 << sync_shift][1 << sync_shift]
@@ -45,6 +45,8 @@ BF_HD WpTop make_wp_top(const uint8_t* base, const WpBlobLayout& L) {
   t.top_fn_caret = reinterpret_cast<const uint32_t*>(base + L.off_caret);
   t.sync_start = base + L.off_sync; t.sync_shift = L.sync_shift;
   t.kind_of_tc = reinterpret_cast<const uint32_t*>(base + L.off_kind);
+  t.fn_root_of_tc = reinterpret_cast<const uint32_t*>(base + L.off_fn_root);
+  t.fn_caret_of_tc = reinterpret_cast<const uint32_t*>(base + L.off_fn_caret);
   t.K = L.K; t.NT = L.NT;
   t.tc_caret = L.tc_caret; t.tc_dollar = L.tc_dollar; t.tc_none = L.tc_none;
   return t;

@@ -34,6 +34,7 @@ struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 inline int2 make_int2(int a, int b) { return int2{a, b}; }
 inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
+inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
 inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, d}; }
 struct dim3s { unsigned x = 0, y = 0, z = 0; };
 
@@ -87,6 +88,7 @@ inline unsigned __ballot_sync(unsigned, bool p) { const uint64_t* b = simt::exch
 inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
 inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, p) == 0xffffffffu; }
 inline int __reduce_max_sync(unsigned, int v) { const uint64_t* b = simt::exchange(simt::pack(v)); int r = simt::unpack<int>(b[0]); for (int i = 1; i < 32; ++i) r = std::max(r, simt::unpack<int>(b[i])); return r; }
+inline unsigned __reduce_add_sync(unsigned, unsigned v) { const uint64_t* b = simt::exchange(simt::pack(v)); unsigned r = 0; for (int i = 0; i < 32; ++i) r += simt::unpack<unsigned>(b[i]); return r; }
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::exchange(0); }
 inline void __syncthreads() { simt::tl.cta->arrive_and_wait(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }

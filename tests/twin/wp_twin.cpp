@@ -113,7 +113,8 @@ int twin_text_to_ids(void* h, const char* s, int n, int32_t* ids, int max_ids, i
   return twin_text_to_ids_ex(h, s, n, ids, max_ids, unk, window, 1, nullptr);
 }
 // use_memo = 0: every chunk through the lexer loops (the memo must not change a single id);
-// stats[0..2] += words found in the table, words the table did not hold, chunks that emit nothing
+// stats[0..3] += single-piece words found in the table, words the table did not hold, chunks that emit nothing,
+// words found with another number of pieces (learned at run time)
 int twin_text_to_ids_ex(void* h, const char* s, int n, int32_t* ids, int max_ids, int unk, int window, int use_memo, int64_t* stats) {
   Twin* t = (Twin*)h;
   if (!twin_fast_ok(h)) return -2;
@@ -162,6 +163,7 @@ int twin_text_to_ids_ex(void* h, const char* s, int n, int32_t* ids, int max_ids
   if (T.wide_states) fill_g(g32, T.trans32.data()); else fill_g(g16, T.trans16.data());
   WpWords words = t->blob.words;
   words.slots = t->blob.word_slots.data();
+  const bool learn = use_memo == 1;      // use_memo 2: the table as built at load time, nothing added
   if (!use_memo) words.max_len = 0;
 
   int m = 0, bpos = lo, out = 0;
@@ -216,6 +218,7 @@ int twin_text_to_ids_ex(void* h, const char* s, int n, int32_t* ids, int max_ids
         }
       }
       if (!shaped || (!at_end && e > limit)) {
+        if (stats) ++stats[!shaped ? 4 : 5];
         const int c0 = carry;
         if (loops(s, e)) return -3;
         // exactness guard of the sync-point argument: a chunk must end exactly on the next start
@@ -223,14 +226,27 @@ int twin_text_to_ids_ex(void* h, const char* s, int n, int32_t* ids, int max_ids
         continue;
       }
       const int r = wp_classify_run(top.kind_of_tc[tcs[s]], we - s, words.max_len, first && s == 0, at_end && we == m);
-      if (r == 0) { if (loops(s, e)) return -3; continue; }
+      if (r == 0) { if (stats) ++stats[(we - s) > (int)words.max_len && (top.kind_of_tc[tcs[s]] & kKindWordRun) ? 6 : 7]; if (loops(s, e)) return -3; continue; }
       if (e > carry) carry = e;
       if (r == 2) {
-        uint32_t kw[4];
+        uint32_t kw[8];
+        const bool wide = we - s > (int)(4 * words.cpw);
         wp_pack_key_any(words.cpw, cls.data() + s, we - s, we - s, words.cb, kw);
-        const int32_t id = wp_words_find(words, kw);
-        if (id != kNoPiece) { ids_at[s] = id; if (stats) ++stats[0]; }
-        else { if (stats) ++stats[1]; if (loops(s, we)) return -3; }
+        const WpWordHit hit = wp_words_find(words, kw, wide);
+        if (hit.meta) { wp_apply_hit(hit, s, unk, ids_at.data()); if (stats) ++stats[(hit.meta & 7u) == 1 ? 0 : 3]; }
+        else {
+          // the kernel's slow_round for a word run: the function sub-grammar alone, then into the table
+          if (stats) ++stats[1];
+          const unsigned tc = tcs[s];
+          int tiled;
+          if (T.wide_states) tiled = wp_word<uint32_t>(g32, cls.data(), s, we - 1, top.fn_root_of_tc[tc], top.fn_caret_of_tc[tc], ids_at.data());
+          else tiled = wp_word<uint16_t>(g16, cls.data(), s, we - 1, top.fn_root_of_tc[tc], top.fn_caret_of_tc[tc], ids_at.data());
+          int n = 0, offs[kMaxLearnPieces];
+          int32_t pids[kMaxLearnPieces];
+          if (!tiled) { for (int p = s + 1; p < we; ++p) ids_at[p] = kNoPiece; ids_at[s] = unk; }
+          else for (int p = s; p < we; ++p) if (ids_at[p] != kNoPiece) { if (n < kMaxLearnPieces) { pids[n] = ids_at[p]; offs[n] = p - s; } ++n; }
+          if (learn && n <= kMaxLearnPieces) wp_words_insert(words, kw, wide, n, pids, offs);
+        }
       } else if (stats) ++stats[2];
     }
     for (int p = 0; p < carry && p < m; ++p)
