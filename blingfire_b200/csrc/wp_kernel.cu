@@ -171,38 +171,35 @@ __device__ __forceinline__ void gen_events(WarpWin& w, const WpTop& top, int pb,
 // the table, or needs the loops -- as does every chunk of another shape.
 __device__ __forceinline__ void classify_round(WarpWin& w, const WpTop& top, const WpWords& words, int i0, int cnt, int lane, int m,
                                                bool at_end, int limit, bool first) {
-  int action = 0;      // 1 = table, 2 = loops
-  int s = 0, we = 0, e = 0;
-  if (lane < cnt) {
-    const unsigned e0 = w.ev[i0 + lane], e1 = w.ev[i0 + lane + 1];
-    s = (int)(e0 & 0x7FFFu);
-    if (e0 & 0x8000u) {
-      bool shaped = true;
-      we = e = (int)(e1 & 0x7FFFu);
-      if (!(e1 & 0x8000u)) {
-        const unsigned e2 = w.ev[i0 + lane + 2];
-        e = (int)(e2 & 0x7FFFu);
-        shaped = (e2 & 0x8000u) && (top.kind_of_tc[w.meta[we]] & kKindDead);
-        if (!shaped) {
-          // some other mix of groups: find where the chunk really ends
-          int p = we + 1;
-          while (p < m && !(top.sync_start[((unsigned)w.meta[p - 1] << top.sync_shift) | (unsigned)w.meta[p]] & kSyncStart)) ++p;
-          e = p;
-        }
-      }
-      if (!shaped || (!at_end && e > limit)) {
-        action = 2;                                  // (a chunk that is not final in this window: the loops clip it)
-      } else {
-        const int r = wp_classify_run(top.kind_of_tc[w.meta[s]], we - s, words.max_len, first && s == 0, at_end && we == m);
-        if (r == 0) action = 2;
-        else { action = r == 2 ? 1 : 0; w.carry = max(w.carry, e); }
-      }
+  // straight-line on purpose: every lane reads three (clamped) events and two kinds, the decisions are selects
+  const int i = i0 + (lane < cnt ? lane : cnt - 1);
+  const unsigned e0 = w.ev[i], e1 = w.ev[i + 1], e2 = w.ev[i + 2];
+  const int s = (int)(e0 & 0x7FFFu), p1 = (int)(e1 & 0x7FFFu), p2 = (int)(e2 & 0x7FFFu);
+  const bool b0 = lane < cnt && (e0 & 0x8000u), b1 = (e1 & 0x8000u) != 0, b2 = (e2 & 0x8000u) != 0;
+  const uint32_t k0 = top.kind_of_tc[w.meta[s]];
+  const uint32_t k1 = top.kind_of_tc[w.meta[p1 < m ? p1 : m - 1]];
+  const bool shaped = b1 || (b2 && (k1 & kKindDead));      // run [s, p1) of one group, then nothing or positions that match nothing
+  const int we = p1;
+  int e = b1 ? p1 : p2;
+  if (__any_sync(0xffffffffu, b0 && !shaped)) {            // rare: some other mix of groups -- find where the chunk really ends
+    if (b0 && !shaped) {
+      int p = we + 1;
+      while (p < m && !(top.sync_start[((unsigned)w.meta[p - 1] << top.sync_shift) | (unsigned)w.meta[p]] & kSyncStart)) ++p;
+      e = p;
     }
   }
+  const int len = we - s;
+  const bool inert = (k0 & kKindInert) != 0;
+  const bool anchors_ok = !(first && s == 0 && !(k0 & kKindCaretOk)) && !(at_end && we == m && !(k0 & kKindDollarOk));
+  const bool word = len <= (int)words.max_len && ((k0 & kKindWordRun) || (len == 1 && (k0 & kKindWordOne)));
+  // (a chunk that is not final in this window goes to the loops, which clip it)
+  const bool memo = shaped && (at_end || e <= limit) && (inert || (anchors_ok && word));
+  const bool to_table = b0 && memo && !inert, to_loops = b0 && !memo;
+  if (b0 && memo) w.carry = max(w.carry, e);
   const unsigned lt = lanemask_lt();
-  const unsigned bf = __ballot_sync(0xffffffffu, action == 1), bs = __ballot_sync(0xffffffffu, action == 2);
-  if (action == 1) w.fastq[(w.fh + w.nfast + __popc(bf & lt)) & (kRing - 1)] = (uint32_t)s | ((uint32_t)(we - s) << 16);
-  if (action == 2) w.slowq[(w.sh + w.nslow + __popc(bs & lt)) & (kRing - 1)] = (uint32_t)s | ((uint32_t)e << 16);
+  const unsigned bf = __ballot_sync(0xffffffffu, to_table), bs = __ballot_sync(0xffffffffu, to_loops);
+  if (to_table) w.fastq[(w.fh + w.nfast + __popc(bf & lt)) & (kRing - 1)] = (uint32_t)s | ((uint32_t)len << 16);
+  if (to_loops) w.slowq[(w.sh + w.nslow + __popc(bs & lt)) & (kRing - 1)] = (uint32_t)s | ((uint32_t)e << 16);
   w.nfast += __popc(bf); w.nslow += __popc(bs);
   __syncwarp();
 }

@@ -144,6 +144,40 @@ def test_ragged_edge_and_invalid_documents(bf, oracle):
         check_batch(bf, oracle, "bert_base_tok.bin", docs, max_ids, 100)
 
 
+def test_learned_words_on_a_fresh_model(bf, oracle):
+    """The run-time side of the word table on the device: thousands of warps add the same words at once on a model that has
+    just been loaded; the following passes (same ids, then another UnkId and a small cap) find them in the table."""
+    name = "bert_base_tok.bin"
+    words = [b"unaffable", b"antidisestablishmentarianism", b"supercalifragilisticexpialidocious", b"qwrtzxqwrtzx", b"a" * 24,
+             b"a" * 25, b"b" * 13, "naïveté".encode(), b"electroencephalography", b"zzzzzzzzzzzzzzzzzzzzzzzz", b"hydroxychloroquine",
+             b"internationalization", b"1234567890123", b"tokenization's", b"pneumonoultramicroscopicsilicovolcanoconiosis"]
+    lines = read_lines("test.txt", drop_empty=False)[60000:90000]
+    docs = [b" ".join(words[i % len(words):] + words[:i % len(words)]) for i in range(20000)]
+    docs += [b" ".join(lines[i:i + 6]) for i in range(0, len(lines), 6)]
+    saved = _models.pop(name, None)
+    try:
+        _models[name] = bf.load_model(model_path(name))
+        for max_ids, unk in ((512, 100), (512, 100), (9, 4242)):
+            check_batch(bf, oracle, name, docs, max_ids, unk)
+        bf.free_model(_models.pop(name))
+    finally:
+        if saved is not None:
+            _models[name] = saved
+
+
+@pytest.mark.timeout(900)
+def test_wide_table_model_on_the_device(bf, oracle):
+    """bert_multi_cased: 232k states x 10 004 classes -- the 32-bit table entries (9.3 GB in HBM), 14-bit classes in the
+    word keys (two per key word), 119k-word vocabulary."""
+    name = "bert_multi_cased.bin"
+    lines = read_lines("test.multi.txt", drop_empty=False)[:30000]
+    docs = [b" ".join(lines[i:i + 3]) for i in range(0, len(lines), 3)]
+    docs += [b"", b"abc \xff def", "我爱北京".encode() * 200, b"a" * 700, "é".encode() * 700, b"[UNK] [CLS]x [unused1]"]
+    check_batch(bf, oracle, name, docs, 512, 100)
+    check_batch(bf, oracle, name, docs[:3000], 512, 100)
+    bf.free_model(_models.pop(name))
+
+
 def test_unaligned_offsets_and_unk_id(bf, oracle):
     """Documents starting at every byte alignment; a non-default UnkId."""
     docs = [b"x" * k + b" unaffable qwrtzx " + "naïve café".encode() for k in range(0, 9)] * 50

@@ -135,8 +135,8 @@ def wpsim():
     return L
 
 
-def check_wp(wpsim, name, docs, max_ids, unk=100, warps=4):
-    h = wpsim.wpsim_load(model_path(name).encode())
+def check_wp(wpsim, name, docs, max_ids, unk=100, warps=4, handle=None):
+    h = handle or wpsim.wpsim_load(model_path(name).encode())
     assert wpsim.wpsim_error(h) == b"", wpsim.wpsim_error(h)
     o = Oracle()
     ho = o.load(model_path(name))
@@ -152,7 +152,8 @@ def check_wp(wpsim, name, docs, max_ids, unk=100, warps=4):
         assert (ids[i, :n] == a[:n]).all(), (name, i, d[:60])
         assert (ids[i, n:] == -7).all(), "a row was written beyond its count"
     o.free(ho)
-    wpsim.wpsim_free(h)
+    if handle is None:
+        wpsim.wpsim_free(h)
 
 
 def wp_docs(seed, n):
@@ -183,6 +184,21 @@ def test_wp_kernel_source_matches_oracle(wpsim, name):
     docs = wp_docs(5, 320)
     check_wp(wpsim, name, docs, 512)
     check_wp(wpsim, name, docs[:120], 7, unk=7777)
+
+
+def test_wp_kernel_source_learned_words(wpsim):
+    """The run-time side of the word table: several warps add words concurrently (same words in different documents), a
+    second pass over the same model finds them, a third one with another UnkId and a small output cap does too."""
+    name = "bert_base_tok.bin"
+    words = [b"unaffable", b"antidisestablishmentarianism", b"supercalifragilisticexpialidocious", b"qwrtzxqwrtzx", b"a" * 24,
+             b"a" * 25, b"b" * 13, "naïveté".encode(), b"electroencephalography", b"zzzzzzzzzzzzzzzzzzzzzzzz", b"hydroxychloroquine",
+             b"internationalization", b"1234567890123", b"tokenization's"]
+    docs = [b" ".join(words[i:] + words[:i]) for i in range(len(words))] * 3 + wp_docs(21, 60)
+    h = wpsim.wpsim_load(model_path(name).encode())
+    check_wp(wpsim, name, docs, 512, warps=8, handle=h)
+    check_wp(wpsim, name, docs, 512, warps=3, handle=h)
+    check_wp(wpsim, name, docs, 9, unk=4242, warps=5, handle=h)
+    wpsim.wpsim_free(h)
 
 
 def test_wp_kernel_source_wide_table(wpsim):

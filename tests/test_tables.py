@@ -33,6 +33,8 @@ class Twin:
         L.twin_ptr.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.twin_text_to_ids.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int]
+        L.twin_text_to_ids_ex.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
 
     def load(self, name):
         h = self.lib.twin_load(model_path(name).encode())
@@ -42,6 +44,12 @@ class Twin:
     def arr(self, h, what, dtype, n):
         p = self.lib.twin_ptr(h, what)
         return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(n,))
+
+    def ids_ex(self, h, data, max_ids, unk, window, use_memo, stats=None):
+        out = np.full(max_ids, -7, np.int32)
+        n = self.lib.twin_text_to_ids_ex(h, data, len(data), out.ctypes.data, max_ids, unk, window, use_memo,
+                                         stats.ctypes.data if stats is not None else None)
+        return n, out
 
     def ids(self, h, data, max_ids, unk, window):
         out = np.full(max_ids, -7, np.int32)
@@ -195,4 +203,38 @@ def test_twin_fuzz(twin, oracle):
         n1, a = oracle.text_to_ids(ho, d, 300, 100)
         n2, b = twin.ids(h, d, 300, 100, rng.choice([340, 400, 640]))
         assert n1 == n2 and (a[:n1] == b[:n1]).all(), d[:80]
+    twin.lib.twin_free(h)
+
+
+MEMO_WORDS = [b"unaffable", b"antidisestablishmentarianism", b"supercalifragilisticexpialidocious", b"qwrtzxqwrtzx",
+              b"internationalization", b"a" * 24, b"a" * 25, b"b" * 12, b"b" * 13, "naïveté".encode(), b"electroencephalography",
+              b"x", b"zzzzzzzzzzzzzzzzzzzzzzzz", b"tokenization's", b"[unk]", b"[UNK]x", b"don't", b"www.example-site.com/path",
+              b"1234567890123", b"hydroxychloroquine", b"pneumonoultramicroscopicsilicovolcanoconiosis"]
+
+
+@pytest.mark.parametrize("name,corpus", [("bert_base_tok.bin", "test.txt"), ("bert_base_cased_tok.bin", "test.txt"),
+                                         ("bert_chinese.bin", "test.multi.txt")])
+def test_memo_never_changes_an_id(twin, name, corpus):
+    """The load-time memo (class groups, whole-word table) and the words learned at run time are abbreviations of the lexer
+    loops: with the memo off (0), with the table as built at load time (2) and with learning on (1, twice, so that the
+    second pass finds what the first one added) every document yields the same ids."""
+    h = twin.load(name)
+    assert twin.lib.twin_info(h, 13) > 1000 and twin.lib.twin_info(h, 15) >= 8      # vocabulary words in the table; key length
+    lines = read_lines(corpus, drop_empty=False)[:6000]
+    docs = [b" ".join(lines[i:i + 3]) for i in range(0, len(lines), 3)] + EDGE
+    docs += [b" ".join(MEMO_WORDS), b" ".join(reversed(MEMO_WORDS)), b"".join(MEMO_WORDS)] + MEMO_WORDS
+    want = [twin.ids_ex(h, d, 512, 100, 640, 0) for d in docs]
+    stats = [np.zeros(8, np.int64) for _ in range(3)]
+    for k, mode in enumerate((2, 1, 1)):
+        for d, (n0, a0) in zip(docs, want):
+            n, a = twin.ids_ex(h, d, 512, 100, 640, mode, stats[k])
+            assert n == n0 and (a[:max(n, 0)] == a0[:max(n, 0)]).all(), (mode, d[:80])
+    # the table serves most words; what it did not hold at load time it holds after one pass
+    assert stats[0][0] > 3 * stats[0][1] or name == "bert_chinese.bin"
+    assert stats[0][3] == 0 and stats[2][3] > 0 and stats[2][1] < stats[1][1]
+    # another UnkId: a learned "this word is one UnkId" entry does not remember the id
+    for d in docs[:300] + MEMO_WORDS:
+        n0, a0 = twin.ids_ex(h, d, 512, 7777, 640, 0)
+        n, a = twin.ids_ex(h, d, 512, 7777, 640, 1)
+        assert n == n0 and (a[:max(n, 0)] == a0[:max(n, 0)]).all(), d[:80]
     twin.lib.twin_free(h)
