@@ -92,8 +92,11 @@ struct PinBuf {
 };
 
 // per-slot working set of the host batch pipeline
-constexpr int kSlots = 4;    // chunks in flight in the host pipeline
-constexpr int kAhead = 2;    // chunks enqueued behind the one whose counts the host waits for
+constexpr int kMaxSlots = 8;
+// chunks in flight in the host pipeline / chunks enqueued behind the one whose counts the host waits for
+// (BLINGFIRE_B200_SLOTS / BLINGFIRE_B200_AHEAD override the defaults: tuning knobs)
+static const int kSlots = [] { const char* e = std::getenv("BLINGFIRE_B200_SLOTS"); const int v = e ? std::atoi(e) : 4; return v < 2 ? 2 : (v > kMaxSlots ? kMaxSlots : v); }();
+static const int kAhead = [] { const char* e = std::getenv("BLINGFIRE_B200_AHEAD"); const int v = e ? std::atoi(e) : 2; return v < 1 ? 1 : (v >= kSlots ? kSlots - 1 : v); }();
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -135,7 +138,7 @@ struct Slot {
 
 // everything one host call needs; leased from the model for the duration of the call
 struct Ctx {
-  Slot slots[kSlots];
+  Slot slots[kMaxSlots];
   PinBuf<int32_t> h_words;     // single-document calls: [ncps, tri_count, triples...] / ids, starts, ends
   void release() {
     for (auto& s : slots) s.release();
@@ -184,6 +187,8 @@ struct Model {
   int32_t* d_norm_values = nullptr;
   int32_t* d_bpe_ord = nullptr;
   int32_t* d_bpe_id_of_ord = nullptr;
+  WpWordSlot* d_seg_memo = nullptr;   // BPE: run-time memo of resolved segments (sp_bpe.cuh)
+  WpWords seg_memo{};
   I2w i2w;
   int32_t max_tag = 0;         // largest id the model itself can emit (UnkId aside)
 
@@ -227,6 +232,7 @@ struct Model {
     if (d_norm_values) cudaFree(d_norm_values);
     if (d_bpe_ord) cudaFree(d_bpe_ord);
     if (d_bpe_id_of_ord) cudaFree(d_bpe_id_of_ord);
+    if (d_seg_memo) cudaFree(d_seg_memo);
   }
 };
 
@@ -378,6 +384,17 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
     if (S.bpe_ord_ok) {
       if (!upload(&m->d_bpe_ord, S.bpe_ord.data(), S.bpe_ord.size(), 1)) return nullptr;
       if (!upload(&m->d_bpe_id_of_ord, S.bpe_id_of_ord.data(), S.bpe_id_of_ord.size(), 1)) return nullptr;
+      // the segment memo: 2 x 2^18 slots of 64 B (32 MB), empty at load
+      m->seg_memo = sp_seg_memo_params(S.alphabet, 18);
+      if (m->seg_memo.max_len > 0 && !std::getenv("BLINGFIRE_B200_NO_MEMO")) {
+        const size_t bytes = ((size_t)2 << m->seg_memo.log2_size) * sizeof(WpWordSlot);
+        if (!cuda_ok(cudaMalloc(&m->d_seg_memo, bytes), "cudaMalloc (segment memo)") ||
+            !cuda_ok(cudaMemset(m->d_seg_memo, 0, bytes), "cudaMemset (segment memo)"))
+          return nullptr;
+        m->seg_memo.slots = m->d_seg_memo;
+      } else {
+        m->seg_memo.max_len = 0;
+      }
     }
     m->no_dummy_prefix = S.no_dummy_prefix;
     for (const SegInfo& i : S.info) if (i.id != INT32_MIN) m->max_tag = std::max<int64_t>(m->max_tag, (int64_t)i.id + S.id_offset);
@@ -395,6 +412,7 @@ SpModelDev make_sp_model(const Model* m) {
   d.delim_inside_tokens = S.delim_inside_tokens; d.delim_is_token = S.delim_is_token; d.max_arc_len = S.max_arc_len;
   d.bpe_ord = S.bpe_ord_ok ? m->d_bpe_ord : nullptr; d.bpe_id_of_ord = m->d_bpe_id_of_ord;
   d.bpe_singles_first = S.bpe_singles_first;
+  d.seg_memo = m->seg_memo;
   return d;
 }
 
@@ -666,7 +684,7 @@ template <typename Issue, typename Finish>
 bool run_pipeline(Model* m, Ctx* ctx, const HostBatch& B, Issue issue, Finish finish) {
   if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return false;
   g_last_kernel_ms = 0.0;
-  bool copying[kSlots] = {};
+  bool copying[kMaxSlots] = {};
   auto settle = [&](int si) -> bool {   // wait for the ids copy of the chunk that last used slot si
     if (!copying[si]) return true;
     copying[si] = false;

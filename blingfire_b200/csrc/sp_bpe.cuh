@@ -200,6 +200,34 @@ __device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch&
   if (lane == 0) w.seg[nseg] = (uint16_t)cut;
   for (int i = lane; i < kBWin / 32; i += 32) w.mark[i] = 0;
   __syncwarp();
+  // ---- memo pass: a segment's ids depend on its symbols alone (no token crosses a U+2581, the whole-word shortcut looks
+  // only at the segment's own end) -- segments seen before come out of the table, one lane per segment.  A segment found
+  // there is flagged in seg[] (bit 15) and skipped by the passes below; the others are added once those have resolved them.
+  const WpWords& memo = m.seg_memo;
+  const bool use_memo = memo.max_len > 0;
+  if (use_memo) {
+    for (int g0 = 0; g0 < nseg; g0 += 32) {
+      const int g = g0 + lane;
+      int a = 0, L = 0;
+      if (g < nseg && !(open_ended && g == nseg - 1)) { a = w.seg[g]; L = (int)w.seg[g + 1] - a; if (L > (int)memo.max_len) L = 0; }
+      const int lcap = __reduce_max_sync(full, L);
+      if (lcap == 0) continue;
+      const bool wide = lcap > (int)(4 * memo.cpw);
+      uint32_t kw[8];
+      wp_pack_key_any(memo.cpw, w.sym + a, L, lcap, memo.cb, kw);
+      const WpWordHit hit = wp_words_find(memo, kw, wide);
+      if (L > 0 && hit.meta != 0) {
+        const int n = (int)(hit.meta & 7u);                   // 1..6 tokens, at most one per symbol
+        for (int k = 0; k < n; ++k) {
+          w.ids_at[a + k] = hit.id[k];
+          atomicOr(&w.mark[(a + k) >> 5], 1u << ((a + k) & 31));
+        }
+      }
+      __syncwarp();
+      if (L > 0 && hit.meta != 0) w.seg[g] = (uint16_t)(a | 0x8000);
+    }
+    __syncwarp();
+  }
   // ---- easy pass: the bpe-opt whole-word shortcut, one lane per segment ----
   // Walking from the segment start, an arc that ends exactly at the segment end after a shorter
   // arc was already seen makes the reference keep ONLY that arc and skip the interior starts
@@ -209,10 +237,12 @@ __device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch&
     const int g = g0 + lane;
     bool hard = false;
     int a = 0, b = 0;
-    if (g < nseg && open_ended && g == nseg - 1) {             // its true end is not in the window: no shortcut
-      a = w.seg[g]; b = w.seg[g + 1]; hard = true;
+    if (g < nseg && (w.seg[g] & 0x8000u)) {
+      // served by the memo pass
+    } else if (g < nseg && open_ended && g == nseg - 1) {      // its true end is not in the window: no shortcut
+      a = w.seg[g]; b = w.seg[g + 1] & 0x7FFF; hard = true;
     } else if (g < nseg) {
-      a = w.seg[g]; b = w.seg[g + 1];
+      a = w.seg[g]; b = w.seg[g + 1] & 0x7FFF;
       uint32_t q = m.root; int sum = 0, narcs = 0, whole_key = -1; bool whole = false;
       for (int i = a; i < b; ++i) {
         bool fin;
@@ -366,6 +396,33 @@ __device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch&
     }
   }
   __syncwarp();
+  // ---- learn pass: the segments the table did not hold, now resolved, go into it (not those with a start nothing
+  // claimed: that id is the caller's UnkId) ----
+  if (use_memo) {
+    for (int g0 = 0; g0 < nseg; g0 += 32) {
+      const int g = g0 + lane;
+      if (g < nseg && !(w.seg[g] & 0x8000u) && !(open_ended && g == nseg - 1)) {
+        const int a = w.seg[g], b = w.seg[g + 1] & 0x7FFF, L = b - a;
+        if (L <= (int)memo.max_len) {
+          int n = 0, offs[kMaxLearnPieces];
+          int32_t ids[kMaxLearnPieces];
+          bool clean = true;
+          for (int p = a; p < b; ++p)
+            if ((w.mark[p >> 5] >> (p & 31)) & 1u) {
+              const int32_t id = w.ids_at[p];
+              if (id == unk) clean = false;
+              if (n < kMaxLearnPieces) { ids[n] = id; offs[n] = n; }
+              ++n;
+            }
+          if (clean && n >= 1 && n <= kMaxLearnPieces) {
+            uint32_t kw[8];
+            wp_pack_key_any(memo.cpw, w.sym + a, L, L, memo.cb, kw);
+            wp_words_insert(memo, kw, L > (int)(4 * memo.cpw), n, ids, offs);
+          }
+        }
+      }
+    }
+  }
   // ---- ordered emission ----
   for (int p0 = 0; p0 < cut && out < max_ids; p0 += 32) {
     const uint32_t word = w.mark[p0 >> 5];

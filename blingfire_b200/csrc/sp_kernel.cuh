@@ -7,6 +7,7 @@
 #include <cstdint>
 
 #include "seg_tables.h"
+#include "wp_core.cuh"   // WpWords: the run-time memo table (segment -> ids) of the streaming BPE path
 
 namespace bfb200 {
 
@@ -28,7 +29,24 @@ struct SpModelDev {
   const int32_t* bpe_ord;        // [info_count]
   const int32_t* bpe_id_of_ord;
   bool bpe_singles_first;        // one-symbol tokens sort before all others (seg_tables.h)
+  // streaming BPE path: U+2581-delimited segments are independent subproblems, so a segment's ids are a function of its
+  // symbols alone; segments resolved once are kept in this table (filled at run time only; max_len 0 = off)
+  WpWords seg_memo;
 };
+
+// Parameters of the BPE segment memo for an alphabet of `alphabet` symbols (slots = nullptr: the caller allocates
+// (2 << log2_size) zeroed WpWordSlot and sets the pointer).  max_len 0: the model's symbols do not fit a key.
+inline WpWords sp_seg_memo_params(int alphabet, uint32_t log2_size) {
+  WpWords W{};
+  W.log2_size = log2_size;
+  W.cb = 1;
+  while ((1u << W.cb) < (uint32_t)alphabet) ++W.cb;
+  W.cpw = W.cb > 30 ? 0u : (30u / W.cb > 3u ? 3u : 30u / W.cb);
+  W.max_len = W.cpw == 0 ? 0u : (8u * W.cpw < (uint32_t)kMaxFastLen ? 8u * W.cpw : (uint32_t)kMaxFastLen);
+  const uint32_t mul[9] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u, 0x2545F491u};
+  for (int i = 0; i < 9; ++i) W.mul[i] = mul[i];
+  return W;
+}
 
 struct SpLaunch {
   const uint8_t* text;           // biased: absolute offsets index it

@@ -23,6 +23,7 @@ struct SpSim {
   LdbImage ldb;
   SegTables S;
   std::string err;
+  std::vector<WpWordSlot> memo_slots;
 };
 
 SpModelDev model_view(const SegTables& S) {
@@ -33,6 +34,7 @@ SpModelDev model_view(const SegTables& S) {
   d.delim_inside_tokens = S.delim_inside_tokens; d.delim_is_token = S.delim_is_token; d.max_arc_len = S.max_arc_len;
   d.bpe_ord = S.bpe_ord_ok ? S.bpe_ord.data() : nullptr; d.bpe_id_of_ord = S.bpe_id_of_ord.data();
   d.bpe_singles_first = S.bpe_singles_first;
+  d.seg_memo = WpWords{};
   return d;
 }
 
@@ -77,7 +79,12 @@ int spsim_batch(void* h, const char* text, const int64_t* offsets, int64_t ndocs
   X.ids = ids; X.counts = counts; X.starts = starts; X.ends = ends; X.max_ids = max_ids; X.unk_id = unk;
   X.work_counter = counter; X.arena = arena.data(); X.arena_stride = per_warp; X.arena_cap = cap; X.grid_warps = cta_warps;
   X.overflow = overflow.data(); X.overflow_cap = ovf_entries;
-  const SpModelDev m = model_view(S);
+  SpModelDev m = model_view(S);
+  if (bpe && S.bpe_ord_ok) {      // the segment memo persists across the batches of one handle, like the device table
+    if (t->memo_slots.empty()) t->memo_slots.assign((size_t)2 << 12, WpWordSlot{});
+    m.seg_memo = sp_seg_memo_params(S.alphabet, 12);
+    m.seg_memo.slots = t->memo_slots.data();
+  }
   int* err = reinterpret_cast<int*>(counter + 1);
   blockDim.x = (unsigned)cta_warps * 32; gridDim.x = 1;
   const size_t smem = bpe ? (size_t)kBWarps * kBWorkBytes : (size_t)kUWarps * kUWorkBytes;

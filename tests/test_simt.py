@@ -100,6 +100,15 @@ def test_kernel_source_matches_oracle(sim, name, unk):
     check(sim, name, docs[:60], 5, unk)              # truncation, incl. invalid bytes after MaxIds was reached
 
 
+@pytest.mark.parametrize("name", ["gpt2.bin", "roberta.bin"])
+def test_bpe_segment_memo(sim, name):
+    """The streaming BPE path keeps resolved U+2581-delimited segments in a table (sp_bpe.cuh): the same documents again
+    (now served from the table), then with other UnkIds -- one of them a real token id -- on the same model."""
+    docs = corpus_docs(77, 60) + [b"supercalifragilisticexpialidocious antidisestablishmentarianism " * 6, b" a" * 300, b"the the the the"]
+    for unk in (0, 0, 50256, 7, 262):
+        check(sim, name, docs, 512, unk)
+
+
 @pytest.mark.parametrize("name,unk", [("xlm_roberta_base.bin", 3), ("xlnet.bin", 0), ("gpt2.bin", 0), ("roberta.bin", 3)])
 def test_kernel_source_long_documents(sim, name, unk):
     """Several windows per document: the streamed Unigram form (cuts at U+2581 and inside U+2581-free runs, the
