@@ -49,6 +49,8 @@ def lib():
         L.TextToIdsBatch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int]
         L.TextToIdsBatchCsr.restype = c_int64
         L.TextToIdsBatchCsr.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int]
+        L.TextToWordsBatch.restype = c_int64
+        L.TextToWordsBatch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]
         L.TextToIdsBatchCsrU16.restype = c_int64
         L.TextToIdsBatchCsrU16.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int]
         L.TextToIdsBatchDevice.restype = c_int
@@ -157,6 +159,31 @@ def text_to_words_with_model(h, s):
 def text_to_words(s):
     """dist-pypi/blingfire/__init__.py:85-102 (default word-breaking model)."""
     return text_to_words_with_model(None, s)
+
+
+def text_to_words_batch(docs, h=None, raw=False):
+    """ADDITIVE: text_to_words[_with_model] for many documents in one call (TextToWordsBatch: lexer and string building on
+    the GPU).  `docs`: str / bytes items, or a (uint8 buffer, int64 offsets) pair.  Returns the list of strings ("" where
+    the per-document call returns "": bad UTF-8, empty input); with raw=True, (buffer, offsets, results) as numpy arrays."""
+    buf, offs = make_csr([d.encode("utf-8") if isinstance(d, str) else d for d in docs]) if not isinstance(docs, tuple) else docs
+    n = len(offs) - 1
+    out_offs = np.zeros(n + 1, np.int64)
+    results = np.zeros(n, np.int32)
+    cap = int(2 * len(buf) + n + 16)
+    out = np.empty(cap, np.uint8)
+    r = lib().TextToWordsBatch(c_void_p(h) if h else None, buf.ctypes.data if len(buf) else None, offs.ctypes.data, n, out.ctypes.data, cap,
+                               out_offs.ctypes.data, results.ctypes.data)
+    if r < 0 and -r > cap:
+        cap = int(-r)
+        out = np.empty(cap, np.uint8)
+        r = lib().TextToWordsBatch(c_void_p(h) if h else None, buf.ctypes.data if len(buf) else None, offs.ctypes.data, n, out.ctypes.data,
+                                   cap, out_offs.ctypes.data, results.ctypes.data)
+    if r < 0:
+        raise RuntimeError(f"TextToWordsBatch failed: {last_error()}")
+    if raw:
+        return out[:r], out_offs, results
+    data = out[:r].tobytes()
+    return [data[out_offs[i]:out_offs[i + 1] - 1].decode("utf-8") if results[i] > 0 else "" for i in range(n)]
 
 
 def text_to_sentences_with_model(h, s):

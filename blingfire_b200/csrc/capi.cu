@@ -95,13 +95,14 @@ struct PinBuf {
 constexpr int kMaxSlots = 8;
 // chunks in flight in the host pipeline / chunks enqueued behind the one whose counts the host waits for
 // (BLINGFIRE_B200_SLOTS / BLINGFIRE_B200_AHEAD override the defaults: tuning knobs)
-static const int kSlots = [] { const char* e = std::getenv("BLINGFIRE_B200_SLOTS"); const int v = e ? std::atoi(e) : 4; return v < 2 ? 2 : (v > kMaxSlots ? kMaxSlots : v); }();
-static const int kAhead = [] { const char* e = std::getenv("BLINGFIRE_B200_AHEAD"); const int v = e ? std::atoi(e) : 2; return v < 1 ? 1 : (v >= kSlots ? kSlots - 1 : v); }();
+static const int kSlots = [] { const char* e = std::getenv("BLINGFIRE_B200_SLOTS"); const int v = e ? std::atoi(e) : 8; return v < 2 ? 2 : (v > kMaxSlots ? kMaxSlots : v); }();
+static const int kAhead = [] { const char* e = std::getenv("BLINGFIRE_B200_AHEAD"); const int v = e ? std::atoi(e) : 4; return v < 1 ? 1 : (v >= kSlots ? kSlots - 1 : v); }();
 
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t counts_ready = nullptr;   // recorded after the chunk's row offsets were copied to the host
   cudaEvent_t k_begin = nullptr, k_end = nullptr;   // around the engine's kernels (device time of the tokenization alone)
+  cudaEvent_t h2d_done = nullptr;       // the chunk's text and offsets have left the (staging) host buffers
   DevBuf<uint8_t> text;
   DevBuf<int64_t> offsets;
   DevBuf<int32_t> ids;
@@ -121,6 +122,9 @@ struct Slot {
   // bookkeeping of the chunk in flight
   int64_t doc0 = 0, ndocs = 0;
   int64_t out_base = 0, out_n = 0;      // where the chunk's ids go in the caller's CSR buffer
+  // pageable caller buffers: copies between them and the pinned staging buffers run on the copy pool, asynchronously
+  CopyJob in_job, out_job;
+  int64_t staged_doc0 = -1;             // the chunk whose text is (being) staged into h_text
   void release() {
     lex_cls.release(); lex_ncps.release(); lex_tri.release(); lex_tri_count.release(); lex_boff.release();
     sp_arena.release(); sp_overflow.release();
@@ -129,6 +133,8 @@ struct Slot {
     if (counts_ready) cudaEventDestroy(counts_ready);
     counts_ready = nullptr;
     if (k_begin) cudaEventDestroy(k_begin);
+    if (h2d_done) cudaEventDestroy(h2d_done);
+    h2d_done = nullptr;
     if (k_end) cudaEventDestroy(k_end);
     k_begin = k_end = nullptr;
     if (stream) cudaStreamDestroy(stream);
@@ -465,6 +471,7 @@ bool ensure_stream(Slot& s) {
   if (s.stream) return true;
   if (!cuda_ok(cudaEventCreateWithFlags(&s.counts_ready, cudaEventDisableTiming), "cudaEventCreate")) return false;
   if (!cuda_ok(cudaEventCreate(&s.k_begin), "cudaEventCreate") || !cuda_ok(cudaEventCreate(&s.k_end), "cudaEventCreate")) return false;
+  if (!cuda_ok(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming), "cudaEventCreate")) return false;
   return cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
 }
 
@@ -583,6 +590,18 @@ struct HostBatch {
   OutKind out = OutKind::kCsr32;
 };
 
+// Pageable caller text: start copying the chunk into the slot's pinned staging buffers (copy-pool threads).
+bool stage_chunk(Model* m, Slot& s, const HostBatch& B, int64_t doc0, int64_t ndocs) {
+  const int64_t b0 = B.offsets[doc0] & ~(int64_t)3, b1 = B.offsets[doc0 + ndocs];
+  const size_t nbytes = (size_t)(b1 - b0);
+  if (!s.h_text.reserve(nbytes + 64) || !s.h_offsets.reserve((size_t)ndocs + 1)) return false;
+  CopyPool* pool = copy_pool_of(m);
+  pool->submit(s.h_text.p, B.utf8 + b0, nbytes, &s.in_job);
+  pool->submit(s.h_offsets.p, B.offsets + doc0, ((size_t)ndocs + 1) * sizeof(int64_t), &s.in_job);
+  s.staged_doc0 = doc0;
+  return true;
+}
+
 // Enqueue one chunk [doc0, doc0+ndocs) of a host CSR batch on slot s: H2D, tokenize, scan, compact,
 // D2H of the row offsets.  Offsets stay absolute; the device text pointer is biased instead.
 bool enqueue_chunk(Model* m, Slot& s, const HostBatch& B, int64_t doc0, int64_t ndocs) {
@@ -608,9 +627,9 @@ bool enqueue_chunk(Model* m, Slot& s, const HostBatch& B, int64_t doc0, int64_t 
   const char* text_src = B.utf8 + b0;
   const int64_t* offs_src = offsets + doc0;
   if (B.stage_in) {
-    if (!s.h_text.reserve(nbytes + 64) || !s.h_offsets.reserve((size_t)ndocs + 1)) return false;
-    copy_pool_of(m)->copy(s.h_text.p, text_src, nbytes);
-    std::memcpy(s.h_offsets.p, offs_src, ((size_t)ndocs + 1) * sizeof(int64_t));
+    if (s.staged_doc0 != doc0 && !stage_chunk(m, s, B, doc0, ndocs)) return false;   // (normally prefetched by run_pipeline)
+    copy_pool_of(m)->wait(&s.in_job);
+    s.staged_doc0 = -1;
     text_src = (const char*)s.h_text.p;
     offs_src = s.h_offsets.p;
   }
@@ -618,6 +637,7 @@ bool enqueue_chunk(Model* m, Slot& s, const HostBatch& B, int64_t doc0, int64_t 
   if (!cuda_ok(cudaMemcpyAsync(s.offsets.p, offs_src, ((size_t)ndocs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream), "H2D offsets")) return false;
 
   int nl = 0;
+  if (!cuda_ok(cudaEventRecord(s.h2d_done, s.stream), "event record")) return false;
   if (!cuda_ok(cudaEventRecord(s.k_begin, s.stream), "event record")) return false;
   const uint8_t* text_biased = s.text.p - b0;
   if (m->engine == 3) {
@@ -666,7 +686,7 @@ int64_t chunk_docs(const int64_t* offsets, int64_t doc0, int64_t ndocs_total, in
   // the generic lexer keeps 26 scratch bytes per input byte (classes + triples)
   // chunk size of the host pipeline; BLINGFIRE_B200_CHUNK_MB overrides it (tuning knob)
   static const int64_t env_mb = [] { const char* e = std::getenv("BLINGFIRE_B200_CHUNK_MB"); return e ? std::atoll(e) : 0ll; }();
-  const int64_t kMaxBytes = engine == 2 ? (8ll << 20) : ((env_mb > 0 ? env_mb : 32) << 20);
+  const int64_t kMaxBytes = engine == 2 ? (8ll << 20) : ((env_mb > 0 ? env_mb : 16) << 20);
   const int64_t kMaxIdsCells = 160ll << 20;     // 640 MB of int32 per slot
   const int64_t max_docs = std::max<int64_t>(1, kMaxIdsCells / std::max(1, max_ids));
   int64_t d = doc0;
@@ -715,6 +735,14 @@ bool run_pipeline(Model* m, Ctx* ctx, const HostBatch& B, Issue issue, Finish fi
     double t1 = now();
     const int64_t nd = chunk_docs(B.offsets, d, B.ndocs, B.max_ids, m->engine);
     if (!enqueue_chunk(m, ctx->slots[si], B, d, nd)) { ok = false; break; }
+    if (B.stage_in && d + nd < B.ndocs) {
+      // pageable text: the copy threads stage the next chunk while this one is in flight
+      const int sj = (c + 1) % kSlots;
+      if (!settle(sj)) { ok = false; break; }
+      if (ctx->slots[sj].h2d_done && !cuda_ok(cudaEventSynchronize(ctx->slots[sj].h2d_done), "event sync")) { ok = false; break; }
+      const int64_t nd2 = chunk_docs(B.offsets, d + nd, B.ndocs, B.max_ids, m->engine);
+      if (!stage_chunk(m, ctx->slots[sj], B, d + nd, nd2)) { ok = false; break; }
+    }
     double t2 = now();
     // chunk c-kAhead: its kernels had kAhead chunks of queued work behind them, so the copy
     // engines and the SMs never wait for the host
@@ -732,6 +760,13 @@ bool run_pipeline(Model* m, Ctx* ctx, const HostBatch& B, Issue issue, Finish fi
   if (ok)
     for (int k = c >= kSlots ? c - kSlots : 0; k < c && ok; ++k)     // the chunks still copying, oldest first
       ok = settle(k % kSlots);
+  // the asynchronous host copies of this call (they read / write the caller's buffers)
+  if (m->copy_pool)
+    for (int k = 0; k < kMaxSlots; ++k) {
+      m->copy_pool->wait(&ctx->slots[k].in_job);
+      m->copy_pool->wait(&ctx->slots[k].out_job);
+      ctx->slots[k].staged_doc0 = -1;
+    }
   if (!ok) {
     // the context goes back to the pool: nothing of this call may still be in flight on its streams
     const std::string keep = g_last_error;
@@ -776,6 +811,7 @@ int64_t batch_csr(Model* m, const char* utf8, const int64_t* offsets, int64_t nd
     else if (n > 0) {
       void* dst = ids_csr + total;
       if (stage_out) {
+        copy_pool_of(m)->wait(&s.out_job);          // the slot's previous ids have left the staging buffer
         if (!s.h_csr.reserve(((size_t)n * sizeof(OutT) + 3) / 4 + 1)) return false;
         dst = s.h_csr.p;
         s.out_n = n;
@@ -786,7 +822,7 @@ int64_t batch_csr(Model* m, const char* utf8, const int64_t* offsets, int64_t nd
     return true;
   };
   auto finish = [&](Slot& s) -> bool {
-    if (s.out_n > 0) copy_pool_of(m)->copy(ids_csr + s.out_base, s.h_csr.p, (size_t)s.out_n * sizeof(OutT));
+    if (s.out_n > 0) copy_pool_of(m)->submit(ids_csr + s.out_base, s.h_csr.p, (size_t)s.out_n * sizeof(OutT), &s.out_job);
     return true;
   };
   if (!run_pipeline(m, lease.c, B, issue, finish)) return -1;
@@ -1272,6 +1308,70 @@ int TextToWordsWithModel(const char* s, int n, char* out, const int max_out, voi
   return TextToWordsWithOffsetsWithModel(s, n, out, nullptr, nullptr, max_out, hModel);
 }
 int TextToWords(const char* s, int n, char* out, const int max_out) { return TextToWordsWithOffsetsWithModel(s, n, out, nullptr, nullptr, max_out, nullptr); }
+
+// Additive: TextToWords[WithModel] for a batch (CSR documents in, CSR strings out).  The lexer AND the string building
+// (blingfiretokdll.cpp:507-555) run on the GPU; documents go through in chunks of a few MB.
+//   results[i]      what TextToWordsWithModel returns for document i: -1 error, 0 empty input, else the byte length of
+//                   its string including the NUL
+//   out_offsets[i]  where that string starts in `out` (documents without one take no bytes); out_offsets[ndocs] = total
+// Returns the total bytes, or -total when `capacity` is too small (out_offsets and results are complete then), -1 on error.
+int64_t TextToWordsBatch(void* hModel, const char* utf8, const int64_t* offsets, int64_t ndocs, char* out, int64_t capacity,
+                         int64_t* out_offsets, int32_t* results) {
+  try {
+    g_last_error.clear();
+    Model* m = hModel ? (Model*)hModel : default_model(0);
+    if (!m) return -1;
+    if (ndocs < 0 || !out_offsets || !results || (ndocs > 0 && (!utf8 || !offsets)) || (capacity > 0 && !out)) { set_error("bad batch arguments"); return -1; }
+    if (!m->has_wbd || !m->lex_ok) { set_error("model has no lexer engine"); return -1; }
+    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
+    CtxLease lease(m);
+    Slot& sl = lease.c->slots[0];
+    if (!ensure_stream(sl)) return -1;
+    int64_t total = 0;
+    bool overflow = false;
+    out_offsets[0] = 0;
+    const int64_t kChunkBytes = 8ll << 20;
+    for (int64_t d0 = 0; d0 < ndocs;) {
+      int64_t d1 = d0;
+      while (d1 < ndocs && (d1 == d0 || offsets[d1 + 1] - offsets[d0] <= kChunkBytes) && d1 - d0 < (1 << 20)) ++d1;
+      const int64_t nd = d1 - d0;
+      const int64_t b0 = offsets[d0] & ~(int64_t)3, b1 = offsets[d1];
+      const size_t nb = (size_t)(b1 - b0), span = (size_t)(b1 - offsets[d0]);
+      if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve((size_t)nd + 1) || !sl.lex_cls.reserve(span + 8) || !sl.lex_ncps.reserve((size_t)nd) ||
+          !sl.lex_tri_count.reserve((size_t)nd) || !sl.lex_tri.reserve(3 * span + 8) || !sl.lex_boff.reserve(span + 8) ||
+          !sl.counts.reserve((size_t)nd + 1) || !sl.ids.reserve((size_t)nd + 1) || !sl.row_off.reserve((size_t)nd + 1) ||
+          !sl.h_row_off.reserve((size_t)nd + 2) || !sl.h_csr.reserve((size_t)nd + 1))
+        return -1;
+      if (nb && !cuda_ok(cudaMemcpyAsync(sl.text.p, utf8 + b0, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return -1;
+      if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offsets + d0, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return -1;
+      LexLaunch X = make_lex_launch(sl, sl.text.p - b0, sl.offsets.p, offsets[d0], b1, nd, m->d_cls_words, 1);   // MaxOut = 3 * MaxBuffSize (:492-499)
+      X.boff_buf = sl.lex_boff.p;
+      int nl = 0;
+      if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return -1;
+      int32_t* d_lens = sl.counts.p;
+      int32_t* d_results = sl.ids.p;
+      if (!cuda_ok(lex_words_len_launch(X, d_lens, d_results, sl.stream), "words length launch")) return -1;
+      if (!cuda_ok(wp_scan_counts(d_lens, sl.row_off.p, nd, sl.stream), "scan")) return -1;
+      g_launches += nl + 2;
+      if (!cuda_ok(cudaMemcpyAsync(sl.h_row_off.p, sl.row_off.p, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, sl.stream), "D2H offsets")) return -1;
+      if (!cuda_ok(cudaMemcpyAsync(sl.h_csr.p, d_results, (size_t)nd * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H results")) return -1;
+      if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
+      const int64_t nout = sl.h_row_off.p[nd];
+      for (int64_t i = 0; i < nd; ++i) { out_offsets[d0 + i + 1] = total + sl.h_row_off.p[i + 1]; results[d0 + i] = sl.h_csr.p[i]; }
+      if (total + nout > capacity) overflow = true;
+      else if (nout > 0) {
+        if (!sl.csr.reserve((size_t)(nout + 3) / 4 + 1)) return -1;
+        if (!cuda_ok(lex_words_write_launch(X, sl.row_off.p, d_results, reinterpret_cast<char*>(sl.csr.p), sl.stream), "words write launch")) return -1;
+        g_launches += 1;
+        if (!cuda_ok(cudaMemcpyAsync(out + total, sl.csr.p, (size_t)nout, cudaMemcpyDeviceToHost, sl.stream), "D2H text")) return -1;
+        if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
+      }
+      total += nout;
+      d0 = d1;
+    }
+    return overflow ? -total : total;
+  } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
 
 // blingfiretokdll.cpp:163-355.  One sentence per triple of the sentence-breaking lexer: it starts right
 // after the previous one (tags and Froms are ignored, :262-266), leading white space is dropped, '\n'

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fstream>
 #include <functional>
 #include <memory>
@@ -57,6 +58,12 @@ inline bool numa_cpus_of_pci(const char* bus_id, cpu_set_t* out) {
   return n > 0;
 }
 
+// Completion of one (or several) submitted copies.
+struct CopyJob {
+  std::atomic<size_t> left{0};
+  bool done() const { return left.load(std::memory_order_acquire) == 0; }
+};
+
 class CopyPool {
  public:
   // `threads` workers in addition to the calling thread; `cpus` (may be null) = where they may run
@@ -67,71 +74,84 @@ class CopyPool {
     }
   }
   ~CopyPool() {
-    { std::lock_guard<std::mutex> l(mu_); stop_ = true; ++epoch_; }
+    { std::lock_guard<std::mutex> l(mu_); stop_ = true; }
     cv_.notify_all();
     for (auto& t : workers_) t.join();
   }
   int threads() const { return (int)workers_.size(); }
 
+  // Queues the copy in slices and returns; `job` counts them down.  The buffers must stay valid until wait(job).
+  void submit(void* dst, const void* src, size_t n, CopyJob* job) {
+    if (n == 0) return;
+    const size_t parts = (n + kSlice - 1) / kSlice;
+    job->left.fetch_add(parts, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      for (size_t k = 0; k < parts; ++k) {
+        const size_t a = k * kSlice, b = a + kSlice < n ? a + kSlice : n;
+        q_.push_back(Slice{(uint8_t*)dst + a, (const uint8_t*)src + a, b - a, job, nullptr});
+      }
+    }
+    if (parts > 1) cv_.notify_all(); else cv_.notify_one();
+  }
+  // Blocks until every slice of `job` is through; the caller takes slices (of any job) meanwhile.
+  void wait(CopyJob* job) {
+    while (!job->done()) {
+      Slice s;
+      if (pop(&s)) run_slice(s); else std::this_thread::yield();
+    }
+  }
   // blocking parallel loop: fn(k) for k in [0, parts), the calling thread takes its share
   void parallel_for(size_t parts, const std::function<void(size_t)>& fn) {
     if (parts == 0) return;
     if (parts == 1 || workers_.empty()) { for (size_t k = 0; k < parts; ++k) fn(k); return; }
-    auto job = std::make_shared<Job>();
-    job->fn = &fn; job->parts = parts;
-    { std::lock_guard<std::mutex> l(mu_); job_ = job; ++epoch_; }
+    CopyJob job;
+    job.left.fetch_add(parts, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      for (size_t k = 0; k < parts; ++k) q_.push_back(Slice{nullptr, nullptr, k, &job, &fn});
+    }
     cv_.notify_all();
-    work(*job);
-    // the parts are short: spin until the last worker is through
-    while (job->done.load(std::memory_order_acquire) < job->parts) std::this_thread::yield();
+    wait(&job);
   }
-
   // blocking parallel memcpy
   void copy(void* dst, const void* src, size_t n) {
     if (n <= 2 * kSlice || workers_.empty()) { std::memcpy(dst, src, n); return; }
-    uint8_t* d = (uint8_t*)dst;
-    const uint8_t* s = (const uint8_t*)src;
-    parallel_for((n + kSlice - 1) / kSlice, [&](size_t k) {
-      const size_t a = k * kSlice, b = a + kSlice < n ? a + kSlice : n;
-      std::memcpy(d + a, s + a, b - a);
-    });
+    CopyJob job;
+    submit(dst, src, n, &job);
+    wait(&job);
   }
 
  private:
   static constexpr size_t kSlice = 1u << 20;
-  struct Job {
-    const std::function<void(size_t)>* fn = nullptr;   // outlives the job: parallel_for blocks until done == parts
-    size_t parts = 0;
-    std::atomic<size_t> next{0}, done{0};
-  };
-  static void work(Job& j) {
-    for (;;) {
-      const size_t k = j.next.fetch_add(1, std::memory_order_relaxed);
-      if (k >= j.parts) break;
-      (*j.fn)(k);
-      j.done.fetch_add(1, std::memory_order_release);
-    }
+  struct Slice { uint8_t* dst; const uint8_t* src; size_t n; CopyJob* job; const std::function<void(size_t)>* fn = nullptr; };
+  static void run_slice(const Slice& s) {
+    if (s.fn) (*s.fn)(s.n); else std::memcpy(s.dst, s.src, s.n);
+    s.job->left.fetch_sub(1, std::memory_order_release);
+  }
+  bool pop(Slice* out) {
+    std::lock_guard<std::mutex> l(mu_);
+    if (q_.empty()) return false;
+    *out = q_.front(); q_.pop_front();
+    return true;
   }
   void run() {
-    uint64_t seen = 0;
     for (;;) {
-      std::shared_ptr<Job> job;
+      Slice s;
       {
         std::unique_lock<std::mutex> l(mu_);
-        cv_.wait(l, [&] { return epoch_ != seen; });
-        seen = epoch_;
+        cv_.wait(l, [&] { return stop_ || !q_.empty(); });
         if (stop_) return;
-        job = job_;      // a worker that wakes late works on (the leftovers of) the job it saw
+        s = q_.front(); q_.pop_front();
       }
-      if (job) work(*job);
+      run_slice(s);
     }
   }
   std::vector<std::thread> workers_;
   std::mutex mu_;
   std::condition_variable cv_;
-  uint64_t epoch_ = 0;
+  std::deque<Slice> q_;
   bool stop_ = false;
-  std::shared_ptr<Job> job_;
 };
 
 }  // namespace bfb200

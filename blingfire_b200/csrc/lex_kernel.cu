@@ -159,9 +159,86 @@ __global__ void __launch_bounds__(128) lex_wp_offsets_kernel(const LexLaunch p, 
   counts[doc] = out;
 }
 
+// ---- TextToWords for a batch: the output strings are put together on the device ----
+// blingfiretokdll.cpp:507-555: every token that is not IGNORE, ' ' inside a token -> '_', U+0000 -> ' ' (:482), tokens joined
+// by one ' ', a trailing NUL.  One thread per document walks its triples twice: lengths first, bytes after the scan.
+struct WordsDoc {
+  const int32_t* tri; const int32_t* boff; const uint8_t* text;
+  int rn, ncps, nbytes;
+};
+__device__ __forceinline__ int words_doc(const LexLaunch& p, int64_t doc, WordsDoc* d) {   // 1 ok, 0 empty input, -1 error
+  const int64_t lo = __ldg(p.offsets + doc), n = __ldg(p.offsets + doc + 1) - lo;
+  if (n == 0) return 0;                                             // :446-448
+  if (n < 0 || n > 1000000000) return -1;                           // :449-454
+  const int ncps = p.ncps[doc];
+  if (ncps <= 0) return -1;                                         // invalid UTF-8, or nothing decoded (:475-478)
+  const int rn = p.tri_count[doc];
+  if (rn < 0 || rn > 3 * ncps || rn % 3 != 0) return -1;            // :500-502
+  const int64_t rel = lo - p.base_offset;
+  d->tri = p.tri_buf + 3 * (int64_t)p.tri_mul * rel; d->boff = p.boff_buf + rel; d->text = p.text + lo;
+  d->rn = rn; d->ncps = ncps; d->nbytes = (int)n;
+  return 1;
+}
+__device__ __forceinline__ int words_cp_off(const WordsDoc& d, int i) { return i >= d.ncps ? d.nbytes : d.boff[i]; }
+
+__global__ void __launch_bounds__(128) lex_words_len_kernel(const LexLaunch p, int32_t* lens, int32_t* results) {
+  const int64_t doc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (doc >= p.ndocs) return;
+  WordsDoc d;
+  int r = words_doc(p, doc, &d), total = 0;
+  if (r == 1) {
+    int words = 0;
+    for (int i = 0; i < d.rn && r == 1; i += 3) {
+      if (d.tri[i] == 4) continue;                                  // WBD_IGNORE_TAG (:511-514)
+      const int from = d.tri[i + 1], to = d.tri[i + 2];
+      if (from < 0 || from > d.ncps || to >= d.ncps || to < -1) { r = -1; break; }
+      const int b0 = words_cp_off(d, from), b1 = words_cp_off(d, to + 1);
+      total += (b1 > b0 ? b1 - b0 : 0) + (words > 0 ? 1 : 0);
+      ++words;
+    }
+    total += 1;                                                     // the NUL (:555)
+  }
+  lens[doc] = r == 1 ? total : 0;
+  results[doc] = r == 1 ? total : r;
+}
+
+__global__ void __launch_bounds__(128) lex_words_write_kernel(const LexLaunch p, const int64_t* out_off, const int32_t* results, char* out) {
+  const int64_t doc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (doc >= p.ndocs || results[doc] <= 0) return;
+  WordsDoc d;
+  if (words_doc(p, doc, &d) != 1) return;
+  char* o = out + out_off[doc];
+  int words = 0;
+  for (int i = 0; i < d.rn; i += 3) {
+    if (d.tri[i] == 4) continue;
+    const int b0 = words_cp_off(d, d.tri[i + 1]), b1 = words_cp_off(d, d.tri[i + 2] + 1);
+    if (words > 0) *o++ = ' ';
+    for (int b = b0; b < b1; ++b) {
+      char c = (char)d.text[b];
+      if (c == 0) c = 0x20;
+      if (c == ' ') c = '_';
+      *o++ = c;
+    }
+    ++words;
+  }
+  *o = 0;
+}
+
 }  // namespace
 
 #ifndef BF_SIMT_HOST                       // tests/simt compiles the kernels above for the host
+cudaError_t lex_words_len_launch(const LexLaunch& p, int32_t* lens, int32_t* results, cudaStream_t stream) {
+  if (p.ndocs <= 0) return cudaSuccess;
+  if (!p.boff_buf) return cudaErrorInvalidValue;
+  lex_words_len_kernel<<<(int)((p.ndocs + 127) / 128), 128, 0, stream>>>(p, lens, results);
+  return cudaGetLastError();
+}
+cudaError_t lex_words_write_launch(const LexLaunch& p, const int64_t* out_off, const int32_t* results, char* out, cudaStream_t stream) {
+  if (p.ndocs <= 0) return cudaSuccess;
+  lex_words_write_kernel<<<(int)((p.ndocs + 127) / 128), 128, 0, stream>>>(p, out_off, results, out);
+  return cudaGetLastError();
+}
+
 cudaError_t lex_wp_offsets_launch(const LexLaunch& p, int32_t* ids, int32_t* starts, int32_t* ends, int32_t* counts,
                                   int max_ids, int unk, cudaStream_t stream, int* launches) {
   if (p.ndocs <= 0) return cudaSuccess;

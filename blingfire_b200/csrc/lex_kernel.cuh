@@ -42,4 +42,9 @@ cudaError_t lex_wp_launch(const LexLaunch& p, int32_t* ids, int32_t* counts, int
 cudaError_t lex_wp_offsets_launch(const LexLaunch& p, int32_t* ids, int32_t* starts, int32_t* ends, int32_t* counts,
                                   int max_ids, int unk, cudaStream_t stream, int* launches);
 
+// TextToWords for a batch (needs p.boff_buf): bytes of every document's output string incl. its NUL (0 when the document has
+// none) and what TextToWords returns for it; then the strings themselves at out + out_off[doc]
+cudaError_t lex_words_len_launch(const LexLaunch& p, int32_t* lens, int32_t* results, cudaStream_t stream);
+cudaError_t lex_words_write_launch(const LexLaunch& p, const int64_t* out_off, const int32_t* results, char* out, cudaStream_t stream);
+
 }  // namespace bfb200

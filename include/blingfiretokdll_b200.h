@@ -114,6 +114,17 @@ int TextToWordsWithOffsetsWithModel(const char* pInUtf8Str, int InUtf8StrByteCou
 int TextToWordsWithOffsets(const char* pInUtf8Str, int InUtf8StrByteCount, char* pOutUtf8Str,
                            int* pStartOffsets, int* pEndOffsets, const int MaxOutUtf8StrByteCount);
 
+/* ADDITIVE (not in the reference, which takes one document per call: blingfiretokdll.cpp:415-566).  TextToWords[WithModel]
+ * for a batch: documents as CSR (pUtf8, pOffsets[DocCount+1]), strings as CSR.  The lexer and the string building
+ * (:507-555) both run on the GPU.  hModel may be NULL (the default word breaker, like TextToWords).
+ *   pResults[i]     what TextToWordsWithModel would return for document i: -1 (bad UTF-8), 0 (empty input), else the byte
+ *                   length of its string INCLUDING the trailing NUL
+ *   pOutOffsets[i]  where that string starts in pOut; documents without one take no bytes; pOutOffsets[DocCount] = total
+ * Returns the total bytes; -total when Capacity is too small (pOutOffsets / pResults are complete, call again); -1 on
+ * error (BlingFireB200LastError). */
+int64_t TextToWordsBatch(void* hModel, const char* pUtf8, const int64_t* pOffsets, int64_t DocCount, char* pOut,
+                         int64_t Capacity, int64_t* pOutOffsets, int32_t* pResults);
+
 /* blingfiretokdll.h:33 / :31-32 / :29-30 / :27-28, blingfiretokdll.cpp:398-401 / :378-381 / :364-368 / :163-355.
  * Splits a paragraph into sentences, '\n'-joined (a '\n' inside a sentence becomes ' '); same return
  * convention as TextToWords.  The sentence-breaking lexer (default: sbd.bin, loaded from

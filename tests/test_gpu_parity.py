@@ -274,6 +274,45 @@ def test_cfg1_text_to_words_10k_ascii_lines(bf, oracle):
     assert L.TextToWords(b"\xff\xfe", 2, out, 1024) == -1
 
 
+def test_text_to_words_batch(bf, oracle):
+    """The additive batch form (lexer AND string building on the GPU) against the per-document reference semantics:
+    cfg 1's 10 000 lines with the default model, multilingual and edge documents with wbd.bin / wbd_chuni.bin handles,
+    a too-small buffer."""
+    import ctypes
+    import time
+    L = bf.lib()
+    lines = [l for l in read_lines("test.txt") if len(l) <= 120 and all(c < 128 for c in l)][:10000]
+    ho = oracle.load(model_path("wbd.bin"))
+    want = [oracle.text_to_words(ho, l, 1024) for l in lines]
+    buf, offs = bf.make_csr(lines)
+    out, out_offs, results = bf.text_to_words_batch((buf, offs), raw=True)       # warm-up + result
+    t0 = time.perf_counter()
+    out, out_offs, results = bf.text_to_words_batch((buf, offs), raw=True)
+    dt = time.perf_counter() - t0
+    data = out.tobytes()
+    for i, (n2, s2) in enumerate(want):
+        assert results[i] == n2 and data[out_offs[i]:out_offs[i + 1]] == s2, lines[i]
+    assert len(buf) / dt / 1e6 > 19.6, f"batch TextToWords at {len(buf) / dt / 1e6:.1f} MB/s: the reference does 19.6 MB/s on one CPU thread"
+    assert bf.text_to_words_batch(["I saw a girl with a telescope.", ""]) == ["I saw a girl with a telescope .", ""]
+    docs = read_lines("test.multi.txt", drop_empty=False)[:4000] + [b"", b"\xff\xfe", b"\xef\xbb\xbf", b"\xef\xbb\xbfbom", b"a\x00b c", b"x" * 5000,
+                                                                    b"can't won't cannot U.S.A. 3.14 e-mail", b" ", b"\xe6\x88"]
+    for name in ("wbd.bin", "wbd_chuni.bin"):
+        h = bf.load_model(model_path(name))
+        ho2 = oracle.load(model_path(name))
+        out, out_offs, results = bf.text_to_words_batch(bf.make_csr(docs), h=h, raw=True)
+        data = out.tobytes()
+        for i, d in enumerate(docs):
+            n2, s2 = oracle.text_to_words(ho2, d, 2 * len(d) + 16)
+            assert results[i] == n2, (name, d[:40], int(results[i]), n2)
+            assert data[out_offs[i]:out_offs[i + 1]] == (s2 if n2 > 0 else b""), (name, d[:40])
+        bf.free_model(h)
+    # capacity too small: -total, offsets and results complete
+    b2, o2 = bf.make_csr(lines[:100])
+    oo = np.zeros(101, np.int64); rr = np.zeros(100, np.int32); small = np.zeros(8, np.uint8)
+    r = L.TextToWordsBatch(None, b2.ctypes.data, o2.ctypes.data, 100, small.ctypes.data, 8, oo.ctypes.data, rr.ctypes.data)
+    assert r == -int(sum(w[0] for w in want[:100])) and oo[100] == -r and (rr == [w[0] for w in want[:100]]).all()
+
+
 def test_text_to_words_with_model_multilingual(bf, oracle):
     import ctypes
     L = bf.lib()
