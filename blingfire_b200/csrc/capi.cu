@@ -318,6 +318,40 @@ bool load_i2w(const LdbImage& ldb, I2w* w) {
   return true;
 }
 
+// The dense state x class table of a wide (32-bit entries) lexer model, built in HBM from the stored arcs: the table is
+// 9.3 GB for bert_multi_cased with 0.03 % of its cells set -- staging it on the host took 12 s and 9.3 GB of RAM.
+// One thread per state: its arcs, then -- for the rare state with an IW_ANY arc -- the fallback into every empty cell
+// (FALexTools_t.h:266-270), exactly like lexer_tables.cpp does for the host copy.
+__global__ void trans_fill_kernel(uint32_t* __restrict__ trans, const int64_t* __restrict__ arc_begin, const uint32_t* __restrict__ arc_label,
+                                  const uint32_t* __restrict__ arc_dst, const uint32_t* __restrict__ any_dst, int ns, uint32_t W) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ns) return;
+  uint32_t* row = trans + (size_t)s * W;
+  for (int64_t k = arc_begin[s]; k < arc_begin[s + 1]; ++k) row[arc_label[k]] = arc_dst[k];
+  const uint32_t any = any_dst[s];
+  if (any != 0xFFFFFFFFu)
+    for (uint32_t c = 0; c < W; ++c) if (row[c] == 0xFFFFFFFFu) row[c] = any;
+}
+
+bool build_trans_on_device(Model* m) {
+  const LexerTables& T = m->T;
+  const size_t W = (size_t)T.NC + 1, cells = (size_t)T.NS * W;
+  uint32_t* d = nullptr;
+  int64_t* d_begin = nullptr; uint32_t *d_label = nullptr, *d_dst = nullptr, *d_any = nullptr;
+  bool ok = cuda_ok(cudaMalloc(&d, (cells + 16) * sizeof(uint32_t)), "cudaMalloc (transition table)") &&
+            cuda_ok(cudaMemset(d, 0xFF, (cells + 16) * sizeof(uint32_t)), "cudaMemset") &&
+            upload(&d_begin, T.arc_begin.data(), T.arc_begin.size()) && upload(&d_label, T.arc_label.data(), T.arc_label.size(), 1) &&
+            upload(&d_dst, T.arc_dst.data(), T.arc_dst.size(), 1) && upload(&d_any, T.any_dst.data(), T.any_dst.size());
+  if (ok) {
+    trans_fill_kernel<<<(T.NS + 127) / 128, 128>>>(d, d_begin, d_label, d_dst, d_any, T.NS, (uint32_t)W);
+    ok = cuda_ok(cudaGetLastError(), "table fill launch") && cuda_ok(cudaDeviceSynchronize(), "table fill");
+  }
+  cudaFree(d_begin); cudaFree(d_label); cudaFree(d_dst); cudaFree(d_any);
+  if (!ok) { cudaFree(d); return false; }
+  m->d_trans = d;
+  return true;
+}
+
 Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
   m->has_wbd = ldb.conf().get(kFuncWbd) != nullptr;
   m->has_seg = ldb.conf().get(kFuncPosDict) != nullptr;
@@ -338,10 +372,12 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
   }
   if (m->has_wbd && !m->has_seg) {
     std::string err;
-    if (!build_lexer_tables(ldb, &m->T, &err)) { set_error("lexer model: " + err); return nullptr; }
+    // a table with 32-bit entries is built in HBM from the stored arcs, not staged on the host
+    if (!build_lexer_tables(ldb, &m->T, &err, /*dense_wide=*/false)) { set_error("lexer model: " + err); return nullptr; }
     LexerTables& T = m->T;
     const size_t cells = (size_t)T.NS * ((size_t)T.NC + 1);
-    if (T.wide_states) { if (!upload((uint32_t**)&m->d_trans, T.trans32.data(), cells, 16)) return nullptr; }
+    if (!T.dense_on_host) { if (!build_trans_on_device(m.get())) return nullptr; }
+    else if (T.wide_states) { if (!upload((uint32_t**)&m->d_trans, T.trans32.data(), cells, 16)) return nullptr; }
     else { if (!upload((uint16_t**)&m->d_trans, T.trans16.data(), cells, 16)) return nullptr; }
     // generic lexer engine: serves TextToWords for every [wbd] model, and TextToIds for the
     // grammars outside the FastPath shape
@@ -372,6 +408,7 @@ Model* finish_model(std::unique_ptr<Model> m, const LdbImage& ldb) {
     // the dense table is the bulk of the host footprint; the device copy is the one that serves
     DenseVec<uint16_t>().swap(T.trans16);
     DenseVec<uint32_t>().swap(T.trans32);
+    T.dense_on_host = false;               // (next() answers from the stored arcs from here on)
   }
   if (m->has_seg) {
     // blingfiretokdll.cpp:1636-1645: a [pos-dict] model is served by the segmentation engine
@@ -1137,6 +1174,81 @@ int TextToIdsWithOffsets(void* h, const char* s, int n, int32_t* ids, int* start
     std::memcpy(ends, hw + 4 + 2 * (size_t)max_ids, (size_t)count * 4);
     return count;
   } catch (const std::exception& e) { set_error(e.what()); return 0; }
+}
+
+// Additive: TextToIdsWithOffsets for a batch (CSR documents in; row-major ids / starts / ends [ndocs][max_ids] and counts out;
+// a row beyond its count stays untouched, like the arrays of the per-document call).  The same kernels as the
+// per-document call -- they take batches already -- over chunks of a few MB.  Returns the total number of ids, -1 on error.
+int64_t TextToIdsWithOffsetsBatch(void* h, const char* utf8, const int64_t* offsets, int64_t ndocs, int32_t* ids, int32_t* starts,
+                                  int32_t* ends, int32_t* counts, int max_ids, int unk) {
+  try {
+    g_last_error.clear();
+    Model* m = (Model*)h;
+    if (!check_batch_args(m, utf8, offsets, ndocs, max_ids)) return -1;
+    if (ndocs > 0 && (!ids || !starts || !ends || !counts)) { set_error("bad output arguments"); return -1; }
+    if (max_ids <= 0) { for (int64_t i = 0; i < ndocs; ++i) counts[i] = 0; return 0; }
+    const bool seg = m->has_seg;
+    if (!seg && !(m->has_wbd && m->lex_ok && m->T.charmap_one_to_one)) { set_error("offsets are not served for this lexer model"); return -1; }
+    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
+    CtxLease lease(m);
+    Slot& sl = lease.c->slots[0];
+    if (!ensure_stream(sl)) return -1;
+    int64_t total = 0;
+    const int64_t kChunkBytes = 8ll << 20, kMaxCells = 16ll << 20;
+    for (int64_t d0 = 0; d0 < ndocs;) {
+      int64_t d1 = d0, max_len = 0;
+      while (d1 < ndocs && (d1 == d0 || (offsets[d1 + 1] - offsets[d0] <= kChunkBytes && (d1 - d0 + 1) * (int64_t)max_ids <= kMaxCells))) {
+        max_len = std::max(max_len, offsets[d1 + 1] - offsets[d1]);
+        ++d1;
+      }
+      const int64_t nd = d1 - d0;
+      const int64_t b0 = offsets[d0] & ~(int64_t)3, b1 = offsets[d1];
+      const size_t nb = (size_t)(b1 - b0), span = (size_t)(b1 - offsets[d0]), cells = (size_t)nd * (size_t)max_ids;
+      if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve((size_t)nd + 1) || !sl.ids.reserve(3 * cells) || !sl.counts.reserve((size_t)nd + 1) ||
+          !sl.counter.reserve(2) || !sl.h_csr.reserve(3 * cells + (size_t)nd + 4))
+        return -1;
+      if (nb && !cuda_ok(cudaMemcpyAsync(sl.text.p, utf8 + b0, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return -1;
+      if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offsets + d0, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return -1;
+      int32_t* d_ids = sl.ids.p;
+      int nl = 0;
+      if (seg) {
+        if (!launch_segmentation(m, sl, sl.text.p - b0, sl.offsets.p, b1, nd, max_len, d_ids, sl.counts.p, d_ids + cells, d_ids + 2 * cells, max_ids, unk,
+                                 sl.stream, &nl))
+          return -1;
+      } else {
+        if (!sl.lex_cls.reserve(span + 8) || !sl.lex_ncps.reserve((size_t)nd) || !sl.lex_tri_count.reserve((size_t)nd) ||
+            !sl.lex_tri.reserve(6 * span + 8) || !sl.lex_boff.reserve(span + 8))
+          return -1;
+        LexLaunch X = make_lex_launch(sl, sl.text.p - b0, sl.offsets.p, offsets[d0], b1, nd, m->d_cls, 2);
+        X.boff_buf = sl.lex_boff.p;
+        if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return -1;
+        if (!cuda_ok(lex_wp_offsets_launch(X, d_ids, d_ids + cells, d_ids + 2 * cells, sl.counts.p, max_ids, unk, sl.stream, &nl), "post-pass launch"))
+          return -1;
+      }
+      g_launches += nl;
+      int32_t* hw = sl.h_csr.p;                                      // [3 * cells] rows, then [nd] counts, then the error word
+      if (!cuda_ok(cudaMemcpyAsync(hw, d_ids, 3 * cells * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H rows")) return -1;
+      if (!cuda_ok(cudaMemcpyAsync(hw + 3 * cells, sl.counts.p, (size_t)nd * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H counts")) return -1;
+      hw[3 * cells + (size_t)nd] = 0;
+      if (seg && !cuda_ok(cudaMemcpyAsync(hw + 3 * cells + (size_t)nd, sl.counter.p + 1, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H flag")) return -1;
+      if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
+      if (hw[3 * cells + (size_t)nd] != 0) { set_error("segmentation engine: scratch exhausted (code " + std::to_string(hw[3 * cells + (size_t)nd]) + ")"); return -1; }
+      for (int64_t i = 0; i < nd; ++i) {
+        int c = hw[3 * cells + (size_t)i];
+        if (c < 0 || c > max_ids) c = 0;
+        counts[d0 + i] = c;
+        total += c;
+        if (c > 0) {
+          const size_t row = (size_t)i * (size_t)max_ids, dst = (size_t)(d0 + i) * (size_t)max_ids;
+          std::memcpy(ids + dst, hw + row, (size_t)c * 4);
+          std::memcpy(starts + dst, hw + cells + row, (size_t)c * 4);
+          std::memcpy(ends + dst, hw + 2 * cells + row, (size_t)c * 4);
+        }
+      }
+      d0 = d1;
+    }
+    return total;
+  } catch (const std::exception& e) { set_error(e.what()); return -1; }
 }
 
 int TextToIdsWithOffsets_wp(void* h, const char* s, int n, int32_t* ids, int* starts, int* ends, const int max_ids, const int unk) {

@@ -58,7 +58,7 @@ int action_fn_start(const std::vector<int>& a) {
 
 }  // namespace
 
-bool build_lexer_tables(const LdbImage& ldb, LexerTables* T, std::string* err) {
+bool build_lexer_tables(const LdbImage& ldb, LexerTables* T, std::string* err, bool dense_wide) {
   const std::vector<int>* sec = ldb.conf().get(kFuncWbd);
   if (!sec) { *err = "no [wbd] section"; return false; }
   WbdConf conf;
@@ -126,41 +126,45 @@ bool build_lexer_tables(const LdbImage& ldb, LexerTables* T, std::string* err) {
   T->wide_states = T->NS >= 65535;
 
   // ---- dense table with the IW_ANY fallback folded in ----
+  const bool dense = dense_wide || !T->wide_states;
+  T->dense_on_host = dense;
   const size_t W = (size_t)NC + 1;
-  const size_t cells = (size_t)T->NS * W;
-  if (cells > ((size_t)1 << 33)) { *err = "dense transition table too large"; return false; }
-  // The table starts as "no transition" everywhere and only the arcs are written: a row is touched in
-  // full only when its state has an IW_ANY arc (the 9.3 GB table of bert_multi_cased has 0.03 % of its
-  // cells set).
-  auto fill_parallel = [&](auto* p, auto none) {
-    unsigned nt = cells < ((size_t)1 << 26) ? 1u : std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
-    std::vector<std::thread> th;
-    const size_t per = (cells + nt - 1) / nt;
-    for (unsigned t = 0; t < nt; ++t) {
-      const size_t lo = (size_t)t * per, hi = std::min(cells, lo + per);
-      if (lo >= hi) break;
-      th.emplace_back([=] { std::fill(p + lo, p + hi, none); });
-    }
-    for (auto& x : th) x.join();
-  };
-  if (T->wide_states) { T->trans32.resize(cells); fill_parallel(T->trans32.data(), (uint32_t)kNoState); }
-  else { T->trans16.resize(cells); fill_parallel(T->trans16.data(), (uint16_t)0xFFFF); }
-  auto fill_rows = [&](auto* table, auto none) {
-    using E = decltype(none);
-    for (int s = 0; s < n; ++s) {
-      E* row = table + (size_t)newid[s] * W;
-      for (int64_t k = A.arc_begin[s]; k < A.arc_begin[s + 1]; ++k) {
-        const Arc& a = A.arcs[k];
-        if (a.label < 0 || a.label >= NC) continue;   // a class no input can produce
-        row[a.label] = (E)(a.dst == kDeadState ? T->dead : newid[a.dst]);
+  if (dense) {
+    const size_t cells = (size_t)T->NS * W;
+    if (cells > ((size_t)1 << 33)) { *err = "dense transition table too large"; return false; }
+    // The table starts as "no transition" everywhere and only the arcs are written: a row is touched in
+    // full only when its state has an IW_ANY arc (the 9.3 GB table of bert_multi_cased has 0.03 % of its
+    // cells set).
+    auto fill_parallel = [&](auto* p, auto none) {
+      unsigned nt = cells < ((size_t)1 << 26) ? 1u : std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+      std::vector<std::thread> th;
+      const size_t per = (cells + nt - 1) / nt;
+      for (unsigned t = 0; t < nt; ++t) {
+        const size_t lo = (size_t)t * per, hi = std::min(cells, lo + per);
+        if (lo >= hi) break;
+        th.emplace_back([=] { std::fill(p + lo, p + hi, none); });
       }
-      if (cls_any < (uint32_t)NC && row[cls_any] != none) {
-        const E any = row[cls_any];
-        for (size_t c = 0; c < W; ++c) if (row[c] == none) row[c] = any;
+      for (auto& x : th) x.join();
+    };
+    if (T->wide_states) { T->trans32.resize(cells); fill_parallel(T->trans32.data(), (uint32_t)kNoState); }
+    else { T->trans16.resize(cells); fill_parallel(T->trans16.data(), (uint16_t)0xFFFF); }
+    auto fill_rows = [&](auto* table, auto none) {
+      using E = decltype(none);
+      for (int s = 0; s < n; ++s) {
+        E* row = table + (size_t)newid[s] * W;
+        for (int64_t k = A.arc_begin[s]; k < A.arc_begin[s + 1]; ++k) {
+          const Arc& a = A.arcs[k];
+          if (a.label < 0 || a.label >= NC) continue;   // a class no input can produce
+          row[a.label] = (E)(a.dst == kDeadState ? T->dead : newid[a.dst]);
+        }
+        if (cls_any < (uint32_t)NC && row[cls_any] != none) {
+          const E any = row[cls_any];
+          for (size_t c = 0; c < W; ++c) if (row[c] == none) row[c] = any;
+        }
       }
-    }
-  };
-  if (T->wide_states) fill_rows(T->trans32.data(), (uint32_t)kNoState); else fill_rows(T->trans16.data(), (uint16_t)0xFFFF);
+    };
+    if (T->wide_states) fill_rows(T->trans32.data(), (uint32_t)kNoState); else fill_rows(T->trans16.data(), (uint16_t)0xFFFF);
+  }
 
   // ---- the stored arcs in the new numbering ----
   {
@@ -180,6 +184,12 @@ bool build_lexer_tables(const LdbImage& ldb, LexerTables* T, std::string* err) {
       }
     }
     T->arc_begin[T->NS] = (int64_t)T->arc_label.size();
+    // IW_ANY: the fallback of every class the state has no arc for (FALexTools_t.h:266-270)
+    T->any_dst.assign((size_t)T->NS, kNoState);
+    if (cls_any < (uint32_t)NC)
+      for (int ns = 0; ns < T->NS; ++ns)
+        for (int64_t k = T->arc_begin[ns]; k < T->arc_begin[(size_t)ns + 1]; ++k)
+          if (T->arc_label[k] == cls_any) T->any_dst[ns] = T->arc_dst[k];
   }
 
   // ---- rule ids, actions ----

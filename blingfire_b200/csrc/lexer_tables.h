@@ -116,17 +116,33 @@ struct LexerTables {
 
   FastPath fast;
 
+  std::vector<uint32_t> any_dst;       // [NS] destination of the state's IW_ANY arc (the fallback of every other class), or kNoState
+  bool dense_on_host = true;           // trans16 / trans32 are filled (false: only the stored arcs; the device builds the table)
+
+  // the transition, from the dense table when it is here, else from the stored arcs (binary search + IW_ANY fallback)
   uint32_t next(uint32_t s, uint32_t c) const {
-    const size_t i = (size_t)s * (NC + 1) + c;
-    if (wide_states) return trans32[i];
-    const uint16_t v = trans16[i];
-    return v == 0xFFFF ? kNoState : v;
+    if (dense_on_host) {
+      const size_t i = (size_t)s * (NC + 1) + c;
+      if (wide_states) return trans32[i];
+      const uint16_t v = trans16[i];
+      return v == 0xFFFF ? kNoState : v;
+    }
+    int64_t lo = arc_begin[s], hi = arc_begin[(size_t)s + 1];
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) / 2;
+      if (arc_label[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    if (lo < arc_begin[(size_t)s + 1] && arc_label[lo] == c) return arc_dst[lo];
+    return any_dst[s];
   }
   bool is_final(uint32_t s) const { return s != kNoState && s >= first_final; }
 };
 
 // Returns false with *err set if the model cannot be served (malformed, or uses a feature
 // the reference itself would assert on).
-bool build_lexer_tables(const LdbImage& ldb, LexerTables* out, std::string* err);
+// dense_wide = false: a table with 32-bit entries (9.3 GB for bert_multi_cased) is not built on the host; the caller fills
+// the device copy from the stored arcs (capi.cu) and every host-side question goes through next().  Tables with 16-bit
+// entries (129 MB for bert_base_tok) are always built.
+bool build_lexer_tables(const LdbImage& ldb, LexerTables* out, std::string* err, bool dense_wide = true);
 
 }  // namespace bfb200

@@ -540,18 +540,25 @@ __global__ void wp_compact_kernel(const int32_t* __restrict__ ids, const int32_t
   }
 }
 
-// Exclusive prefix sum of per-document counts (int32 -> int64), one CTA: the input is a few
-// hundred thousand items per chunk and sits between two much longer kernels.
+// Exclusive prefix sum of per-document counts (int32 -> int64), one CTA: the input is a few ten thousand items per
+// chunk and sits between two much longer kernels.  16 consecutive items per thread (two int4 loads), a warp scan and a
+// scan of the warp totals per 16 384 items.
+constexpr int kScanPerThread = 16;
 __global__ void __launch_bounds__(1024) wp_scan_kernel(const int32_t* __restrict__ counts, int64_t* __restrict__ row_off, int64_t n) {
   __shared__ int64_t warp_sums[32];
   __shared__ int64_t carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (int64_t base = 0; base < n; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const int64_t v = i < n ? (int64_t)counts[i] : 0;
-    int64_t incl = v;
+  for (int64_t base = 0; base < n; base += 1024 * kScanPerThread) {
+    const int64_t i0 = base + (int64_t)threadIdx.x * kScanPerThread;
+    int32_t v[kScanPerThread];
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) v[k] = i0 + k < n ? counts[i0 + k] : 0;
+    int64_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) mine += v[k];
+    int64_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -569,11 +576,14 @@ __global__ void __launch_bounds__(1024) wp_scan_kernel(const int32_t* __restrict
       warp_sums[lane] = w;
     }
     __syncthreads();
-    const int64_t carry = carry_s;
-    const int64_t prefix = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + incl - v;
-    if (i < n) row_off[i] = prefix;
+    int64_t run = carry_s + (warp > 0 ? warp_sums[warp - 1] : 0) + incl - mine;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+      if (i0 + k < n) row_off[i0 + k] = run;
+      run += v[k];
+    }
     __syncthreads();
-    if (threadIdx.x == 1023) carry_s = prefix + v;
+    if (threadIdx.x == 1023) carry_s = run;
     __syncthreads();
   }
   if (threadIdx.x == 0) row_off[n] = carry_s;

@@ -8,6 +8,21 @@
 
 namespace bfb200 {
 
+// Host-only view of the automaton through LexerTables::next() (stored arcs when the dense table is not on the host):
+// wp_word runs over it at load time exactly as it runs over the dense table on the device.
+struct HostArcs {};
+template <>
+struct WpGlobal<HostArcs> {
+  const LexerTables* T;
+  const int32_t* tag_of_state;
+  uint32_t NC1, first_final, cls_caret, cls_dollar;
+  int max_token_length;
+};
+inline uint32_t wp_step(const WpGlobal<HostArcs>& g, uint32_t q, uint32_t c) {
+  const uint32_t d = g.T->next(q, c);
+  return d == kNoState ? kNone32 : d;
+}
+
 namespace {
 
 struct TopTok {
@@ -166,13 +181,12 @@ bool cuckoo_build(const std::vector<WpWordSlot>& keys, WpWords* W, std::vector<W
 // Fills the whole-word table: every class sequence within one group of top-level classes (at most max_len classes) for which
 // the function sub-grammar yields exactly one piece.  Candidates are the paths of the function automaton from
 // its two entry states; each is decided by wp_word itself.
-template <typename TE>
-void build_words(const LexerTables& T, const TE* trans, const TopGroups& G, const std::vector<uint32_t>& kind_of_group,
-                 WpBlob* out) {
+void build_words(const LexerTables& T, const TopGroups& G, const std::vector<uint32_t>& kind_of_group, WpBlob* out) {
+  using TE = HostArcs;
   const FastPath& F = T.fast;
   WpWords& W = out->words;
   WpGlobal<TE> g{};
-  g.trans = trans; g.tag_of_state = T.tag_of_state.data();
+  g.T = &T; g.tag_of_state = T.tag_of_state.data();
   g.NC1 = (uint32_t)T.NC + 1; g.first_final = T.first_final; g.cls_caret = T.cls_caret; g.cls_dollar = T.cls_dollar;
   g.max_token_length = T.max_token_length;
 
@@ -301,8 +315,7 @@ void build_wp_blob(const LexerTables& T, WpBlob* out) {
   }
 
   // ---- the whole-word table ----
-  if (T.wide_states) build_words<uint32_t>(T, T.trans32.data(), G, kind_of_group, out);
-  else build_words<uint16_t>(T, T.trans16.data(), G, kind_of_group, out);
+  build_words(T, G, kind_of_group, out);
   if (W.max_len == 0)
     for (uint32_t& k : kind_of_group) k &= ~(kKindWordRun | kKindWordOne);
   std::vector<uint32_t> kind((size_t)F.NT, 0);

@@ -114,6 +114,14 @@ int TextToWordsWithOffsetsWithModel(const char* pInUtf8Str, int InUtf8StrByteCou
 int TextToWordsWithOffsets(const char* pInUtf8Str, int InUtf8StrByteCount, char* pOutUtf8Str,
                            int* pStartOffsets, int* pEndOffsets, const int MaxOutUtf8StrByteCount);
 
+/* ADDITIVE.  TextToIdsWithOffsets (blingfiretokdll.cpp:1563-1609, -> _wp :1108-1314 / _sp :1349-1535 with offsets) for a
+ * batch: documents as CSR; pIds / pStarts / pEnds are row-major [DocCount][MaxIdsPerDoc], pCounts[i] = what the per-document
+ * call returns for document i; entries of a row beyond its count stay untouched.  Byte offsets count from the document's
+ * first byte, with the reference's conventions (end = last byte of the last character; -1 for the dummy prefix).
+ * Returns the total number of ids, -1 on error. */
+int64_t TextToIdsWithOffsetsBatch(void* ModelPtr, const char* pUtf8, const int64_t* pOffsets, int64_t DocCount, int32_t* pIds,
+                                  int32_t* pStarts, int32_t* pEnds, int32_t* pCounts, int MaxIdsPerDoc, int UnkId);
+
 /* ADDITIVE (not in the reference, which takes one document per call: blingfiretokdll.cpp:415-566).  TextToWords[WithModel]
  * for a batch: documents as CSR (pUtf8, pOffsets[DocCount+1]), strings as CSR.  The lexer and the string building
  * (:507-555) both run on the GPU.  hModel may be NULL (the default word breaker, like TextToWords).

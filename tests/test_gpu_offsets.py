@@ -112,6 +112,27 @@ def test_sp_offsets_vs_oracle(bf, name, unk):
     bf.free_model(h)
 
 
+@pytest.mark.parametrize("name,unk", [("bert_base_tok.bin", 100), ("bert_chinese.bin", 100), ("xlm_roberta_base.bin", 3), ("gpt2.bin", 0),
+                                      ("xlnet.bin", 0)])
+def test_offsets_batch_vs_oracle(bf, name, unk):
+    """The additive batch form of TextToIdsWithOffsets: row-major ids / starts / ends with untouched tails, per-document
+    counts, against the per-document oracle; a small cap; more documents than one chunk holds."""
+    h = bf.load_model(model_path(name))
+    o = Oracle()
+    ho = o.load(model_path(name))
+    docs = _sp_docs(5) + [b""] + read_lines("test.txt")[:1500]
+    for max_ids in (300, 4):
+        ids, st, en, counts = bf.text_to_ids_with_offsets_batch(h, docs, max_ids, unk)
+        for i, d in enumerate(docs):
+            n, oi, os_, oe = o.text_to_ids_with_offsets(ho, d, max_ids, unk)
+            assert counts[i] == n, (name, d[:40], int(counts[i]), n)
+            assert (ids[i, :n] == oi[:n]).all() and (st[i, :n] == os_[:n]).all(), (name, d[:40])
+            keep = [k for k in range(n) if os_[k] >= 0 or oe[k] == -1]         # (blingfiretokdll.cpp:1527, see test_offsets_vs_golden)
+            assert (en[i, keep] == oe[keep]).all(), (name, d[:40])
+            assert (ids[i, n:] == 0).all() and (st[i, n:] == 0).all() and (en[i, n:] == 0).all()
+    bf.free_model(h)
+
+
 def _split_via_capi(bf, fn_name, data, model, max_out):
     from _common import split_call
     L = bf.lib()

@@ -23,6 +23,11 @@ class Twin:
         L.twin_load.restype = ctypes.c_void_p
         L.twin_load.argtypes = [ctypes.c_char_p]
         L.twin_free.argtypes = [ctypes.c_void_p]
+        L.twin_load_sparse.restype = ctypes.c_void_p
+        L.twin_load_sparse.argtypes = [ctypes.c_char_p]
+        L.twin_blob_digest.restype = ctypes.c_uint64
+        L.twin_blob_digest.argtypes = [ctypes.c_void_p]
+        L.twin_dense_on_host.argtypes = [ctypes.c_void_p]
         L.twin_error.restype = ctypes.c_char_p
         L.twin_error.argtypes = [ctypes.c_void_p]
         L.twin_fast_ok.argtypes = [ctypes.c_void_p]
@@ -238,3 +243,25 @@ def test_memo_never_changes_an_id(twin, name, corpus):
         n, a = twin.ids_ex(h, d, 512, 7777, 640, 1)
         assert n == n0 and (a[:max(n, 0)] == a0[:max(n, 0)]).all(), d[:80]
     twin.lib.twin_free(h)
+
+
+def test_wide_model_without_the_dense_host_table(twin):
+    """LoadModel does not stage a table with 32-bit entries on the host (9.3 GB for bert_multi_cased): the grammar analysis,
+    the class groups and the word table come out of the stored arcs -- bit for bit what the dense table gives."""
+    import time
+    t0 = time.time()
+    hs = twin.lib.twin_load_sparse(model_path("bert_multi_cased.bin").encode())
+    t1 = time.time()
+    assert twin.lib.twin_error(hs) == b"" and twin.lib.twin_dense_on_host(hs) == 0 and twin.lib.twin_fast_ok(hs) == 1
+    hd = twin.load("bert_multi_cased.bin")
+    t2 = time.time()
+    assert twin.lib.twin_dense_on_host(hd) == 1
+    assert twin.lib.twin_info(hs, 13) == twin.lib.twin_info(hd, 13) > 50000
+    assert twin.lib.twin_blob_digest(hs) == twin.lib.twin_blob_digest(hd)
+    print(f"bert_multi_cased: host tables from the stored arcs {t1 - t0:.2f} s, with the dense table {t2 - t1:.2f} s")
+    twin.lib.twin_free(hs)
+    twin.lib.twin_free(hd)
+    # a narrow table is always dense on the host
+    hn = twin.lib.twin_load_sparse(model_path("bert_base_tok.bin").encode())
+    assert twin.lib.twin_dense_on_host(hn) == 1
+    twin.lib.twin_free(hn)

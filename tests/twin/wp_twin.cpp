@@ -37,6 +37,26 @@ void* twin_load(const char* path) {
   if (t->T.fast.ok && t->T.charmap_one_to_one) build_wp_blob(t->T, &t->blob);
   return t;
 }
+// the same model with the dense table left out on the host when it is wide (what LoadModel does): only the load-time
+// products can be asked for (twin_info, twin_blob_digest)
+void* twin_load_sparse(const char* path) {
+  Twin* t = new Twin();
+  if (!t->ldb.load_file(path)) { t->err = t->ldb.error(); return t; }
+  if (!build_lexer_tables(t->ldb, &t->T, &t->err, /*dense_wide=*/false)) return t;
+  if (t->T.fast.ok && t->T.charmap_one_to_one) build_wp_blob(t->T, &t->blob);
+  return t;
+}
+// FNV-1a-64 over the staged blob, the word table and its parameters
+uint64_t twin_blob_digest(void* h) {
+  Twin* t = (Twin*)h;
+  uint64_t x = 0xcbf29ce484222325ull;
+  auto eat = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; for (size_t i = 0; i < n; ++i) { x ^= b[i]; x *= 0x100000001b3ull; } };
+  eat(t->blob.bytes.data(), t->blob.bytes.size());
+  eat(t->blob.word_slots.data(), t->blob.word_slots.size() * sizeof(WpWordSlot));
+  eat(&t->blob.words.log2_size, 4); eat(&t->blob.words.cb, 4); eat(&t->blob.words.cpw, 4); eat(&t->blob.words.max_len, 4); eat(t->blob.words.mul, 36);
+  return x;
+}
+int twin_dense_on_host(void* h) { return ((Twin*)h)->T.dense_on_host ? 1 : 0; }
 void twin_free(void* h) { delete (Twin*)h; }
 const char* twin_error(void* h) { return ((Twin*)h)->err.c_str(); }
 int twin_fast_ok(void* h) { Twin* t = (Twin*)h; return t->err.empty() && t->T.fast.ok && t->T.charmap_one_to_one; }
