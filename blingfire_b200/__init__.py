@@ -53,6 +53,8 @@ def lib():
         L.TextToIdsWithOffsetsBatch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]
         L.TextToWordsBatch.restype = c_int64
         L.TextToWordsBatch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]
+        L.TextToSentencesBatch.restype = c_int64
+        L.TextToSentencesBatch.argtypes = L.TextToWordsBatch.argtypes
         L.TextToIdsBatchCsrU16.restype = c_int64
         L.TextToIdsBatchCsrU16.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int]
         L.TextToIdsBatchDevice.restype = c_int
@@ -179,7 +181,12 @@ def text_to_ids_with_offsets_batch(h, docs, max_len, unk=0):
     return ids, starts, ends, counts
 
 
-def text_to_words_batch(docs, h=None, raw=False):
+def text_to_sentences_batch(docs, h=None, raw=False):
+    """ADDITIVE: text_to_sentences[_with_model] for many documents in one call (TextToSentencesBatch)."""
+    return text_to_words_batch(docs, h, raw, _fn="TextToSentencesBatch")
+
+
+def text_to_words_batch(docs, h=None, raw=False, _fn="TextToWordsBatch"):
     """ADDITIVE: text_to_words[_with_model] for many documents in one call (TextToWordsBatch: lexer and string building on
     the GPU).  `docs`: str / bytes items, or a (uint8 buffer, int64 offsets) pair.  Returns the list of strings ("" where
     the per-document call returns "": bad UTF-8, empty input); with raw=True, (buffer, offsets, results) as numpy arrays."""
@@ -189,15 +196,16 @@ def text_to_words_batch(docs, h=None, raw=False):
     results = np.zeros(n, np.int32)
     cap = int(2 * len(buf) + n + 16)
     out = np.empty(cap, np.uint8)
-    r = lib().TextToWordsBatch(c_void_p(h) if h else None, buf.ctypes.data if len(buf) else None, offs.ctypes.data, n, out.ctypes.data, cap,
-                               out_offs.ctypes.data, results.ctypes.data)
+    fn = getattr(lib(), _fn)
+    r = fn(c_void_p(h) if h else None, buf.ctypes.data if len(buf) else None, offs.ctypes.data, n, out.ctypes.data, cap,
+           out_offs.ctypes.data, results.ctypes.data)
     if r < 0 and -r > cap:
         cap = int(-r)
         out = np.empty(cap, np.uint8)
-        r = lib().TextToWordsBatch(c_void_p(h) if h else None, buf.ctypes.data if len(buf) else None, offs.ctypes.data, n, out.ctypes.data,
-                                   cap, out_offs.ctypes.data, results.ctypes.data)
+        r = fn(c_void_p(h) if h else None, buf.ctypes.data if len(buf) else None, offs.ctypes.data, n, out.ctypes.data, cap,
+               out_offs.ctypes.data, results.ctypes.data)
     if r < 0:
-        raise RuntimeError(f"TextToWordsBatch failed: {last_error()}")
+        raise RuntimeError(f"{_fn} failed: {last_error()}")
     if raw:
         return out[:r], out_offs, results
     data = out[:r].tobytes()

@@ -1427,11 +1427,11 @@ int TextToWords(const char* s, int n, char* out, const int max_out) { return Tex
 //                   its string including the NUL
 //   out_offsets[i]  where that string starts in `out` (documents without one take no bytes); out_offsets[ndocs] = total
 // Returns the total bytes, or -total when `capacity` is too small (out_offsets and results are complete then), -1 on error.
-int64_t TextToWordsBatch(void* hModel, const char* utf8, const int64_t* offsets, int64_t ndocs, char* out, int64_t capacity,
-                         int64_t* out_offsets, int32_t* results) {
+static int64_t text_batch(bool sentences, void* hModel, const char* utf8, const int64_t* offsets, int64_t ndocs, char* out, int64_t capacity,
+                          int64_t* out_offsets, int32_t* results) {
   try {
     g_last_error.clear();
-    Model* m = hModel ? (Model*)hModel : default_model(0);
+    Model* m = hModel ? (Model*)hModel : default_model(sentences ? 1 : 0);
     if (!m) return -1;
     if (ndocs < 0 || !out_offsets || !results || (ndocs > 0 && (!utf8 || !offsets)) || (capacity > 0 && !out)) { set_error("bad batch arguments"); return -1; }
     if (!m->has_wbd || !m->lex_ok) { set_error("model has no lexer engine"); return -1; }
@@ -1462,7 +1462,7 @@ int64_t TextToWordsBatch(void* hModel, const char* utf8, const int64_t* offsets,
       if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return -1;
       int32_t* d_lens = sl.counts.p;
       int32_t* d_results = sl.ids.p;
-      if (!cuda_ok(lex_words_len_launch(X, d_lens, d_results, sl.stream), "words length launch")) return -1;
+      if (!cuda_ok(lex_words_len_launch(X, sentences, d_lens, d_results, sl.stream), "words length launch")) return -1;
       if (!cuda_ok(wp_scan_counts(d_lens, sl.row_off.p, nd, sl.stream), "scan")) return -1;
       g_launches += nl + 2;
       if (!cuda_ok(cudaMemcpyAsync(sl.h_row_off.p, sl.row_off.p, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, sl.stream), "D2H offsets")) return -1;
@@ -1473,7 +1473,7 @@ int64_t TextToWordsBatch(void* hModel, const char* utf8, const int64_t* offsets,
       if (total + nout > capacity) overflow = true;
       else if (nout > 0) {
         if (!sl.csr.reserve((size_t)(nout + 3) / 4 + 1)) return -1;
-        if (!cuda_ok(lex_words_write_launch(X, sl.row_off.p, d_results, reinterpret_cast<char*>(sl.csr.p), sl.stream), "words write launch")) return -1;
+        if (!cuda_ok(lex_words_write_launch(X, sentences, sl.row_off.p, d_results, reinterpret_cast<char*>(sl.csr.p), sl.stream), "words write launch")) return -1;
         g_launches += 1;
         if (!cuda_ok(cudaMemcpyAsync(out + total, sl.csr.p, (size_t)nout, cudaMemcpyDeviceToHost, sl.stream), "D2H text")) return -1;
         if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
@@ -1483,6 +1483,15 @@ int64_t TextToWordsBatch(void* hModel, const char* utf8, const int64_t* offsets,
     }
     return overflow ? -total : total;
   } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+int64_t TextToWordsBatch(void* hModel, const char* utf8, const int64_t* offsets, int64_t ndocs, char* out, int64_t capacity,
+                         int64_t* out_offsets, int32_t* results) {
+  return text_batch(false, hModel, utf8, offsets, ndocs, out, capacity, out_offsets, results);
+}
+// Additive: TextToSentences[WithModel] for a batch, same conventions (blingfiretokdll.cpp:163-355; sentences joined by '\n').
+int64_t TextToSentencesBatch(void* hModel, const char* utf8, const int64_t* offsets, int64_t ndocs, char* out, int64_t capacity,
+                             int64_t* out_offsets, int32_t* results) {
+  return text_batch(true, hModel, utf8, offsets, ndocs, out, capacity, out_offsets, results);
 }
 
 // blingfiretokdll.cpp:163-355.  One sentence per triple of the sentence-breaking lexer: it starts right

@@ -181,61 +181,108 @@ __device__ __forceinline__ int words_doc(const LexLaunch& p, int64_t doc, WordsD
 }
 __device__ __forceinline__ int words_cp_off(const WordsDoc& d, int i) { return i >= d.ncps ? d.nbytes : d.boff[i]; }
 
+// __FAIsWhiteSpace__ (blingfiretokdll.h:17-21) of the (valid) code point at byte b; U+0000 was replaced by U+0020 before
+// the lexer ran (:237)
+__device__ __forceinline__ bool words_white_at(const uint8_t* s, int b) {
+  const uint32_t c0 = s[b];
+  uint32_t cp;
+  if (c0 < 0x80) cp = c0;
+  else if ((c0 & 0xE0) == 0xC0) cp = ((c0 & 0x1Fu) << 6) | (s[b + 1] & 0x3Fu);
+  else if ((c0 & 0xF0) == 0xE0) cp = ((c0 & 0x0Fu) << 12) | ((s[b + 1] & 0x3Fu) << 6) | (s[b + 2] & 0x3Fu);
+  else cp = ((c0 & 0x07u) << 18) | ((s[b + 1] & 0x3Fu) << 12) | ((s[b + 2] & 0x3Fu) << 6) | (s[b + 3] & 0x3Fu);
+  if (cp == 0) cp = 0x20;
+  return cp <= 0x20 || cp == 0xa0 || (cp >= 0x2000 && cp <= 0x200f) || cp == 0x202f || cp == 0x205f || cp == 0x2060 ||
+         cp == 0x2420 || cp == 0x2424 || cp == 0x3000 || cp == 0xfeff;
+}
+
+// The pieces of a document's output string, in order: f(b0, b1) for the bytes [b0, b1) of each.  false: malformed triples.
+//   words      every token that is not IGNORE (blingfiretokdll.cpp:507-552)
+//   sentences  one per triple, from right after the previous one's end to this one's To, leading white space dropped
+//              (FAGetFirstNonWhiteSpace, :138-150), empty ones skipped; what follows the last boundary is the last sentence
+//              (:257-338)
+template <bool kSentences, typename F>
+__device__ __forceinline__ bool words_pieces(const WordsDoc& d, F f) {
+  if (!kSentences) {
+    for (int i = 0; i < d.rn; i += 3) {
+      if (d.tri[i] == 4) continue;                                  // WBD_IGNORE_TAG (:511-514)
+      const int from = d.tri[i + 1], to = d.tri[i + 2];
+      if (from < 0 || from > d.ncps || to >= d.ncps || to < -1) return false;
+      const int b0 = words_cp_off(d, from), b1 = words_cp_off(d, to + 1);
+      f(b0, b1 > b0 ? b1 : b0);
+    }
+    return true;
+  }
+  int prev_end = -1;
+  auto sentence = [&](int from, int to) {
+    int first = from;
+    while (first <= to && words_white_at(d.text, words_cp_off(d, first))) ++first;
+    if (first > to) return;
+    f(words_cp_off(d, first), words_cp_off(d, to + 1));
+  };
+  for (int i = 0; i < d.rn; i += 3) {
+    const int to = d.tri[i + 2];
+    if (to < -1 || to >= d.ncps) return false;
+    sentence(prev_end + 1, to);
+    prev_end = to;
+  }
+  if (prev_end + 1 < d.ncps) sentence(prev_end + 1, d.ncps - 1);
+  return true;
+}
+
+template <bool kSentences>
 __global__ void __launch_bounds__(128) lex_words_len_kernel(const LexLaunch p, int32_t* lens, int32_t* results) {
   const int64_t doc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (doc >= p.ndocs) return;
   WordsDoc d;
   int r = words_doc(p, doc, &d), total = 0;
   if (r == 1) {
-    int words = 0;
-    for (int i = 0; i < d.rn && r == 1; i += 3) {
-      if (d.tri[i] == 4) continue;                                  // WBD_IGNORE_TAG (:511-514)
-      const int from = d.tri[i + 1], to = d.tri[i + 2];
-      if (from < 0 || from > d.ncps || to >= d.ncps || to < -1) { r = -1; break; }
-      const int b0 = words_cp_off(d, from), b1 = words_cp_off(d, to + 1);
-      total += (b1 > b0 ? b1 - b0 : 0) + (words > 0 ? 1 : 0);
-      ++words;
-    }
-    total += 1;                                                     // the NUL (:555)
+    int pieces = 0;
+    if (!words_pieces<kSentences>(d, [&](int b0, int b1) { total += (b1 - b0) + (pieces > 0 ? 1 : 0); ++pieces; })) r = -1;
+    total += 1;                                                     // the NUL (:555, :343)
   }
   lens[doc] = r == 1 ? total : 0;
   results[doc] = r == 1 ? total : r;
 }
 
+template <bool kSentences>
 __global__ void __launch_bounds__(128) lex_words_write_kernel(const LexLaunch p, const int64_t* out_off, const int32_t* results, char* out) {
   const int64_t doc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (doc >= p.ndocs || results[doc] <= 0) return;
   WordsDoc d;
   if (words_doc(p, doc, &d) != 1) return;
   char* o = out + out_off[doc];
-  int words = 0;
-  for (int i = 0; i < d.rn; i += 3) {
-    if (d.tri[i] == 4) continue;
-    const int b0 = words_cp_off(d, d.tri[i + 1]), b1 = words_cp_off(d, d.tri[i + 2] + 1);
-    if (words > 0) *o++ = ' ';
+  int pieces = 0;
+  const char sep = kSentences ? '\n' : ' ', repl = kSentences ? ' ' : '_';
+  words_pieces<kSentences>(d, [&](int b0, int b1) {
+    if (pieces > 0) *o++ = sep;
     for (int b = b0; b < b1; ++b) {
       char c = (char)d.text[b];
-      if (c == 0) c = 0x20;
-      if (c == ' ') c = '_';
+      if (c == 0) c = 0x20;                                         // U+0000 -> U+0020 (:482, :237)
+      if (c == sep) c = repl;                                       // the delimiter inside a piece (:546, :292)
       *o++ = c;
     }
-    ++words;
-  }
+    ++pieces;
+  });
   *o = 0;
 }
 
 }  // namespace
 
 #ifndef BF_SIMT_HOST                       // tests/simt compiles the kernels above for the host
-cudaError_t lex_words_len_launch(const LexLaunch& p, int32_t* lens, int32_t* results, cudaStream_t stream) {
+cudaError_t lex_words_len_launch(const LexLaunch& p, bool sentences, int32_t* lens, int32_t* results, cudaStream_t stream) {
   if (p.ndocs <= 0) return cudaSuccess;
   if (!p.boff_buf) return cudaErrorInvalidValue;
-  lex_words_len_kernel<<<(int)((p.ndocs + 127) / 128), 128, 0, stream>>>(p, lens, results);
+  const int grid = (int)((p.ndocs + 127) / 128);
+  if (sentences) lex_words_len_kernel<true><<<grid, 128, 0, stream>>>(p, lens, results);
+  else lex_words_len_kernel<false><<<grid, 128, 0, stream>>>(p, lens, results);
   return cudaGetLastError();
 }
-cudaError_t lex_words_write_launch(const LexLaunch& p, const int64_t* out_off, const int32_t* results, char* out, cudaStream_t stream) {
+cudaError_t lex_words_write_launch(const LexLaunch& p, bool sentences, const int64_t* out_off, const int32_t* results, char* out,
+                                   cudaStream_t stream) {
   if (p.ndocs <= 0) return cudaSuccess;
-  lex_words_write_kernel<<<(int)((p.ndocs + 127) / 128), 128, 0, stream>>>(p, out_off, results, out);
+  const int grid = (int)((p.ndocs + 127) / 128);
+  if (sentences) lex_words_write_kernel<true><<<grid, 128, 0, stream>>>(p, out_off, results, out);
+  else lex_words_write_kernel<false><<<grid, 128, 0, stream>>>(p, out_off, results, out);
   return cudaGetLastError();
 }
 

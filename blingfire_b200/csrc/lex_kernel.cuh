@@ -44,7 +44,9 @@ cudaError_t lex_wp_offsets_launch(const LexLaunch& p, int32_t* ids, int32_t* sta
 
 // TextToWords for a batch (needs p.boff_buf): bytes of every document's output string incl. its NUL (0 when the document has
 // none) and what TextToWords returns for it; then the strings themselves at out + out_off[doc]
-cudaError_t lex_words_len_launch(const LexLaunch& p, int32_t* lens, int32_t* results, cudaStream_t stream);
-cudaError_t lex_words_write_launch(const LexLaunch& p, const int64_t* out_off, const int32_t* results, char* out, cudaStream_t stream);
+// (sentences: TextToSentences' string instead, blingfiretokdll.cpp:257-338)
+cudaError_t lex_words_len_launch(const LexLaunch& p, bool sentences, int32_t* lens, int32_t* results, cudaStream_t stream);
+cudaError_t lex_words_write_launch(const LexLaunch& p, bool sentences, const int64_t* out_off, const int32_t* results, char* out,
+                                   cudaStream_t stream);
 
 }  // namespace bfb200

@@ -132,6 +132,10 @@ int64_t TextToIdsWithOffsetsBatch(void* ModelPtr, const char* pUtf8, const int64
  * error (BlingFireB200LastError). */
 int64_t TextToWordsBatch(void* hModel, const char* pUtf8, const int64_t* pOffsets, int64_t DocCount, char* pOut,
                          int64_t Capacity, int64_t* pOutOffsets, int32_t* pResults);
+/* ADDITIVE.  The same for TextToSentences[WithModel] (blingfiretokdll.cpp:163-355): one string per document, its sentences
+ * joined by '\n'; hModel NULL = the default sentence breaker. */
+int64_t TextToSentencesBatch(void* hModel, const char* pUtf8, const int64_t* pOffsets, int64_t DocCount, char* pOut,
+                             int64_t Capacity, int64_t* pOutOffsets, int32_t* pResults);
 
 /* blingfiretokdll.h:33 / :31-32 / :29-30 / :27-28, blingfiretokdll.cpp:398-401 / :378-381 / :364-368 / :163-355.
  * Splits a paragraph into sentences, '\n'-joined (a '\n' inside a sentence becomes ' '); same return

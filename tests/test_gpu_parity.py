@@ -313,6 +313,26 @@ def test_text_to_words_batch(bf, oracle):
     assert r == -int(sum(w[0] for w in want[:100])) and oo[100] == -r and (rr == [w[0] for w in want[:100]]).all()
 
 
+def test_text_to_sentences_batch(bf, oracle):
+    """The additive batch form of TextToSentences against the per-document reference semantics: default model and an
+    sbd.bin handle, paragraphs of several sentences, leading white space, embedded newlines and NULs, invalid input."""
+    lines = read_lines("test.txt", drop_empty=False)[:3000]
+    docs = [b" ".join(lines[i:i + 5]) for i in range(0, len(lines), 5)]
+    docs += [b"", b"  Hello there.  How are you?\nFine, thanks!  ", b"Dr. Smith went to Washington. He arrived at 5 p.m. It was late!", b"\xff\xfe", b"a\x00b. c\nd.",
+             b"   ", b"No end", "Это первое. А это второе? Да!".encode(), b"x" * 3000] + read_lines("test.multi.txt")[:800]
+    ho = oracle.load(model_path("sbd.bin"))
+    h = bf.load_model(model_path("sbd.bin"))
+    for handle in (None, h):
+        out, out_offs, results = bf.text_to_sentences_batch(bf.make_csr(docs), h=handle, raw=True)
+        data = out.tobytes()
+        for i, d in enumerate(docs):
+            n2, s2, _, _ = oracle.split("sentences", ho, d, 2 * len(d) + 16)
+            assert results[i] == n2, (d[:40], int(results[i]), n2)
+            assert data[out_offs[i]:out_offs[i + 1]] == (s2 if n2 > 0 else b""), d[:40]
+    assert bf.text_to_sentences_batch(["Hello there. How are you?"]) == ["Hello there.\nHow are you?"]
+    bf.free_model(h)
+
+
 def test_text_to_words_with_model_multilingual(bf, oracle):
     import ctypes
     L = bf.lib()
