@@ -14,7 +14,10 @@ from _common import GOLDEN, Oracle, fnv1a64_ids, have_data, model_path, read_lin
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_data(), reason="data/ not staged")]
 
-SP_MODELS = [("gpt2.bin", 0), ("xlm_roberta_base.bin", 3), ("roberta.bin", 3), ("xlnet.bin", 0), ("bpe_example.bin", 0)]
+# every [pos-dict] model the reference ships (ldbsrc/ldb): BPE-opt, BPE with merge ranks, plain BPE; Unigram with and without
+# a charmap, the 100k-vocabulary ones (laser100k, uri100k)
+SP_MODELS = [("gpt2.bin", 0), ("xlm_roberta_base.bin", 3), ("roberta.bin", 3), ("xlnet.bin", 0), ("bpe_example.bin", 0),
+             ("xlnet_nonorm.bin", 0), ("laser100k.bin", 1), ("uri100k.bin", 1)]
 
 
 @pytest.fixture(scope="module")
