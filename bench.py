@@ -347,7 +347,7 @@ def run_config(name, args, rank, local_rank, world, dev, full):
         if k == 0:
             cold[1].record(stream)
     torch.cuda.synchronize()
-    cold_ms = cold[0].elapsed_time(cold[1]) if args.warmup > 0 else None
+    cold_ms = cold[0].elapsed_time(cold[1]) if (args.warmup > 0 and world == 1) else None   # (N > 1: the first step also sets NCCL up)
     if world > 1:
         dist.barrier()
     launches0 = bf.kernel_launches()
