@@ -322,6 +322,8 @@ def run_config(name, args, rank, local_rank, world, dev, full):
     d_ids = torch.empty((n, max_ids), dtype=torch.int32, device=dev)
     d_counts = torch.zeros(n, dtype=torch.int32, device=dev)
     stats = torch.zeros(3, dtype=torch.int64, device=dev)
+    stats_base = torch.tensor([n, nbytes, 0], dtype=torch.int64, device=dev)   # (device-side: a Python scalar written into a
+                                                                               # CUDA tensor is a pageable copy that waits for the stream)
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream()
 
@@ -330,7 +332,8 @@ def run_config(name, args, rank, local_rank, world, dev, full):
                                     d_counts.data_ptr(), max_ids, unk, stream.cuda_stream, max_doc_bytes=max_doc)
         if world > 1:
             # the path's only exchange: per-rank {docs, bytes, tokens}
-            stats[0] = n; stats[1] = nbytes; stats[2] = d_counts.sum()
+            stats.copy_(stats_base)
+            stats[2:3] += d_counts.sum(dtype=torch.int64)
             dist.all_reduce(stats)
 
     sampler = ClockSampler(local_rank)
