@@ -723,7 +723,9 @@ int64_t chunk_docs(const int64_t* offsets, int64_t doc0, int64_t ndocs_total, in
   // the generic lexer keeps 26 scratch bytes per input byte (classes + triples)
   // chunk size of the host pipeline; BLINGFIRE_B200_CHUNK_MB overrides it (tuning knob)
   static const int64_t env_mb = [] { const char* e = std::getenv("BLINGFIRE_B200_CHUNK_MB"); return e ? std::atoll(e) : 0ll; }();
-  const int64_t kMaxBytes = engine == 2 ? (8ll << 20) : ((env_mb > 0 ? env_mb : 16) << 20);
+  // (measured, tools/e2e_sweep.py / tools/e2e_trace.sh: the fused WordPiece kernel is fastest end to end with 16 MB chunks, the
+  // segmentation kernels -- longer, less even documents per warp -- with 32 MB)
+  const int64_t kMaxBytes = engine == 2 ? (8ll << 20) : ((env_mb > 0 ? env_mb : (engine == 3 ? 32 : 16)) << 20);
   const int64_t kMaxIdsCells = 160ll << 20;     // 640 MB of int32 per slot
   const int64_t max_docs = std::max<int64_t>(1, kMaxIdsCells / std::max(1, max_ids));
   int64_t d = doc0;
