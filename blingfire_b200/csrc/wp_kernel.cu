@@ -443,54 +443,21 @@ __global__ void __launch_bounds__(kThreads, 2) wp_tokenize_kernel(const WpLaunch
             const int cnt = __popc(dcd.start_mask);
             const int incl = warp_incl_scan(cnt, lane);
             int idx = m + incl - cnt;
-            // the top-level class of the position before this lane's first one: the last position of the nearest earlier
-            // lane that has any, else the position before the block
-            const unsigned hb = __ballot_sync(0xffffffffu, cnt != 0);
-            uint32_t xs[4];
-            unsigned my_last = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              xs[k] = 0;
               if (dcd.start_mask & (1u << k)) {
                 const uint32_t cp = dcd.cp[k];
-                xs[k] = cp < 128 ? top.ascii_clsx[cp] : __ldg(p.clsx_of_cp + cp);
-                my_last = xs[k] >> 16;
-              }
-            }
-            const unsigned before = hb & lanemask_lt();
-            unsigned tp = __shfl_sync(0xffffffffu, my_last, before ? 31 - __clz((int)before) : 0);
-            if (!before) tp = prev_tc;
-            // classes out, events of this lane's positions in registers (as in the all-ASCII blocks)
-            unsigned sv[4];
-            int nevl = 0;
-            const int idx0 = idx;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              sv[k] = 0;
-              if (dcd.start_mask & (1u << k)) {
-                const unsigned tc = xs[k] >> 16;
-                w.cls[idx] = (uint16_t)xs[k];
-                w.meta[idx] = (uint8_t)tc;
+                const uint32_t x = cp < 128 ? top.ascii_clsx[cp] : __ldg(p.clsx_of_cp + cp);
+                w.cls[idx] = (uint16_t)x;
+                w.meta[idx] = (uint8_t)(x >> 16);
                 w.ids_at[idx] = kNoPiece;
-                sv[k] = idx == 0 ? (unsigned)kSyncStart : (unsigned)top.sync_start[(tp << sh) | tc];
-                nevl += sv[k] != 0;
-                tp = tc;
                 ++idx;
               }
             }
-            const int e_incl = warp_incl_scan(nevl, lane);
-            int ei = w.nev + e_incl - nevl;
-            idx = idx0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (dcd.start_mask & (1u << k)) {
-                if (sv[k]) w.ev[ei++] = (uint16_t)((unsigned)idx | ((sv[k] & kSyncStart) << 15));
-                ++idx;
-              }
-            }
-            w.nev += __shfl_sync(0xffffffffu, e_incl, 31);
             const int m1 = m + __shfl_sync(0xffffffffu, incl, 31);
-            if (hb) prev_tc = __shfl_sync(0xffffffffu, my_last, 31 - __clz((int)hb));
+            __syncwarp();
+            gen_events(w, top, m, m1, lane);
+            if (m1 > 0) prev_tc = w.meta[m1 - 1];
             m = m1;
           }
           ub += kBlockBytes;
