@@ -20,7 +20,7 @@ namespace {
 // whole document to sp_doc_generic.
 // =====================================================================================
 constexpr int kBWarps = 8;                 // per CTA
-constexpr int kBCtasPerSm = 2;
+constexpr int kBCtasPerSm = 3;
 constexpr int kBWin = 512;                 // symbols in the window
 constexpr int kBLaneArcs = 48;             // lane-serial segments: at most this many listed arcs ...
 constexpr int kBMaxLen = 64;               // ... and symbols (intermediate[] is one 64-bit register)
@@ -29,7 +29,9 @@ constexpr int kBCoopArcs = 512;            // warp-cooperative segments: arcs so
 constexpr unsigned kBUnclaimed = 0xFFFFFu; // ordinal of "no arc claimed from this start"
 
 struct BWork {
-  uint32_t* scratch;    // [32][kBLaneArcs] lane-interleaved sorted keys; or kBCoopArcs 64-bit keys
+  uint32_t* scratch;    // [32][kBLaneArcs] lane-interleaved sorted keys; or kBCoopArcs 64-bit keys.  GLOBAL memory (the warp's
+                        // arena), like `order`: with the segment memo the hard pass runs for a fraction of the segments, and
+                        // the 7.5 KB they took per warp in shared memory kept the kernel at 16 warps per SM
   int32_t* ids_at;      // [kBWin] claim state {ordinal, tos}, then the token id, at token starts
   uint32_t* mark;       // [kBWin/32] bit p: a token starts at p
   uint16_t* sym;        // [kBWin] alphabet indices
@@ -39,20 +41,21 @@ struct BWork {
   uint32_t* cnt;        // [32] arcs listed per slot; [32] = slots that cannot be served lane-serially
   uint8_t* order;       // [kBLaneArcs][32] list index of the arc of rank r
 };
-constexpr int kBWorkBytes = 4 * 32 * kBLaneArcs + 4 * kBWin + 4 * (kBWin / 32) + 2 * kBWin + 2 * (kBWin / 2 + 8) + 4 * kBWin + 4 * 36 + 32 * kBLaneArcs;
+constexpr int kBWorkBytes = 4 * kBWin + 4 * (kBWin / 32) + 2 * kBWin + 2 * (kBWin / 2 + 8) + 4 * kBWin + 4 * 36;
+constexpr int kBGlobalBytes = 4 * 32 * kBLaneArcs + 32 * kBLaneArcs;   // scratch + order, at the start of the warp's private arc region
 static_assert(kBWorkBytes % 16 == 0 && 8 * kBCoopArcs <= 4 * 32 * kBLaneArcs && kBLaneArcs <= 64 && kBMaxLen <= 64 && kBWin <= 1024, "workspace layout");
 
-__device__ inline BWork make_bwork(uint8_t* b) {
+__device__ inline BWork make_bwork(uint8_t* b, uint8_t* g) {
   BWork w;
-  w.scratch = (uint32_t*)b; b += 4 * 32 * kBLaneArcs;
+  w.scratch = (uint32_t*)g;
+  w.order = g + 4 * 32 * kBLaneArcs;
   w.ids_at = (int32_t*)b; b += 4 * kBWin;
   w.mark = (uint32_t*)b; b += 4 * (kBWin / 32);
   w.sym = (uint16_t*)b; b += 2 * kBWin;
   w.seg = (uint16_t*)b; b += 2 * (kBWin / 2 + 8);
   w.hard_a = (uint16_t*)b; b += 2 * kBWin;
   w.hard_b = (uint16_t*)b; b += 2 * kBWin;
-  w.cnt = (uint32_t*)b; b += 4 * 36;
-  w.order = b;
+  w.cnt = (uint32_t*)b;
   return w;
 }
 
@@ -99,8 +102,8 @@ __device__ bool bpe_coop(const SpModelDev& m, const BWork& w, const ArcScratch& 
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(w.scratch);
   int P = 1; while (P < total) P <<= 1;
   if (P > kBCoopArcs) {                                        // (P is a power of two)
-    if ((int64_t)P > 2 * scratch.priv_cap) return false;
-    keys = reinterpret_cast<unsigned long long*>(scratch.priv);
+    if ((int64_t)P > 2 * (scratch.priv_cap - kBGlobalBytes / 16)) return false;
+    keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(scratch.priv) + kBGlobalBytes);
   }
   __syncwarp();
   for (int s0 = 0; s0 < L; s0 += 32) {

@@ -42,10 +42,10 @@ __global__ void __launch_bounds__(kBWarps * 32, kBCtasPerSm) sp_bpe_kernel(const
 #endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * kBWarps + warp;
-  const BWork w = make_bwork(smem + (size_t)warp * kBWorkBytes);
   uint8_t* my_arena = p.arena + (size_t)gwarp * p.arena_stride;
   Work wa = make_work(my_arena, p.arena_cap, p.starts != nullptr);
   const ArcScratch scratch = make_scratch(p, my_arena, error_flag);
+  const BWork w = make_bwork(smem + (size_t)warp * kBWorkBytes, reinterpret_cast<uint8_t*>(scratch.priv));
   const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
   const uint16_t delim = __ldg(m.sym_of_cp + kSpDelim);
   const bool fast_model = p.starts == nullptr && m.use_raw_bytes && m.norm_count == nullptr && !m.delim_inside_tokens &&
