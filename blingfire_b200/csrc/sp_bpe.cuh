@@ -20,7 +20,7 @@ namespace {
 // whole document to sp_doc_generic.
 // =====================================================================================
 constexpr int kBWarps = 8;                 // per CTA
-constexpr int kBCtasPerSm = 3;
+constexpr int kBCtasPerSm = 4;
 constexpr int kBWin = 512;                 // symbols in the window
 constexpr int kBLaneArcs = 48;             // lane-serial segments: at most this many listed arcs ...
 constexpr int kBMaxLen = 64;               // ... and symbols (intermediate[] is one 64-bit register)
