@@ -41,7 +41,11 @@ int GetBlingFireTokVersion(void);
 
 /* blingfiretokdll.h:48, blingfiretokdll.cpp:1077-1094.  Loads a compiled .bin LDB, flattens
  * its automata and uploads them to the current CUDA device.  Returns an opaque handle,
- * NULL on any failure (missing file, malformed image, CRC mismatch, unsupported model). */
+ * NULL on any failure (missing file, malformed image, CRC mismatch, unsupported model).
+ * The handle also owns run-time state the reference does not have: a device-resident table of words (WordPiece models)
+ * or segments (byte-BPE models) the kernels have already resolved, which they extend as they meet new ones.  It is a memo
+ * of the reference's own algorithm: results never depend on its content, only the speed does (the first pass over new
+ * text is slower than the following ones); it is bounded (64-128 MB per handle) and freed by FreeModel. */
 void* LoadModel(const char* pszLdbFileName);
 
 /* blingfiretokdll.h:47, blingfiretokdll.cpp:1055-1071.  Same, from a memory image (copied). */
