@@ -291,7 +291,7 @@ BF_HD WpWordHit wp_words_find(const WpWords& W, const uint32_t kw[8], bool wide)
   bool m2 = (((b.x ^ kw[0]) | (b.y ^ kw[1]) | (b.z ^ kw[2]) | (b.w ^ kw[3])) == 0) && (bi.w & kSlotValid);
   const uint4* sm = m1 ? s1 : s2;
   if (wide) {                    // (warp-uniform) the upper halves of the keys
-    const uint4 c = s1[2], d = s2[2];
+    const uint4 c = __ldcg(s1 + 2), d = __ldcg(s2 + 2);      // (second sector: from L2 -- see below)
     m1 = m1 && (((c.x ^ kw[4]) | (c.y ^ kw[5]) | (c.z ^ kw[6]) | (c.w ^ kw[7])) == 0);
     m2 = m2 && (((d.x ^ kw[4]) | (d.y ^ kw[5]) | (d.z ^ kw[6]) | (d.w ^ kw[7])) == 0);
     sm = m1 ? s1 : s2;
@@ -300,7 +300,9 @@ BF_HD WpWordHit wp_words_find(const WpWords& W, const uint32_t kw[8], bool wide)
   r.id[0] = (int32_t)(m1 ? ai.x : bi.x); r.id[1] = (int32_t)(m1 ? ai.y : bi.y); r.id[2] = (int32_t)(m1 ? ai.z : bi.z);
   r.offs_hi = 0; r.id[3] = r.id[4] = r.id[5] = 0;
   if ((r.meta & 7u) > 3u) {      // rare: more than three pieces
-    const uint4 e = sm[3];
+    // The first sector (key, ids, meta) is one snapshot: a valid meta in it means the writer's earlier stores are in it too.
+    // The second sector is read on its own, so it must not come from an L1 copy older than that snapshot: read it from L2.
+    const uint4 e = __ldcg(sm + 3);
     r.id[3] = (int32_t)e.x; r.id[4] = (int32_t)e.y; r.id[5] = (int32_t)e.z; r.offs_hi = e.w;
   }
 #else
