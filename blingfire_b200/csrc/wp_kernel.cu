@@ -5,20 +5,24 @@
 // (blingfiretokdll.cpp:1108-1314): FAStrUtf8ToArray -> FANormalize -> FALexTools_t::Process
 // (with the nested FnTokWord call) -> tiling/UNK post-pass -> MaxIdsArrLength truncation.
 //
-// Mapping (DESIGN.md has the derivation and the exactness argument):
+// Mapping (DESIGN.md 3 has the derivation and the exactness argument):
 //   * persistent CTAs, one document per WARP at a time, documents handed out by an atomic
 //     counter (ragged lengths balance themselves);
-//   * the small hot part of the model (top-level automaton, class tables, the two hottest
-//     transition rows) is staged ONCE per CTA into shared memory by a bulk async copy
+//   * the small hot part of the model (top-level automaton, ASCII class table, the pair table of sync points and
+//     class groups, the per-class memo kinds) is staged ONCE per CTA into shared memory by a bulk async copy
 //     (cp.async.bulk + mbarrier, the 1-D TMA path; SASS: UBLKCP);
-//   * bytes are read as coalesced 32-bit words (uchar4 per lane, 128 B per warp step), UTF-8
-//     is decoded and validated in registers, code points are compacted with a warp scan and
-//     mapped to classes (ASCII from shared memory, the rest from the L2-resident class map);
-//   * a ballot over the class pairs marks "sync points" no top-level match can cross; each
-//     lane then owns one chunk between sync points and runs the reference's loops verbatim
-//     (wp_core.cuh), gathering from the dense state x class table in HBM;
-//   * ids are written position-indexed in shared memory and compacted in order with
-//     ballot + popc into the output row.
+//   * bytes are read as coalesced 32-bit words (uchar4 per lane, 128 B per warp step).  An all-ASCII block is
+//     classified from shared memory and its EVENTS (positions where a chunk may start: no top-level match can cross,
+//     or where the group of top-level classes changes) are made in registers, four positions per lane; other blocks
+//     are decoded and validated strictly (FAUtf8ToInt), compacted with a warp scan, classified from the L2-resident
+//     class map;
+//   * one lane per event turns events into chunks; the load-time memo of the lexer loops (wp_core.cuh, wp_model.cpp)
+//     says per chunk: emits nothing / one word for the table / run the loops;
+//   * one lane per word looks the packed class sequence up in the two-choice word table in HBM (vocabulary words placed
+//     at load time, multi-piece words added at run time); what it does not hold runs the reference's loops verbatim
+//     (gathers from the dense state x class table), one lane per chunk, and is added to the table;
+//   * ids are written position-indexed in shared memory and compacted in order (four positions per lane, warp scan)
+//     into the output row.
 #include "wp_kernel.cuh"
 
 namespace bfb200 {
