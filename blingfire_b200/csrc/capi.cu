@@ -1091,6 +1091,49 @@ int TextToIds(void* h, const char* s, int n, int32_t* ids, const int max_ids, co
   Model* m = (Model*)h;
   if (m->engine == 0) { set_error("no GPU engine for this model type"); return 0; }
   if (max_ids <= 0 || !ids) return 0;
+  if (n <= (32 << 10) && max_ids <= 8192) {
+    // One short document: ONE copy in (offsets and text together, from the context's pinned buffer), the engine's kernels,
+    // ONE copy out (the id row and its count together), one synchronisation.  The batch pipeline's chunking, scan,
+    // compaction and two round trips are for batches; a call still costs a launch and two small copies.
+    try {
+      if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return 0;
+      CtxLease lease(m);
+      Slot& sl = lease.c->slots[0];
+      if (!ensure_stream(sl)) return 0;
+      const size_t tb = ((size_t)n + 3) & ~(size_t)3;
+      const size_t in_words = 4 + (tb + 64) / 4, out_words = (size_t)max_ids + 4;
+      if (!lease.c->h_words.reserve(in_words + out_words) || !sl.text.reserve(16 + tb + 64) || !sl.ids.reserve(out_words) || !sl.counter.reserve(2))
+        return 0;
+      int32_t* hw = lease.c->h_words.p;
+      int64_t* ho = reinterpret_cast<int64_t*>(hw);
+      ho[0] = 0; ho[1] = n;
+      std::memcpy(hw + 4, s, (size_t)n);
+      if (!cuda_ok(cudaMemcpyAsync(sl.text.p, hw, 16 + (size_t)n, cudaMemcpyHostToDevice, sl.stream), "H2D")) return 0;
+      const uint8_t* d_text = sl.text.p + 16;
+      const int64_t* d_offs = reinterpret_cast<const int64_t*>(sl.text.p);
+      int32_t* d_ids = sl.ids.p;
+      int32_t* d_counts = d_ids + max_ids;          // the count travels back with the row
+      int nl = 0;
+      bool ok;
+      if (m->engine == 3) ok = launch_segmentation(m, sl, d_text, d_offs, n, 1, n, d_ids, d_counts, nullptr, nullptr, max_ids, unk, sl.stream, &nl);
+      else if (m->engine == 2) ok = launch_lexer_ids(m, sl, d_text, d_offs, 0, n, 1, d_ids, d_counts, max_ids, unk, sl.stream, &nl);
+      else ok = launch_wordpiece(m, d_text, d_offs, n, 1, d_ids, d_counts, max_ids, unk, sl.counter.p, sl.stream, &nl);
+      if (!ok) return 0;
+      g_launches += nl;
+      int32_t* hr = hw + in_words;
+      if (!cuda_ok(cudaMemcpyAsync(hr, d_ids, ((size_t)max_ids + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H")) return 0;
+      hr[max_ids + 1] = 0;
+      if (m->engine == 3 &&
+          !cuda_ok(cudaMemcpyAsync(hr + max_ids + 1, reinterpret_cast<const int32_t*>(sl.counter.p + 1), 4, cudaMemcpyDeviceToHost, sl.stream), "D2H flag"))
+        return 0;
+      if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return 0;
+      if (hr[max_ids + 1] != 0) { set_error("segmentation engine: scratch exhausted (code " + std::to_string(hr[max_ids + 1]) + ")"); return 0; }
+      const int count = hr[max_ids];
+      if (count <= 0 || count > max_ids) return 0;
+      std::memcpy(ids, hr, (size_t)count * sizeof(int32_t));     // the rest of the caller's array stays untouched (:1098-1101)
+      return count;
+    } catch (const std::exception& e) { set_error(e.what()); return 0; }
+  }
   const int64_t offsets[2] = {0, n};
   int32_t count = 0;
   const int64_t r = TextToIdsBatch(h, s, offsets, 1, ids, &count, max_ids, unk);

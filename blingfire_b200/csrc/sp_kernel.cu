@@ -128,9 +128,12 @@ static bool is_bpe_algo(int tok_algo) {
 
 #ifndef BF_SIMT_HOST
 int sp_preferred_warps(int tok_algo) {
-  int dev = 0, sms = 0;
+  // (per thread and device: the per-document calls come here once per call)
+  static thread_local int cached_dev = -1, cached_sms = 0;
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev != cached_dev) { cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev); cached_dev = dev; }
+  const int sms = cached_sms;
   return is_bpe_algo(tok_algo) ? sms * kBWarps * kBCtasPerSm : sms * kUWarps * kUCtasPerSm;
 }
 
@@ -147,8 +150,15 @@ cudaError_t sp_tokenize_launch(const SpLaunch& p, const SpModelDev& m, cudaStrea
   const int cta_warps = bpe ? kBWarps : kUWarps;
   const size_t smem = bpe ? (size_t)kBWarps * kBWorkBytes : (size_t)kUWarps * kUWorkBytes;
   auto kern = bpe ? sp_bpe_kernel : sp_unigram_kernel;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static thread_local int attr_dev[2] = {-1, -1};               // the attribute is set once per (thread, device, kernel)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  if (attr_dev[bpe ? 1 : 0] != dev) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_dev[bpe ? 1 : 0] = dev;
+  }
   int grid = p.grid_warps / cta_warps;
   if (grid < 1) return cudaErrorInvalidValue;
   const int64_t needed = (p.ndocs + cta_warps - 1) / cta_warps;
