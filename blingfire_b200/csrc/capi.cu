@@ -1356,25 +1356,32 @@ bool lex_on_gpu(Model* m, Ctx* ctx, const char* s, int n, LexedText* R) {
   if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return false;
   Slot& sl = ctx->slots[0];
   if (!ensure_stream(sl)) return false;
-  const size_t nb = (size_t)n;
-  if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve(2) || !sl.lex_cls.reserve(nb + 8) || !sl.lex_ncps.reserve(1) ||
-      !sl.lex_tri_count.reserve(1) || !sl.lex_tri.reserve(3 * nb + 8) || !ctx->h_words.reserve(3 * nb + 16))
+  const size_t nb = (size_t)n, tb = (nb + 3) & ~(size_t)3;
+  // pinned staging: [offsets 16 B][text] in, [ncps, tri_count, triples...] out
+  const size_t in_words = 4 + (tb + 64) / 4;
+  if (!sl.text.reserve(16 + tb + 64) || !sl.lex_cls.reserve(nb + 8) || !sl.lex_ncps.reserve(1) ||
+      !sl.lex_tri_count.reserve(1) || !sl.lex_tri.reserve(3 * nb + 8) || !ctx->h_words.reserve(in_words + 3 * nb + 16))
     return false;
-  const int64_t offs[2] = {0, n};
-  if (!cuda_ok(cudaMemcpyAsync(sl.text.p, s, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return false;
-  if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offs, sizeof(offs), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return false;
-  LexLaunch X = make_lex_launch(sl, sl.text.p, sl.offsets.p, 0, n, 1, m->d_cls_words, 1);   // MaxOut = 3 * MaxBuffSize (:492-499, :249-251)
+  int32_t* hin = ctx->h_words.p;
+  int64_t* ho = reinterpret_cast<int64_t*>(hin);
+  ho[0] = 0; ho[1] = n;
+  std::memcpy(hin + 4, s, nb);
+  if (!cuda_ok(cudaMemcpyAsync(sl.text.p, hin, 16 + nb, cudaMemcpyHostToDevice, sl.stream), "H2D")) return false;   // offsets + text, one copy
+  LexLaunch X = make_lex_launch(sl, sl.text.p + 16, reinterpret_cast<const int64_t*>(sl.text.p), 0, n, 1, m->d_cls_words, 1);   // MaxOut = 3 * MaxBuffSize (:492-499, :249-251)
   int nl = 0;
   if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return false;
   g_launches += nl;
-  int32_t* hw = ctx->h_words.p;
+  int32_t* hw = hin + in_words;
   if (!cuda_ok(cudaMemcpyAsync(hw, sl.lex_ncps.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return false;
   if (!cuda_ok(cudaMemcpyAsync(hw + 1, sl.lex_tri_count.p, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H")) return false;
+  // short inputs: the triples travel with the counts (at most 3 per code point), one synchronisation
+  const bool eager = nb <= (8u << 10);
+  if (eager && !cuda_ok(cudaMemcpyAsync(hw + 2, sl.lex_tri.p, 3 * nb * 4, cudaMemcpyDeviceToHost, sl.stream), "D2H triples")) return false;
   if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return false;
   const int ncps = hw[0], rn = hw[1];
   if (ncps <= 0) return false;                                      // invalid UTF-8 or nothing decoded (:475-478, :231-234)
   if (rn < 0 || rn > 3 * ncps || rn % 3 != 0) return false;         // :500-502, :252-254
-  if (rn > 0) {
+  if (rn > 0 && !eager) {
     if (!cuda_ok(cudaMemcpyAsync(hw + 2, sl.lex_tri.p, (size_t)rn * 4, cudaMemcpyDeviceToHost, sl.stream), "D2H triples")) return false;
     if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return false;
   }
