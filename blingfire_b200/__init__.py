@@ -51,6 +51,9 @@ def lib():
         L.TextToIdsBatchCsr.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int]
         L.TextToIdsWithOffsetsBatch.restype = c_int64
         L.TextToIdsWithOffsetsBatch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]
+        L.TextToIdsWithOffsetsBatchCsr.restype = c_int64
+        L.TextToIdsWithOffsetsBatchCsr.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                                   c_int, c_int]
         L.TextToWordsBatch.restype = c_int64
         L.TextToWordsBatch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]
         L.TextToSentencesBatch.restype = c_int64
@@ -179,6 +182,28 @@ def text_to_ids_with_offsets_batch(h, docs, max_len, unk=0):
     if r < 0:
         raise RuntimeError(f"TextToIdsWithOffsetsBatch failed: {last_error()}")
     return ids, starts, ends, counts
+
+
+def text_to_ids_with_offsets_batch_csr(h, docs, max_len, unk=0, capacity=None):
+    """ADDITIVE: the compact form (TextToIdsWithOffsetsBatchCsr).  Returns (ids, starts, ends, id_offsets): the ids and byte
+    offsets of document i are entries id_offsets[i]:id_offsets[i+1] of the three int32 arrays."""
+    buf, offs = make_csr([d.encode("utf-8") if isinstance(d, str) else d for d in docs]) if not isinstance(docs, tuple) else docs
+    n = len(offs) - 1
+    buf = np.ascontiguousarray(buf)
+    offs = np.ascontiguousarray(offs, dtype=np.int64)
+    if capacity is None:
+        capacity = int(np.minimum(np.diff(offs) + 1, max_len).clip(min=0).sum())
+    id_offsets = np.zeros(n + 1, np.int64)
+    for _ in range(2):
+        out = np.empty((3, max(capacity, 1)), np.int32)
+        r = lib().TextToIdsWithOffsetsBatchCsr(c_void_p(h), buf.ctypes.data if len(buf) else None, offs.ctypes.data, n, out[0].ctypes.data,
+                                               out[1].ctypes.data, out[2].ctypes.data, capacity, id_offsets.ctypes.data, max_len, unk)
+        if r >= 0:
+            return out[0, :r], out[1, :r], out[2, :r], id_offsets
+        if r == -1 and last_error():
+            break
+        capacity = -r            # a [pos-dict] model can emit more ids than bytes
+    raise RuntimeError(f"TextToIdsWithOffsetsBatchCsr failed ({r}): {last_error()}")
 
 
 def text_to_sentences_batch(docs, h=None, raw=False):

@@ -1221,78 +1221,130 @@ int TextToIdsWithOffsets(void* h, const char* s, int n, int32_t* ids, int* start
   } catch (const std::exception& e) { set_error(e.what()); return 0; }
 }
 
-// Additive: TextToIdsWithOffsets for a batch (CSR documents in; row-major ids / starts / ends [ndocs][max_ids] and counts out;
-// a row beyond its count stays untouched, like the arrays of the per-document call).  The same kernels as the
-// per-document call -- they take batches already -- over chunks of a few MB.  Returns the total number of ids, -1 on error.
+// Additive: TextToIdsWithOffsets for a batch.  The same kernels as the per-document call -- they take batches already --
+// over chunks of a few MB; the three row-major device arrays of a chunk are compacted on the device (scan of the counts,
+// three gathers), so that 12 bytes per id come back instead of 12 * max_ids per document.
+//   row-major form (id_offsets == nullptr): ids / starts / ends are [ndocs][max_ids], counts [ndocs]; a row beyond its
+//     count stays untouched, like the arrays of the per-document call.
+//   CSR form: ids / starts / ends hold `capacity` entries each, id_offsets [ndocs + 1]; returns the total, negated if it
+//     exceeds the capacity (id_offsets is complete then, the arrays hold the chunks that still fitted).
+static int64_t offsets_batch(Model* m, const char* utf8, const int64_t* offsets, int64_t ndocs, int32_t* ids, int32_t* starts,
+                             int32_t* ends, int32_t* counts, int64_t capacity, int64_t* id_offsets, int max_ids, int unk) {
+  const bool csr = id_offsets != nullptr;
+  if (!check_batch_args(m, utf8, offsets, ndocs, max_ids)) return -1;
+  if (csr) {
+    if (capacity < 0 || (capacity > 0 && (!ids || !starts || !ends))) { set_error("bad output arguments"); return -1; }
+    id_offsets[0] = 0;
+  } else if (ndocs > 0 && (!ids || !starts || !ends || !counts)) {
+    set_error("bad output arguments");
+    return -1;
+  }
+  if (max_ids <= 0) {
+    for (int64_t i = 0; i < ndocs; ++i) {
+      if (csr) id_offsets[i + 1] = 0; else counts[i] = 0;
+    }
+    return 0;
+  }
+  const bool seg = m->has_seg;
+  if (!seg && !(m->has_wbd && m->lex_ok && m->T.charmap_one_to_one)) { set_error("offsets are not served for this lexer model"); return -1; }
+  if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
+  CtxLease lease(m);
+  Slot& sl = lease.c->slots[0];
+  if (!ensure_stream(sl)) return -1;
+  int64_t total = 0;
+  const int64_t kChunkBytes = 8ll << 20, kMaxCells = 16ll << 20;
+  for (int64_t d0 = 0; d0 < ndocs;) {
+    int64_t d1 = d0, max_len = 0;
+    while (d1 < ndocs && (d1 == d0 || (offsets[d1 + 1] - offsets[d0] <= kChunkBytes && (d1 - d0 + 1) * (int64_t)max_ids <= kMaxCells))) {
+      max_len = std::max(max_len, offsets[d1 + 1] - offsets[d1]);
+      ++d1;
+    }
+    const int64_t nd = d1 - d0;
+    const int64_t b0 = offsets[d0] & ~(int64_t)3, b1 = offsets[d1];
+    const size_t nb = (size_t)(b1 - b0), span = (size_t)(b1 - offsets[d0]), cells = (size_t)nd * (size_t)max_ids;
+    if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve((size_t)nd + 1) || !sl.ids.reserve(3 * cells) || !sl.counts.reserve((size_t)nd + 1) ||
+        !sl.counter.reserve(2) || !sl.row_off.reserve((size_t)nd + 1) || !sl.csr.reserve(3 * cells) || !sl.h_row_off.reserve((size_t)nd + 2))
+      return -1;
+    if (nb && !cuda_ok(cudaMemcpyAsync(sl.text.p, utf8 + b0, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return -1;
+    if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offsets + d0, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return -1;
+    int32_t* d_ids = sl.ids.p;
+    int nl = 0;
+    if (seg) {
+      if (!launch_segmentation(m, sl, sl.text.p - b0, sl.offsets.p, b1, nd, max_len, d_ids, sl.counts.p, d_ids + cells, d_ids + 2 * cells, max_ids, unk,
+                               sl.stream, &nl))
+        return -1;
+    } else {
+      if (!sl.lex_cls.reserve(span + 8) || !sl.lex_ncps.reserve((size_t)nd) || !sl.lex_tri_count.reserve((size_t)nd) ||
+          !sl.lex_tri.reserve(6 * span + 8) || !sl.lex_boff.reserve(span + 8))
+        return -1;
+      LexLaunch X = make_lex_launch(sl, sl.text.p - b0, sl.offsets.p, offsets[d0], b1, nd, m->d_cls, 2);
+      X.boff_buf = sl.lex_boff.p;
+      if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return -1;
+      if (!cuda_ok(lex_wp_offsets_launch(X, d_ids, d_ids + cells, d_ids + 2 * cells, sl.counts.p, max_ids, unk, sl.stream, &nl), "post-pass launch"))
+        return -1;
+    }
+    if (!cuda_ok(wp_scan_counts(sl.counts.p, sl.row_off.p, nd, sl.stream), "scan")) return -1;
+    for (int k = 0; k < 3; ++k)
+      if (!cuda_ok(wp_compact_launch(d_ids + (size_t)k * cells, sl.counts.p, sl.row_off.p, nd, max_ids, sl.csr.p + (size_t)k * cells, sl.stream), "compact"))
+        return -1;
+    g_launches += nl + 4;
+    int64_t* hro = sl.h_row_off.p;                                   // [nd + 1] row offsets of the chunk, then the error word
+    if (!cuda_ok(cudaMemcpyAsync(hro, sl.row_off.p, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, sl.stream), "D2H offsets")) return -1;
+    hro[nd + 1] = 0;
+    if (seg && !cuda_ok(cudaMemcpyAsync(hro + nd + 1, sl.counter.p + 1, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H flag")) return -1;
+    if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
+    if (hro[nd + 1] != 0) { set_error("segmentation engine: scratch exhausted (code " + std::to_string((long long)hro[nd + 1]) + ")"); return -1; }
+    const int64_t nout = hro[nd];
+    if (nout < 0 || (size_t)nout > cells) { set_error("offsets batch: inconsistent counts"); return -1; }
+    if (csr) {
+      for (int64_t i = 0; i < nd; ++i) id_offsets[d0 + i + 1] = total + hro[i + 1];
+      if (nout > 0 && total + nout <= capacity) {
+        int32_t* dst[3] = {ids + total, starts + total, ends + total};
+        for (int k = 0; k < 3; ++k)
+          if (!cuda_ok(cudaMemcpyAsync(dst[k], sl.csr.p + (size_t)k * cells, (size_t)nout * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H ids"))
+            return -1;
+        if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
+      }
+    } else {
+      if (!sl.h_csr.reserve(3 * (size_t)nout + 4)) return -1;
+      int32_t* hw = sl.h_csr.p;                                      // the chunk's compact ids, starts, ends
+      if (nout > 0) {
+        for (int k = 0; k < 3; ++k)
+          if (!cuda_ok(cudaMemcpyAsync(hw + (size_t)k * nout, sl.csr.p + (size_t)k * cells, (size_t)nout * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H ids"))
+            return -1;
+        if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
+      }
+      for (int64_t i = 0; i < nd; ++i) {
+        const int64_t r0 = hro[i], c = hro[i + 1] - r0;
+        counts[d0 + i] = (int32_t)c;
+        if (c > 0) {
+          const size_t dst = (size_t)(d0 + i) * (size_t)max_ids;
+          std::memcpy(ids + dst, hw + r0, (size_t)c * 4);
+          std::memcpy(starts + dst, hw + nout + r0, (size_t)c * 4);
+          std::memcpy(ends + dst, hw + 2 * nout + r0, (size_t)c * 4);
+        }
+      }
+    }
+    total += nout;
+    d0 = d1;
+  }
+  return csr && total > capacity ? -total : total;
+}
+
 int64_t TextToIdsWithOffsetsBatch(void* h, const char* utf8, const int64_t* offsets, int64_t ndocs, int32_t* ids, int32_t* starts,
                                   int32_t* ends, int32_t* counts, int max_ids, int unk) {
   try {
     g_last_error.clear();
-    Model* m = (Model*)h;
-    if (!check_batch_args(m, utf8, offsets, ndocs, max_ids)) return -1;
-    if (ndocs > 0 && (!ids || !starts || !ends || !counts)) { set_error("bad output arguments"); return -1; }
-    if (max_ids <= 0) { for (int64_t i = 0; i < ndocs; ++i) counts[i] = 0; return 0; }
-    const bool seg = m->has_seg;
-    if (!seg && !(m->has_wbd && m->lex_ok && m->T.charmap_one_to_one)) { set_error("offsets are not served for this lexer model"); return -1; }
-    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
-    CtxLease lease(m);
-    Slot& sl = lease.c->slots[0];
-    if (!ensure_stream(sl)) return -1;
-    int64_t total = 0;
-    const int64_t kChunkBytes = 8ll << 20, kMaxCells = 16ll << 20;
-    for (int64_t d0 = 0; d0 < ndocs;) {
-      int64_t d1 = d0, max_len = 0;
-      while (d1 < ndocs && (d1 == d0 || (offsets[d1 + 1] - offsets[d0] <= kChunkBytes && (d1 - d0 + 1) * (int64_t)max_ids <= kMaxCells))) {
-        max_len = std::max(max_len, offsets[d1 + 1] - offsets[d1]);
-        ++d1;
-      }
-      const int64_t nd = d1 - d0;
-      const int64_t b0 = offsets[d0] & ~(int64_t)3, b1 = offsets[d1];
-      const size_t nb = (size_t)(b1 - b0), span = (size_t)(b1 - offsets[d0]), cells = (size_t)nd * (size_t)max_ids;
-      if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve((size_t)nd + 1) || !sl.ids.reserve(3 * cells) || !sl.counts.reserve((size_t)nd + 1) ||
-          !sl.counter.reserve(2) || !sl.h_csr.reserve(3 * cells + (size_t)nd + 4))
-        return -1;
-      if (nb && !cuda_ok(cudaMemcpyAsync(sl.text.p, utf8 + b0, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return -1;
-      if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offsets + d0, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return -1;
-      int32_t* d_ids = sl.ids.p;
-      int nl = 0;
-      if (seg) {
-        if (!launch_segmentation(m, sl, sl.text.p - b0, sl.offsets.p, b1, nd, max_len, d_ids, sl.counts.p, d_ids + cells, d_ids + 2 * cells, max_ids, unk,
-                                 sl.stream, &nl))
-          return -1;
-      } else {
-        if (!sl.lex_cls.reserve(span + 8) || !sl.lex_ncps.reserve((size_t)nd) || !sl.lex_tri_count.reserve((size_t)nd) ||
-            !sl.lex_tri.reserve(6 * span + 8) || !sl.lex_boff.reserve(span + 8))
-          return -1;
-        LexLaunch X = make_lex_launch(sl, sl.text.p - b0, sl.offsets.p, offsets[d0], b1, nd, m->d_cls, 2);
-        X.boff_buf = sl.lex_boff.p;
-        if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return -1;
-        if (!cuda_ok(lex_wp_offsets_launch(X, d_ids, d_ids + cells, d_ids + 2 * cells, sl.counts.p, max_ids, unk, sl.stream, &nl), "post-pass launch"))
-          return -1;
-      }
-      g_launches += nl;
-      int32_t* hw = sl.h_csr.p;                                      // [3 * cells] rows, then [nd] counts, then the error word
-      if (!cuda_ok(cudaMemcpyAsync(hw, d_ids, 3 * cells * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H rows")) return -1;
-      if (!cuda_ok(cudaMemcpyAsync(hw + 3 * cells, sl.counts.p, (size_t)nd * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H counts")) return -1;
-      hw[3 * cells + (size_t)nd] = 0;
-      if (seg && !cuda_ok(cudaMemcpyAsync(hw + 3 * cells + (size_t)nd, sl.counter.p + 1, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H flag")) return -1;
-      if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
-      if (hw[3 * cells + (size_t)nd] != 0) { set_error("segmentation engine: scratch exhausted (code " + std::to_string(hw[3 * cells + (size_t)nd]) + ")"); return -1; }
-      for (int64_t i = 0; i < nd; ++i) {
-        int c = hw[3 * cells + (size_t)i];
-        if (c < 0 || c > max_ids) c = 0;
-        counts[d0 + i] = c;
-        total += c;
-        if (c > 0) {
-          const size_t row = (size_t)i * (size_t)max_ids, dst = (size_t)(d0 + i) * (size_t)max_ids;
-          std::memcpy(ids + dst, hw + row, (size_t)c * 4);
-          std::memcpy(starts + dst, hw + cells + row, (size_t)c * 4);
-          std::memcpy(ends + dst, hw + 2 * cells + row, (size_t)c * 4);
-        }
-      }
-      d0 = d1;
-    }
-    return total;
+    return offsets_batch((Model*)h, utf8, offsets, ndocs, ids, starts, ends, counts, 0, nullptr, max_ids, unk);
+  } catch (const std::exception& e) { set_error(e.what()); return -1; }
+}
+
+int64_t TextToIdsWithOffsetsBatchCsr(void* h, const char* utf8, const int64_t* offsets, int64_t ndocs, int32_t* ids_csr, int32_t* starts_csr,
+                                     int32_t* ends_csr, int64_t capacity, int64_t* id_offsets, int max_ids, int unk) {
+  try {
+    g_last_error.clear();
+    if (!id_offsets) { set_error("bad output arguments"); return -1; }
+    return offsets_batch((Model*)h, utf8, offsets, ndocs, ids_csr, starts_csr, ends_csr, nullptr, capacity, id_offsets, max_ids, unk);
   } catch (const std::exception& e) { set_error(e.what()); return -1; }
 }
 

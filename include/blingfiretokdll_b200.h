@@ -126,6 +126,15 @@ int TextToWordsWithOffsets(const char* pInUtf8Str, int InUtf8StrByteCount, char*
 int64_t TextToIdsWithOffsetsBatch(void* ModelPtr, const char* pUtf8, const int64_t* pOffsets, int64_t DocCount, int32_t* pIds,
                                   int32_t* pStarts, int32_t* pEnds, int32_t* pCounts, int MaxIdsPerDoc, int UnkId);
 
+/* ADDITIVE.  The same with compact output, like TextToIdsBatchCsr: ids / starts / ends of document i are entries
+ * [pIdOffsets[i] .. pIdOffsets[i+1]) of the three arrays (CsrCapacity entries each; 12 bytes per id cross PCIe instead of
+ * 12 * MaxIdsPerDoc per document).  pIdOffsets has DocCount+1 entries and is always complete on a non-error return.
+ * Returns the total number of ids; if it exceeds CsrCapacity, negated (the arrays then hold the chunks that still
+ * fitted); -1 on error. */
+int64_t TextToIdsWithOffsetsBatchCsr(void* ModelPtr, const char* pUtf8, const int64_t* pOffsets, int64_t DocCount, int32_t* pIdsCsr,
+                                     int32_t* pStartsCsr, int32_t* pEndsCsr, int64_t CsrCapacity, int64_t* pIdOffsets,
+                                     int MaxIdsPerDoc, int UnkId);
+
 /* ADDITIVE (not in the reference, which takes one document per call: blingfiretokdll.cpp:415-566).  TextToWords[WithModel]
  * for a batch: documents as CSR (pUtf8, pOffsets[DocCount+1]), strings as CSR.  The lexer and the string building
  * (:507-555) both run on the GPU.  hModel may be NULL (the default word breaker, like TextToWords).

@@ -130,6 +130,25 @@ def test_offsets_batch_vs_oracle(bf, name, unk):
             keep = [k for k in range(n) if os_[k] >= 0 or oe[k] == -1]         # (blingfiretokdll.cpp:1527, see test_offsets_vs_golden)
             assert (en[i, keep] == oe[keep]).all(), (name, d[:40])
             assert (ids[i, n:] == 0).all() and (st[i, n:] == 0).all() and (en[i, n:] == 0).all()
+        # the compact form returns the same entries back to back
+        cid, cst, cen, off = bf.text_to_ids_with_offsets_batch_csr(h, docs, max_ids, unk)
+        assert off[0] == 0 and (np.diff(off) == counts).all() and len(cid) == off[-1] == counts.sum()
+        mask = np.arange(max_ids)[None, :] < counts[:, None]
+        assert (cid == ids[mask]).all() and (cst == st[mask]).all() and (cen == en[mask]).all()
+    # more documents than one chunk holds (16 M cells): the same rows, repeated
+    reps = (16 << 20) // (len(docs) * 300) + 2
+    bid, bst, ben, boff = bf.text_to_ids_with_offsets_batch_csr(h, docs * reps, 300, unk)
+    sid, sst, sen, soff = bf.text_to_ids_with_offsets_batch_csr(h, docs, 300, unk)
+    assert len(bid) == reps * len(sid) and (np.diff(boff) == np.tile(np.diff(soff), reps)).all()
+    assert (bid == np.tile(sid, reps)).all() and (bst == np.tile(sst, reps)).all() and (ben == np.tile(sen, reps)).all()
+    # too small a capacity: the need comes back negated, the offsets are complete
+    L = bf.lib()
+    buf, offs = bf.make_csr(docs)
+    small = np.full((3, 16), -7, np.int32)
+    off2 = np.zeros(len(docs) + 1, np.int64)
+    r = L.TextToIdsWithOffsetsBatchCsr(ctypes.c_void_p(h), buf.ctypes.data, offs.ctypes.data, len(docs), small[0].ctypes.data,
+                                       small[1].ctypes.data, small[2].ctypes.data, 16, off2.ctypes.data, 4, unk)
+    assert r == -int(off[-1]) and (off2 == off).all()
     bf.free_model(h)
 
 

@@ -41,6 +41,8 @@ for name, unk in (("bert_base_tok.bin", 100), ("xlm_roberta_base.bin", 3)):
     h = bf.load_model(model_path(name))
     dt = timed(lambda: bf.text_to_ids_with_offsets_batch(h, (buf[: offs[100000]], offs[:100001]), 128, unk), reps=2)
     print(f"TextToIdsWithOffsetsBatch {name}, 100000 lines: {offs[100000] / 1e6 / dt:.1f} MB/s")
+    dt = timed(lambda: bf.text_to_ids_with_offsets_batch_csr(h, (buf, offs), 128, unk), reps=2)
+    print(f"TextToIdsWithOffsetsBatchCsr {name}, {n} lines: {mb / dt:.1f} MB/s")
     bf.free_model(h)
 L = bf.lib()
 out = ctypes.create_string_buffer(4096)
