@@ -107,6 +107,50 @@ __global__ void __launch_bounds__(kUWarps * 32, kUCtasPerSm) sp_unigram_kernel(c
   }
 }
 
+// TextToIdsWithOffsets_sp for the Unigram family: the one-window fast path with the byte offsets carried along (in the head of
+// the warp's arena), sp_doc_generic for what does not fit it.  A kernel of its own, so that sp_unigram_kernel stays what it is.
+__global__ void __launch_bounds__(kUWarps * 32, kUCtasPerSm) sp_unigram_offsets_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
+#ifdef BF_SIMT_HOST                        // tests/simt: the kernel source on the CPU
+  uint8_t* smem = simt::shared_base();
+#else
+  extern __shared__ __align__(16) uint8_t smem[];
+#endif
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * kUWarps + warp;
+  const UWork w = make_uwork(smem + (size_t)warp * kUWorkBytes);
+  uint8_t* my_arena = p.arena + (size_t)gwarp * p.arena_stride;
+  Work wa = make_work(my_arena, p.arena_cap, true);
+  const ArcScratch scratch = make_scratch(p, my_arena, error_flag);
+  const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
+  const bool fast_model = !m.use_raw_bytes && m.max_arc_len <= kUMaxLen && !m.delim_inside_tokens && m.delim_is_token;
+  for (;;) {
+    unsigned long long d64 = 0;
+    if (lane == 0) d64 = atomicAdd(p.work_counter, 1ull);
+    d64 = __shfl_sync(0xffffffffu, d64, 0);
+    if ((int64_t)d64 >= p.ndocs) break;
+    const int64_t doc = (int64_t)d64;
+    const int64_t lo = __ldg(p.offsets + doc), hi = __ldg(p.offsets + doc + 1);
+    const int64_t n = hi - lo;
+    int result = 0;
+    if (n > 0 && n <= 1000000000) {                                       // :1362
+      result = kUFallback;
+      if (fast_model && n <= 4ll * kUCap) {                               // a code point takes at most 4 bytes
+        UOff uo;
+        uo.boff = reinterpret_cast<int32_t*>(my_arena);                   // >= 64 KB per warp (sp_arena_bytes_per_warp)
+        uo.doc = p.text + lo;
+        uo.starts = p.starts + doc * (int64_t)p.max_ids;
+        uo.ends = p.ends + doc * (int64_t)p.max_ids;
+        result = unigram_whole<true>(m, w, p.text, lo, hi, padded_bytes, p.ids + doc * (int64_t)p.max_ids, p.max_ids, p.unk_id, lane, uo);
+        __syncwarp();
+      }
+      if (result == kUFallback)
+        result = sp_doc_generic<false>(p, m, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
+    }
+    if (lane == 0) p.counts[doc] = result;
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 int64_t sp_arena_bytes_per_warp(int cap, int) {
@@ -149,15 +193,16 @@ cudaError_t sp_tokenize_launch(const SpLaunch& p, const SpModelDev& m, cudaStrea
   const bool bpe = is_bpe_algo(m.tok_algo);
   const int cta_warps = bpe ? kBWarps : kUWarps;
   const size_t smem = bpe ? (size_t)kBWarps * kBWorkBytes : (size_t)kUWarps * kUWorkBytes;
-  auto kern = bpe ? sp_bpe_kernel : sp_unigram_kernel;
-  static thread_local int attr_dev[2] = {-1, -1};               // the attribute is set once per (thread, device, kernel)
+  const int which = bpe ? 1 : (p.starts != nullptr ? 2 : 0);
+  auto kern = bpe ? sp_bpe_kernel : (which == 2 ? sp_unigram_offsets_kernel : sp_unigram_kernel);
+  static thread_local int attr_dev[3] = {-1, -1, -1};           // the attribute is set once per (thread, device, kernel)
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (attr_dev[bpe ? 1 : 0] != dev) {
+  if (attr_dev[which] != dev) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_dev[bpe ? 1 : 0] = dev;
+    attr_dev[which] = dev;
   }
   int grid = p.grid_warps / cta_warps;
   if (grid < 1) return cudaErrorInvalidValue;

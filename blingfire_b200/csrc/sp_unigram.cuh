@@ -19,8 +19,9 @@ namespace {
 //     half-tile, lanes 1..31: everything its starts can reach).  Start st's turn: every lane takes
 //     score[st-1] by shuffle, the lane whose position is st+k looks up arc (st, k) in the tile and
 //     relaxes its own registers.  No shared-memory traffic but the arc fetch, no barriers.
-// Anything that does not fit (a run of kUCap symbols without U+2581, offsets, raw bytes, longer
-// tokens) takes sp_doc_generic in the warp's arena.
+// Anything that does not fit (a run of kUCap symbols without U+2581, raw bytes, longer tokens) takes sp_doc_generic in the
+// warp's arena.  With offsets (sp_unigram_offsets_kernel) only the one-window form is fast: a document of more than kUCap
+// symbols takes sp_doc_generic.
 // =====================================================================================
 constexpr int kUWarps = 8;                 // per CTA
 constexpr int kUCtasPerSm = 3;
@@ -48,12 +49,23 @@ __device__ inline UWork make_uwork(uint8_t* b) {
   return w;
 }
 
+// TextToIdsWithOffsets_sp (blingfiretokdll.cpp:1519-1529) on the one-window form: where the byte offsets of one document
+// live and go.  Only the kOff = true instantiations touch it.
+struct UOff {
+  int32_t* boff;       // [kUCap] byte offset (from the document start) of every symbol, -1 = dummy prefix; the warp's own
+                       // global scratch (the head of its arena), so that the shared-memory layout stays the one above
+  const uint8_t* doc;  // first byte of the document
+  int32_t* starts;     // rows parallel to the ids row
+  int32_t* ends;
+};
+
 
 // Best path over the window's symbols sym[0..N) (FATokenSegmentationTools_1best_t.h:174-279); the ids
 // of its tokens are appended to row[out..).  *carry is the best score of the position before the
 // window on entry and of position N-1 on exit.  Returns the new out.
+template <bool kOff>
 __device__ int unigram_window(const SpModelDev& m, const UWork& w, int N, double* carry, int32_t* row, int out, int max_ids,
-                              int unk, int lane) {
+                              int unk, int lane, const UOff& uo) {
   const unsigned full = 0xffffffffu;
   int32_t* bid = w.stage;
   for (int i = lane; i < kUCap / 32; i += 32) w.mark[i] = 0;
@@ -148,6 +160,15 @@ __device__ int unigram_window(const SpModelDev& m, const UWork& w, int N, double
       int id = bid[p0 + lane];
       if (id == -1) id = unk;
       row[rank] = id + m.id_offset;                            // ids[k] = id + IdOffset, UNK included (:1516)
+      if constexpr (kOff) {                                    // the token ends at symbol p0 + lane and starts at begin[] of it
+        int b = w.begin[p0 + lane];
+        if (b == kUNoBegin) b = 0;                             // never-set arc: emitted as the token from symbol 0
+        uo.starts[rank] = uo.boff[b];
+        const int to_off = uo.boff[p0 + lane];
+        // a token that is only the dummy prefix has to_off == -1 (:1527 reads the byte before the input): size 0, like sp_emit
+        const int cs = to_off < 0 ? 0 : sp_utf8_size_of_lead(uo.doc[to_off]);
+        uo.ends[rank] = to_off + (cs > 0 ? cs - 1 : 0);
+      }
     }
     out += __popc(word);
   }
@@ -156,8 +177,9 @@ __device__ int unigram_window(const SpModelDev& m, const UWork& w, int N, double
 
 // The whole document in one window: one fused decode + charmap pass into stage[], one collapse pass.
 // kUFallback when it has more than kUCap symbols after the charmap (the streamed form takes over).
+template <bool kOff>
 __device__ int unigram_whole(const SpModelDev& m, const UWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
-                               int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane) {
+                             int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane, const UOff& uo) {
   const unsigned full = 0xffffffffu;
   int64_t lo = lo0;
   if (hi - lo >= 3) {
@@ -177,6 +199,7 @@ __device__ int unigram_whole(const SpModelDev& m, const UWork& w, const uint8_t*
       if (lane == 0) for (unsigned k = 0; k < nc; ++k) w.stage[k] = __ldg(m.norm_values + f + k);
       total = (int)nc;
     }
+    if constexpr (kOff) { if (lane < total) uo.boff[lane] = -1; }          // (:1387; a charmap row has at most a few symbols)
   }
   {
     const uint32_t* text32 = reinterpret_cast<const uint32_t*>(text);
@@ -204,10 +227,15 @@ __device__ int unigram_whole(const SpModelDev& m, const UWork& w, const uint8_t*
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (d.start_mask & (1u << k)) {
-          if (nck[k] == 0xFFu) w.stage[o++] = (int)d.cp[k];
-          else {
+          if (nck[k] == 0xFFu) {
+            if constexpr (kOff) uo.boff[o] = (int)(pos0 + k - lo0);
+            w.stage[o++] = (int)d.cp[k];
+          } else {
             const uint32_t f = __ldg(m.norm_first + d.cp[k]);
-            for (unsigned j = 0; j < nck[k]; ++j) w.stage[o++] = __ldg(m.norm_values + f + j);
+            for (unsigned j = 0; j < nck[k]; ++j) {
+              if constexpr (kOff) uo.boff[o] = (int)(pos0 + k - lo0);      // every symbol of an expansion: its source character
+              w.stage[o++] = __ldg(m.norm_values + f + j);
+            }
           }
         }
       }
@@ -225,6 +253,11 @@ __device__ int unigram_whole(const SpModelDev& m, const UWork& w, const uint8_t*
   for (int base = 0; base < total; base += 32) {
     const int i = base + lane;
     bool keep = false; int c = 0;
+    int bv = 0;
+    if constexpr (kOff) {                                      // compacted in place: a kept symbol never moves up
+      if (i < total) bv = uo.boff[i];
+      __syncwarp();
+    }
     if (i < total) {
       c = w.stage[i];
       const bool white = sp_is_white(c);
@@ -233,6 +266,7 @@ __device__ int unigram_whole(const SpModelDev& m, const UWork& w, const uint8_t*
       if (white) c = kSpDelim;
     }
     const unsigned bal = __ballot_sync(full, keep);
+    if constexpr (kOff) { if (keep) uo.boff[N + __popc(bal & bf_lanemask_lt())] = bv; }
     if (keep) w.sym[N + __popc(bal & bf_lanemask_lt())] = (unsigned)c <= 0x10FFFFu ? __ldg(m.sym_of_cp + c) : kNoSym;
     if (bal) last_c = __shfl_sync(full, c, 31 - __clz(bal));
     N += __popc(bal);
@@ -241,7 +275,7 @@ __device__ int unigram_whole(const SpModelDev& m, const UWork& w, const uint8_t*
   if (N <= 0) return 0;
   __syncwarp();
   double carry = 0.0;                                          // "position -1": the empty prefix
-  const int out = unigram_window(m, w, N, &carry, row, 0, max_ids, unk, lane);
+  const int out = unigram_window<kOff>(m, w, N, &carry, row, 0, max_ids, unk, lane, uo);
   return out < max_ids ? out : max_ids;
 }
 
@@ -390,7 +424,7 @@ __device__ int unigram_streamed(const SpModelDev& m, const UWork& w, const uint8
       cut = best;
     }
     if (cut > 0) {
-      out = unigram_window(m, w, cut, &carry, row, out, max_ids, unk, lane);
+      out = unigram_window<false>(m, w, cut, &carry, row, out, max_ids, unk, lane, UOff{});
       if (out >= max_ids) {
         // the ids are complete, but an invalid byte or a charmap overflow later in the document must
         // still yield 0 (:1409, :1442-1446)
@@ -438,7 +472,7 @@ __device__ int unigram_streamed(const SpModelDev& m, const UWork& w, const uint8
 __device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
                                int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane) {
   if (hi - lo0 <= 4ll * kUCap) {                               // a code point takes at most 4 bytes
-    const int r = unigram_whole(m, w, text, lo0, hi, padded_bytes, row, max_ids, unk, lane);
+    const int r = unigram_whole<false>(m, w, text, lo0, hi, padded_bytes, row, max_ids, unk, lane, UOff{});
     if (r != kUFallback) return r;
   }
   return unigram_streamed(m, w, text, lo0, hi, padded_bytes, row, max_ids, unk, lane);

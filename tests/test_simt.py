@@ -122,11 +122,18 @@ def test_kernel_source_long_documents(sim, name, unk):
     check(sim, name, docs[::2], 37, unk)
 
 
-@pytest.mark.parametrize("name,unk", [("xlm_roberta_base.bin", 3), ("gpt2.bin", 0), ("bpe_example.bin", 1), ("xlnet_nonorm.bin", 0)])
+@pytest.mark.parametrize("name,unk", [("xlm_roberta_base.bin", 3), ("xlnet.bin", 0), ("laser100k.bin", 1), ("gpt2.bin", 0),
+                                      ("bpe_example.bin", 1), ("xlnet_nonorm.bin", 0)])
 def test_kernel_source_offsets(sim, name, unk):
-    """TextToIdsWithOffsets_sp: the general path with the byte offsets carried through."""
-    docs = corpus_docs(7, 60)
-    check(sim, name, docs, 300, unk, offsets=True)
+    """TextToIdsWithOffsets_sp: the byte offsets carried through -- sp_unigram_offsets_kernel (one-window fast path, the
+    general path behind it for documents of more than a window) for Unigram models, the general path for BPE models."""
+    docs = corpus_docs(7, 140)
+    # around the window's capacity (576 symbols, the dummy prefix included), with and without a charmap expansion in it
+    docs += [b"a" * k for k in (573, 574, 575, 576, 577)] + [("ab " * 191 + "ﬁ").encode(), ("é" * 574).encode(), ("é" * 577).encode(),
+             ("word " * 500).encode(), b"\xef\xbb\xbf" + b"x y " * 140, b"  lead and trail  ", "\u3000ideographic\u3000space".encode(),
+             "½".encode(), " ½".encode(), "▁".encode(), " ".encode() * 50]
+    check(sim, name, docs, 700, unk, offsets=True)
+    check(sim, name, docs[::3], 5, unk, offsets=True)
 
 
 # ---- the fused WordPiece kernel ----------------------------------------------------------------------------
