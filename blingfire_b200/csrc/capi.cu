@@ -1249,70 +1249,81 @@ static int64_t offsets_batch(Model* m, const char* utf8, const int64_t* offsets,
   if (!seg && !(m->has_wbd && m->lex_ok && m->T.charmap_one_to_one)) { set_error("offsets are not served for this lexer model"); return -1; }
   if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return -1;
   CtxLease lease(m);
-  Slot& sl = lease.c->slots[0];
-  if (!ensure_stream(sl)) return -1;
+  // Up to kDepth chunks are in flight, each on the stream of its own slot: the generic lexer engine runs one thread per document,
+  // so a launch lasts as long as its longest document takes -- the launches of several chunks overlap instead of queueing.
+  const int kDepth = std::min(4, kSlots);
+  struct InFlight { int64_t d0 = 0, nd = 0; size_t cells = 0; bool busy = false; };
+  InFlight fl[kMaxSlots];
   int64_t total = 0;
   const int64_t kChunkBytes = 8ll << 20, kMaxCells = 16ll << 20;
-  for (int64_t d0 = 0; d0 < ndocs;) {
-    int64_t d1 = d0, max_len = 0;
-    while (d1 < ndocs && (d1 == d0 || (offsets[d1 + 1] - offsets[d0] <= kChunkBytes && (d1 - d0 + 1) * (int64_t)max_ids <= kMaxCells))) {
-      max_len = std::max(max_len, offsets[d1 + 1] - offsets[d1]);
-      ++d1;
-    }
+
+  // the kernels of chunk [d0, d1) and the copy of its row offsets, all on the slot's stream
+  auto issue = [&](Slot& sl, InFlight& f, int64_t d0, int64_t d1, int64_t max_len) -> bool {
+    if (!ensure_stream(sl)) return false;
     const int64_t nd = d1 - d0;
     const int64_t b0 = offsets[d0] & ~(int64_t)3, b1 = offsets[d1];
     const size_t nb = (size_t)(b1 - b0), span = (size_t)(b1 - offsets[d0]), cells = (size_t)nd * (size_t)max_ids;
     if (!sl.text.reserve(nb + 64) || !sl.offsets.reserve((size_t)nd + 1) || !sl.ids.reserve(3 * cells) || !sl.counts.reserve((size_t)nd + 1) ||
         !sl.counter.reserve(2) || !sl.row_off.reserve((size_t)nd + 1) || !sl.csr.reserve(3 * cells) || !sl.h_row_off.reserve((size_t)nd + 2))
-      return -1;
-    if (nb && !cuda_ok(cudaMemcpyAsync(sl.text.p, utf8 + b0, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return -1;
-    if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offsets + d0, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return -1;
+      return false;
+    if (nb && !cuda_ok(cudaMemcpyAsync(sl.text.p, utf8 + b0, nb, cudaMemcpyHostToDevice, sl.stream), "H2D text")) return false;
+    if (!cuda_ok(cudaMemcpyAsync(sl.offsets.p, offsets + d0, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, sl.stream), "H2D offsets")) return false;
     int32_t* d_ids = sl.ids.p;
     int nl = 0;
     if (seg) {
       if (!launch_segmentation(m, sl, sl.text.p - b0, sl.offsets.p, b1, nd, max_len, d_ids, sl.counts.p, d_ids + cells, d_ids + 2 * cells, max_ids, unk,
                                sl.stream, &nl))
-        return -1;
+        return false;
     } else {
       if (!sl.lex_cls.reserve(span + 8) || !sl.lex_ncps.reserve((size_t)nd) || !sl.lex_tri_count.reserve((size_t)nd) ||
           !sl.lex_tri.reserve(6 * span + 8) || !sl.lex_boff.reserve(span + 8))
-        return -1;
+        return false;
       LexLaunch X = make_lex_launch(sl, sl.text.p - b0, sl.offsets.p, offsets[d0], b1, nd, m->d_cls, 2);
       X.boff_buf = sl.lex_boff.p;
-      if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return -1;
+      if (!cuda_ok(lex_launch(X, make_lex_model(m), sl.stream, &nl), "lexer launch")) return false;
       if (!cuda_ok(lex_wp_offsets_launch(X, d_ids, d_ids + cells, d_ids + 2 * cells, sl.counts.p, max_ids, unk, sl.stream, &nl), "post-pass launch"))
-        return -1;
+        return false;
     }
-    if (!cuda_ok(wp_scan_counts(sl.counts.p, sl.row_off.p, nd, sl.stream), "scan")) return -1;
+    if (!cuda_ok(wp_scan_counts(sl.counts.p, sl.row_off.p, nd, sl.stream), "scan")) return false;
     for (int k = 0; k < 3; ++k)
       if (!cuda_ok(wp_compact_launch(d_ids + (size_t)k * cells, sl.counts.p, sl.row_off.p, nd, max_ids, sl.csr.p + (size_t)k * cells, sl.stream), "compact"))
-        return -1;
+        return false;
     g_launches += nl + 4;
     int64_t* hro = sl.h_row_off.p;                                   // [nd + 1] row offsets of the chunk, then the error word
-    if (!cuda_ok(cudaMemcpyAsync(hro, sl.row_off.p, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, sl.stream), "D2H offsets")) return -1;
+    if (!cuda_ok(cudaMemcpyAsync(hro, sl.row_off.p, ((size_t)nd + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, sl.stream), "D2H offsets")) return false;
     hro[nd + 1] = 0;
-    if (seg && !cuda_ok(cudaMemcpyAsync(hro + nd + 1, sl.counter.p + 1, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H flag")) return -1;
-    if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
-    if (hro[nd + 1] != 0) { set_error("segmentation engine: scratch exhausted (code " + std::to_string((long long)hro[nd + 1]) + ")"); return -1; }
+    if (seg && !cuda_ok(cudaMemcpyAsync(hro + nd + 1, sl.counter.p + 1, 4, cudaMemcpyDeviceToHost, sl.stream), "D2H flag")) return false;
+    f.d0 = d0; f.nd = nd; f.cells = cells; f.busy = true;
+    return true;
+  };
+
+  // waits for the chunk, copies its compact ids / starts / ends out; chunks finish in document order
+  auto finish = [&](Slot& sl, InFlight& f) -> bool {
+    f.busy = false;
+    const int64_t d0 = f.d0, nd = f.nd;
+    const size_t cells = f.cells;
+    if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return false;
+    const int64_t* hro = sl.h_row_off.p;
+    if (hro[nd + 1] != 0) { set_error("segmentation engine: scratch exhausted (code " + std::to_string((long long)hro[nd + 1]) + ")"); return false; }
     const int64_t nout = hro[nd];
-    if (nout < 0 || (size_t)nout > cells) { set_error("offsets batch: inconsistent counts"); return -1; }
+    if (nout < 0 || (size_t)nout > cells) { set_error("offsets batch: inconsistent counts"); return false; }
     if (csr) {
       for (int64_t i = 0; i < nd; ++i) id_offsets[d0 + i + 1] = total + hro[i + 1];
       if (nout > 0 && total + nout <= capacity) {
         int32_t* dst[3] = {ids + total, starts + total, ends + total};
         for (int k = 0; k < 3; ++k)
           if (!cuda_ok(cudaMemcpyAsync(dst[k], sl.csr.p + (size_t)k * cells, (size_t)nout * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H ids"))
-            return -1;
-        if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
+            return false;
+        if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return false;
       }
     } else {
-      if (!sl.h_csr.reserve(3 * (size_t)nout + 4)) return -1;
+      if (!sl.h_csr.reserve(3 * (size_t)nout + 4)) return false;
       int32_t* hw = sl.h_csr.p;                                      // the chunk's compact ids, starts, ends
       if (nout > 0) {
         for (int k = 0; k < 3; ++k)
           if (!cuda_ok(cudaMemcpyAsync(hw + (size_t)k * nout, sl.csr.p + (size_t)k * cells, (size_t)nout * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream), "D2H ids"))
-            return -1;
-        if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return -1;
+            return false;
+        if (!cuda_ok(cudaStreamSynchronize(sl.stream), "sync")) return false;
       }
       for (int64_t i = 0; i < nd; ++i) {
         const int64_t r0 = hro[i], c = hro[i + 1] - r0;
@@ -1326,8 +1337,30 @@ static int64_t offsets_batch(Model* m, const char* utf8, const int64_t* offsets,
       }
     }
     total += nout;
+    return true;
+  };
+
+  bool ok = true;
+  int64_t chunk = 0;
+  for (int64_t d0 = 0; d0 < ndocs && ok; ++chunk) {
+    int64_t d1 = d0, max_len = 0;
+    while (d1 < ndocs && (d1 == d0 || (offsets[d1 + 1] - offsets[d0] <= kChunkBytes && (d1 - d0 + 1) * (int64_t)max_ids <= kMaxCells))) {
+      max_len = std::max(max_len, offsets[d1 + 1] - offsets[d1]);
+      ++d1;
+    }
+    const int si = (int)(chunk % kDepth);
+    if (fl[si].busy) ok = finish(lease.c->slots[si], fl[si]);        // the oldest chunk in flight: the slot is its
+    if (ok) ok = issue(lease.c->slots[si], fl[si], d0, d1, max_len);
     d0 = d1;
   }
+  // the chunks still in flight, oldest first; after an error they are only waited for (their buffers are about to be reused)
+  for (int64_t k = chunk >= kDepth ? chunk - kDepth : 0; k < chunk; ++k) {
+    const int si = (int)(k % kDepth);
+    if (!fl[si].busy) continue;
+    if (ok) ok = finish(lease.c->slots[si], fl[si]);
+    else { fl[si].busy = false; cudaStreamSynchronize(lease.c->slots[si].stream); }
+  }
+  if (!ok) return -1;
   return csr && total > capacity ? -total : total;
 }
 

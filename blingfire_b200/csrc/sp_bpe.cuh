@@ -188,8 +188,9 @@ __device__ __forceinline__ int b_farthest(const SpModelDev& m, const uint4* da, 
 // The segments of sym[0..cut): tokens appended to row[out..).  Returns the new out (it may pass
 // max_ids; nothing is written past it) or kUFallback.  open_ended: the last segment does not end at a
 // U+2581 (nor at the end of the document) but at a position no token can span.
+template <bool kOff>
 __device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch& scratch, int cut, uint16_t delim, int32_t* row,
-                          int out, int max_ids, int unk, bool fast, bool open_ended, int lane) {
+                          int out, int max_ids, int unk, bool fast, bool open_ended, int lane, const WinOffsets& wo) {
   const unsigned full = 0xffffffffu;
   const uint4* da = reinterpret_cast<const uint4*>(m.da);
   int nseg = 0;
@@ -207,7 +208,8 @@ __device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch&
   // only at the segment's own end) -- segments seen before come out of the table, one lane per segment.  A segment found
   // there is flagged in seg[] (bit 15) and skipped by the passes below; the others are added once those have resolved them.
   const WpWords& memo = m.seg_memo;
-  const bool use_memo = memo.max_len > 0;
+  // (not with offsets: a segment served from the table has its ids parked on its first symbols, not on the tokens' starts)
+  const bool use_memo = !kOff && memo.max_len > 0;
   if (use_memo) {
     for (int g0 = 0; g0 < nseg; g0 += 32) {
       const int g = g0 + lane;
@@ -430,14 +432,31 @@ __device__ int bpe_window(const SpModelDev& m, const BWork& w, const ArcScratch&
   for (int p0 = 0; p0 < cut && out < max_ids; p0 += 32) {
     const uint32_t word = w.mark[p0 >> 5];
     const int rank = out + __popc(word & bf_lanemask_lt());
-    if (((word >> lane) & 1u) && rank < max_ids) row[rank] = w.ids_at[p0 + lane] + m.id_offset;   // (:1516)
+    if (((word >> lane) & 1u) && rank < max_ids) {
+      row[rank] = w.ids_at[p0 + lane] + m.id_offset;           // (:1516)
+      if constexpr (kOff) {
+        // the tokens tile the window: this one ends before the next start, the last one at cut - 1
+        int e = cut - 1;
+        const uint32_t rest = lane < 31 ? word >> (lane + 1) : 0u;
+        if (rest) e = p0 + lane + __ffs(rest) - 1;
+        else {
+          for (int q = p0 + 32; q < cut; q += 32) {
+            const uint32_t nw = w.mark[q >> 5];
+            if (nw) { e = q + __ffs(nw) - 2; break; }
+          }
+        }
+        wo.starts[rank] = wo.boff[p0 + lane];
+        wo.ends[rank] = sp_end_offset(wo.doc, wo.boff[e]);
+      }
+    }
     out += __popc(word);
   }
   return out;
 }
 
+template <bool kOff>
 __device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const ArcScratch& scratch, const uint8_t* text, int64_t lo0, int64_t hi,
-                           int64_t padded_bytes, int32_t* row, int max_ids, int unk, uint16_t delim, int lane) {
+                           int64_t padded_bytes, int32_t* row, int max_ids, int unk, uint16_t delim, int lane, const WinOffsets& wo) {
   const unsigned full = 0xffffffffu;
   const bool fast = m.tok_algo == kTokenizeBpeOpt || m.tok_algo == kTokenizeBpeOptWithMerges;
   int64_t lo = lo0;
@@ -450,7 +469,10 @@ __device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const ArcScratch
   int fill = 0, out = 0, last_delim = 0;
   bool prior = false;                                          // an earlier window has been emitted
   unsigned carry = 0;                                          // the previous raw symbol is white, or the dummy prefix
-  if (!m.no_dummy_prefix) { if (lane == 0) w.sym[0] = delim; fill = 1; carry = 1; }   // (:1372,:1387)
+  if (!m.no_dummy_prefix) {                                    // (:1372,:1387)
+    if (lane == 0) { w.sym[0] = delim; if constexpr (kOff) wo.boff[0] = -1; }
+    fill = 1; carry = 1;
+  }
   int64_t bpos = lo;
   for (;;) {
     // ---- fill: whitespace -> U+2581, a white symbol survives iff its predecessor is neither (:1462-1496) ----
@@ -477,6 +499,7 @@ __device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const ArcScratch
         if ((keep >> k) & 1u) {
           const bool wh = (white >> k) & 1u;
           w.sym[o] = wh ? delim : __ldg(m.sym_of_cp + ((word >> (8 * k)) & 0xFFu));
+          if constexpr (kOff) wo.boff[o] = (int)(pos0 + k - lo0);
           if (wh) my_last = o;
           ++o;
         }
@@ -520,7 +543,7 @@ __device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const ArcScratch
       cut = best; open_ended = true;
     }
     if (cut > 0) {
-      out = bpe_window(m, w, scratch, cut, delim, row, out, max_ids, unk, fast, open_ended, lane);
+      out = bpe_window<kOff>(m, w, scratch, cut, delim, row, out, max_ids, unk, fast, open_ended, lane, wo);
       if (out == kUFallback) return kUFallback;
       if (out >= max_ids) return max_ids;
     }
@@ -530,8 +553,11 @@ __device__ int sp_bpe_fast(const SpModelDev& m, const BWork& w, const ArcScratch
     for (int i0 = 0; i0 < rest; i0 += 32) {
       const int i = i0 + lane;
       const uint16_t v = i < rest ? w.sym[cut + i] : (uint16_t)0;
+      int bv = 0;
+      if constexpr (kOff) { if (i < rest) bv = wo.boff[cut + i]; }
       __syncwarp();
       if (i < rest) w.sym[i] = v;
+      if constexpr (kOff) { if (i < rest) wo.boff[i] = bv; }
       __syncwarp();
     }
     fill = rest; last_delim = 0; prior = true;

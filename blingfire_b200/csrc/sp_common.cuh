@@ -216,6 +216,22 @@ __device__ int sp_emit(const Work& w, const int32_t* idsrc, int N, int32_t* row,
   return out < max_ids ? out : max_ids;
 }
 
+// TextToIdsWithOffsets_sp (blingfiretokdll.cpp:1519-1529) on the fast paths: where the byte offsets of the window's symbols
+// live and where those of the tokens go.  Only the kOff = true instantiations touch it.
+struct WinOffsets {
+  int32_t* boff;       // byte offset (from the document start) of every symbol of the window, -1 = dummy prefix; the warp's own
+                       // global scratch (the tail of its arena), so that the shared-memory layouts stay what they are
+  const uint8_t* doc;  // first byte of the document
+  int32_t* starts;     // rows parallel to the ids row
+  int32_t* ends;
+};
+// the end offset of a token whose last symbol sits at byte to_off (:1527): the last byte of that character.  A token that is
+// only the dummy prefix has to_off == -1 (the reference reads the byte before the input): size 0, like sp_emit
+__device__ __forceinline__ int sp_end_offset(const uint8_t* doc, int to_off) {
+  const int cs = to_off < 0 ? 0 : sp_utf8_size_of_lead(doc[to_off]);
+  return to_off + (cs > 0 ? cs - 1 : 0);
+}
+
 constexpr int kUFallback = -2;   // the document does not fit a fast path: the caller takes sp_doc_generic
 
 }  // namespace

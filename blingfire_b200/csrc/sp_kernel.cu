@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(kBWarps * 32, kBCtasPerSm) sp_bpe_kernel(const
     if (n > 0 && n <= 1000000000) {                                       // :1362
       result = kUFallback;
       if (fast_model)
-        result = sp_bpe_fast(m, w, scratch, p.text, lo, hi, padded_bytes, p.ids + doc * (int64_t)p.max_ids, p.max_ids, p.unk_id, delim, lane);
+        result = sp_bpe_fast<false>(m, w, scratch, p.text, lo, hi, padded_bytes, p.ids + doc * (int64_t)p.max_ids, p.max_ids, p.unk_id, delim, lane,
+                                    WinOffsets{});
       if (result == kUFallback)
         result = sp_doc_generic<true>(p, m, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
     }
@@ -107,7 +108,54 @@ __global__ void __launch_bounds__(kUWarps * 32, kUCtasPerSm) sp_unigram_kernel(c
   }
 }
 
-// TextToIdsWithOffsets_sp for the Unigram family: the one-window fast path with the byte offsets carried along (in the head of
+static_assert(4 * kBWin <= kSpOffsetsTailBytes && 4 * kUCap <= kSpOffsetsTailBytes, "the window's byte offsets live in the arena tail");
+
+// TextToIdsWithOffsets_sp for the BPE family: sp_bpe_kernel with the byte offsets of the window's symbols carried along (in the
+// tail of the warp's arena).  A kernel of its own, so that sp_bpe_kernel stays what it is.
+__global__ void __launch_bounds__(kBWarps * 32, kBCtasPerSm) sp_bpe_offsets_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
+#ifdef BF_SIMT_HOST                        // tests/simt: the kernel source on the CPU
+  uint8_t* smem = simt::shared_base();
+#else
+  extern __shared__ __align__(16) uint8_t smem[];
+#endif
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * kBWarps + warp;
+  uint8_t* my_arena = p.arena + (size_t)gwarp * p.arena_stride;
+  Work wa = make_work(my_arena, p.arena_cap, true);
+  const ArcScratch scratch = make_scratch(p, my_arena, error_flag);
+  const BWork w = make_bwork(smem + (size_t)warp * kBWorkBytes, reinterpret_cast<uint8_t*>(scratch.priv));
+  const int64_t padded_bytes = (p.text_bytes + 3) & ~(int64_t)3;
+  const uint16_t delim = __ldg(m.sym_of_cp + kSpDelim);
+  const bool fast_model = m.use_raw_bytes && m.norm_count == nullptr && !m.delim_inside_tokens && m.bpe_ord != nullptr && delim != kNoSym;
+  for (;;) {
+    unsigned long long d64 = 0;
+    if (lane == 0) d64 = atomicAdd(p.work_counter, 1ull);
+    d64 = __shfl_sync(0xffffffffu, d64, 0);
+    if ((int64_t)d64 >= p.ndocs) break;
+    const int64_t doc = (int64_t)d64;
+    const int64_t lo = __ldg(p.offsets + doc), hi = __ldg(p.offsets + doc + 1);
+    const int64_t n = hi - lo;
+    int result = 0;
+    if (n > 0 && n <= 1000000000) {                                       // :1362
+      result = kUFallback;
+      if (fast_model) {
+        WinOffsets wo;
+        wo.boff = reinterpret_cast<int32_t*>(my_arena + p.arena_stride - kSpOffsetsTailBytes);
+        wo.doc = p.text + lo;
+        wo.starts = p.starts + doc * (int64_t)p.max_ids;
+        wo.ends = p.ends + doc * (int64_t)p.max_ids;
+        result = sp_bpe_fast<true>(m, w, scratch, p.text, lo, hi, padded_bytes, p.ids + doc * (int64_t)p.max_ids, p.max_ids, p.unk_id, delim, lane, wo);
+        __syncwarp();
+      }
+      if (result == kUFallback)
+        result = sp_doc_generic<true>(p, m, wa, scratch, doc, lo, hi, padded_bytes, lane, error_flag);
+    }
+    if (lane == 0) p.counts[doc] = result;
+    __syncwarp();
+  }
+}
+
+// TextToIdsWithOffsets_sp for the Unigram family: the one-window fast path with the byte offsets carried along (in the tail of
 // the warp's arena), sp_doc_generic for what does not fit it.  A kernel of its own, so that sp_unigram_kernel stays what it is.
 __global__ void __launch_bounds__(kUWarps * 32, kUCtasPerSm) sp_unigram_offsets_kernel(const SpLaunch p, const SpModelDev m, int* error_flag) {
 #ifdef BF_SIMT_HOST                        // tests/simt: the kernel source on the CPU
@@ -135,8 +183,8 @@ __global__ void __launch_bounds__(kUWarps * 32, kUCtasPerSm) sp_unigram_offsets_
     if (n > 0 && n <= 1000000000) {                                       // :1362
       result = kUFallback;
       if (fast_model && n <= 4ll * kUCap) {                               // a code point takes at most 4 bytes
-        UOff uo;
-        uo.boff = reinterpret_cast<int32_t*>(my_arena);                   // >= 64 KB per warp (sp_arena_bytes_per_warp)
+        WinOffsets uo;
+        uo.boff = reinterpret_cast<int32_t*>(my_arena + p.arena_stride - kSpOffsetsTailBytes);
         uo.doc = p.text + lo;
         uo.starts = p.starts + doc * (int64_t)p.max_ids;
         uo.ends = p.ends + doc * (int64_t)p.max_ids;
@@ -154,7 +202,7 @@ __global__ void __launch_bounds__(kUWarps * 32, kUCtasPerSm) sp_unigram_offsets_
 }  // namespace
 
 int64_t sp_arena_bytes_per_warp(int cap, int) {
-  return align16(work_bytes_arena(cap) + 16ll * ((int64_t)cap * kArcsPerSym + 4096) + 256);
+  return align16(work_bytes_arena(cap) + 16ll * ((int64_t)cap * kArcsPerSym + 4096) + 256) + kSpOffsetsTailBytes;
 }
 
 int64_t sp_overflow_entries(int cap, int max_arc_len) {
@@ -193,9 +241,9 @@ cudaError_t sp_tokenize_launch(const SpLaunch& p, const SpModelDev& m, cudaStrea
   const bool bpe = is_bpe_algo(m.tok_algo);
   const int cta_warps = bpe ? kBWarps : kUWarps;
   const size_t smem = bpe ? (size_t)kBWarps * kBWorkBytes : (size_t)kUWarps * kUWorkBytes;
-  const int which = bpe ? 1 : (p.starts != nullptr ? 2 : 0);
-  auto kern = bpe ? sp_bpe_kernel : (which == 2 ? sp_unigram_offsets_kernel : sp_unigram_kernel);
-  static thread_local int attr_dev[3] = {-1, -1, -1};           // the attribute is set once per (thread, device, kernel)
+  const int which = (bpe ? 1 : 0) + (p.starts != nullptr ? 2 : 0);
+  auto kern = which == 0 ? sp_unigram_kernel : which == 1 ? sp_bpe_kernel : which == 2 ? sp_unigram_offsets_kernel : sp_bpe_offsets_kernel;
+  static thread_local int attr_dev[4] = {-1, -1, -1, -1};       // the attribute is set once per (thread, device, kernel)
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;

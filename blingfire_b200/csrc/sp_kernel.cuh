@@ -76,7 +76,9 @@ struct SpLaunch {
 // arc entries the shared overflow region must hold for documents of up to `cap` symbols
 int64_t sp_overflow_entries(int cap, int max_arc_len);
 
-// bytes of arena one warp needs to process documents of up to `cap` symbols
+// bytes of arena one warp needs to process documents of up to `cap` symbols; its last kSpOffsetsTailBytes hold the byte
+// offsets of the fast paths' window when offsets are asked for (sp_*_offsets_kernel)
+constexpr int kSpOffsetsTailBytes = 4096;
 int64_t sp_arena_bytes_per_warp(int cap, int max_arc_len);
 // preferred number of warps in the grid on the current device
 int sp_preferred_warps(int tok_algo);

@@ -49,23 +49,13 @@ __device__ inline UWork make_uwork(uint8_t* b) {
   return w;
 }
 
-// TextToIdsWithOffsets_sp (blingfiretokdll.cpp:1519-1529) on the one-window form: where the byte offsets of one document
-// live and go.  Only the kOff = true instantiations touch it.
-struct UOff {
-  int32_t* boff;       // [kUCap] byte offset (from the document start) of every symbol, -1 = dummy prefix; the warp's own
-                       // global scratch (the head of its arena), so that the shared-memory layout stays the one above
-  const uint8_t* doc;  // first byte of the document
-  int32_t* starts;     // rows parallel to the ids row
-  int32_t* ends;
-};
-
 
 // Best path over the window's symbols sym[0..N) (FATokenSegmentationTools_1best_t.h:174-279); the ids
 // of its tokens are appended to row[out..).  *carry is the best score of the position before the
 // window on entry and of position N-1 on exit.  Returns the new out.
 template <bool kOff>
 __device__ int unigram_window(const SpModelDev& m, const UWork& w, int N, double* carry, int32_t* row, int out, int max_ids,
-                              int unk, int lane, const UOff& uo) {
+                              int unk, int lane, const WinOffsets& uo) {
   const unsigned full = 0xffffffffu;
   int32_t* bid = w.stage;
   for (int i = lane; i < kUCap / 32; i += 32) w.mark[i] = 0;
@@ -164,10 +154,7 @@ __device__ int unigram_window(const SpModelDev& m, const UWork& w, int N, double
         int b = w.begin[p0 + lane];
         if (b == kUNoBegin) b = 0;                             // never-set arc: emitted as the token from symbol 0
         uo.starts[rank] = uo.boff[b];
-        const int to_off = uo.boff[p0 + lane];
-        // a token that is only the dummy prefix has to_off == -1 (:1527 reads the byte before the input): size 0, like sp_emit
-        const int cs = to_off < 0 ? 0 : sp_utf8_size_of_lead(uo.doc[to_off]);
-        uo.ends[rank] = to_off + (cs > 0 ? cs - 1 : 0);
+        uo.ends[rank] = sp_end_offset(uo.doc, uo.boff[p0 + lane]);
       }
     }
     out += __popc(word);
@@ -179,7 +166,7 @@ __device__ int unigram_window(const SpModelDev& m, const UWork& w, int N, double
 // kUFallback when it has more than kUCap symbols after the charmap (the streamed form takes over).
 template <bool kOff>
 __device__ int unigram_whole(const SpModelDev& m, const UWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
-                             int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane, const UOff& uo) {
+                             int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane, const WinOffsets& uo) {
   const unsigned full = 0xffffffffu;
   int64_t lo = lo0;
   if (hi - lo >= 3) {
@@ -424,7 +411,7 @@ __device__ int unigram_streamed(const SpModelDev& m, const UWork& w, const uint8
       cut = best;
     }
     if (cut > 0) {
-      out = unigram_window<false>(m, w, cut, &carry, row, out, max_ids, unk, lane, UOff{});
+      out = unigram_window<false>(m, w, cut, &carry, row, out, max_ids, unk, lane, WinOffsets{});
       if (out >= max_ids) {
         // the ids are complete, but an invalid byte or a charmap overflow later in the document must
         // still yield 0 (:1409, :1442-1446)
@@ -472,7 +459,7 @@ __device__ int unigram_streamed(const SpModelDev& m, const UWork& w, const uint8
 __device__ int sp_unigram_fast(const SpModelDev& m, const UWork& w, const uint8_t* text, int64_t lo0, int64_t hi,
                                int64_t padded_bytes, int32_t* row, int max_ids, int unk, int lane) {
   if (hi - lo0 <= 4ll * kUCap) {                               // a code point takes at most 4 bytes
-    const int r = unigram_whole<false>(m, w, text, lo0, hi, padded_bytes, row, max_ids, unk, lane, UOff{});
+    const int r = unigram_whole<false>(m, w, text, lo0, hi, padded_bytes, row, max_ids, unk, lane, WinOffsets{});
     if (r != kUFallback) return r;
   }
   return unigram_streamed(m, w, text, lo0, hi, padded_bytes, row, max_ids, unk, lane);

@@ -52,7 +52,7 @@ void spsim_free(void* h) { delete (SpSim*)h; }
 const char* spsim_error(void* h) { return ((SpSim*)h)->err.c_str(); }
 
 // The batch through the kernel source: ids [ndocs][max_ids], counts [ndocs]; with starts/ends the offsets too
-// (the general path for BPE models, sp_unigram_offsets_kernel for Unigram models).  `warps` lane groups pull documents from the shared counter, like a (tiny)
+// (sp_bpe_offsets_kernel / sp_unigram_offsets_kernel).  `warps` lane groups pull documents from the shared counter, like a (tiny)
 // persistent grid of one CTA.  Returns the kernel's error flag (0 = fine), -1 on bad arguments.
 int spsim_batch(void* h, const char* text, const int64_t* offsets, int64_t ndocs, int32_t* ids, int32_t* counts,
                 int32_t* starts, int32_t* ends, int max_ids, int unk, int warps) {
@@ -89,8 +89,8 @@ int spsim_batch(void* h, const char* text, const int64_t* offsets, int64_t ndocs
   blockDim.x = (unsigned)cta_warps * 32; gridDim.x = 1;
   const size_t smem = bpe ? (size_t)kBWarps * kBWorkBytes : (size_t)kUWarps * kUWorkBytes;
   simt::run_cta(warps, smem, [&] {
-    if (bpe) sp_bpe_kernel(X, m, err);
-    else if (starts) sp_unigram_offsets_kernel(X, m, err);      // sp_tokenize_launch's choice
+    if (bpe) { if (starts) sp_bpe_offsets_kernel(X, m, err); else sp_bpe_kernel(X, m, err); }      // sp_tokenize_launch's choice
+    else if (starts) sp_unigram_offsets_kernel(X, m, err);
     else sp_unigram_kernel(X, m, err);
   });
   return *err;

@@ -141,6 +141,12 @@ def test_offsets_batch_vs_oracle(bf, name, unk):
     sid, sst, sen, soff = bf.text_to_ids_with_offsets_batch_csr(h, docs, 300, unk)
     assert len(bid) == reps * len(sid) and (np.diff(boff) == np.tile(np.diff(soff), reps)).all()
     assert (bid == np.tile(sid, reps)).all() and (bst == np.tile(sst, reps)).all() and (ben == np.tile(sen, reps)).all()
+    # more chunks than the call keeps in flight (a wide row makes a chunk hold few documents): the slots are reused
+    reps = 5 * (16 << 20) // (len(docs) * 2048) + 2
+    bid, bst, ben, boff = bf.text_to_ids_with_offsets_batch_csr(h, docs * reps, 2048, unk)
+    sid, sst, sen, soff = bf.text_to_ids_with_offsets_batch_csr(h, docs, 2048, unk)
+    assert len(bid) == reps * len(sid) and (np.diff(boff) == np.tile(np.diff(soff), reps)).all()
+    assert (bid == np.tile(sid, reps)).all() and (bst == np.tile(sst, reps)).all() and (ben == np.tile(sen, reps)).all()
     # too small a capacity: the need comes back negated, the offsets are complete
     L = bf.lib()
     buf, offs = bf.make_csr(docs)

@@ -122,12 +122,16 @@ def test_kernel_source_long_documents(sim, name, unk):
     check(sim, name, docs[::2], 37, unk)
 
 
-@pytest.mark.parametrize("name,unk", [("xlm_roberta_base.bin", 3), ("xlnet.bin", 0), ("laser100k.bin", 1), ("gpt2.bin", 0),
+@pytest.mark.parametrize("name,unk", [("xlm_roberta_base.bin", 3), ("xlnet.bin", 0), ("laser100k.bin", 1), ("gpt2.bin", 0), ("roberta.bin", 3),
                                       ("bpe_example.bin", 1), ("xlnet_nonorm.bin", 0)])
 def test_kernel_source_offsets(sim, name, unk):
     """TextToIdsWithOffsets_sp: the byte offsets carried through -- sp_unigram_offsets_kernel (one-window fast path, the
-    general path behind it for documents of more than a window) for Unigram models, the general path for BPE models."""
+    general path behind it for documents of more than a window), sp_bpe_offsets_kernel (the sliding window: offsets slide
+    with the symbols; cuts at U+2581 and inside a run without one), the general path for the models neither serves."""
     docs = corpus_docs(7, 140)
+    lines = read_lines("test.txt")[:400]
+    docs += [b" ".join(lines[i:i + 30]) for i in range(0, 120, 30)] + [b"ab" * 700, b" a" * 300, b"=" * 700 + b" x",
+             b"supercalifragilisticexpialidocious antidisestablishmentarianism " * 12, b"\xef\xbb\xbf" + b"word " * 300]
     # around the window's capacity (576 symbols, the dummy prefix included), with and without a charmap expansion in it
     docs += [b"a" * k for k in (573, 574, 575, 576, 577)] + [("ab " * 191 + "ﬁ").encode(), ("é" * 574).encode(), ("é" * 577).encode(),
              ("word " * 500).encode(), b"\xef\xbb\xbf" + b"x y " * 140, b"  lead and trail  ", "\u3000ideographic\u3000space".encode(),
