@@ -2,7 +2,8 @@
 """Long-running differential fuzz of the kernel SOURCES over the SIMT shim (tests/simt) against the oracle, on the CPU:
 random joins of corpus lines, truncations, injected bytes, whitespace-free runs, runs of one character, random
 output caps, all [pos-dict] models and two WordPiece models.  Not part of the pytest suite (a round of 400
-documents takes minutes).  Usage: python tools/simt_fuzz.py [seed] [rounds]"""
+documents takes minutes).  Usage: python tools/simt_fuzz.py [seed] [rounds] [offsets]
+("offsets": the [pos-dict] models through sp_unigram_offsets_kernel / sp_bpe_offsets_kernel, ids + starts + ends)"""
 import sys, random, time
 import os as _os
 sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), 'tests'))
@@ -40,13 +41,14 @@ def docs(n):
         out.append(d)
     return out
 sp=load_sp(); wp=load_wp()
+with_offsets = "offsets" in sys.argv[3:]
 t0=time.time(); nd=0
 for rnd in range(int(sys.argv[2]) if len(sys.argv)>2 else 3):
     D=docs(400)
     for name,unk in T.SP_MODELS:
         for max_ids in (2048, rng.choice([1,3,17,64])):
-            T.check(sp, name, D, max_ids, unk)
-    for name in ["bert_base_tok.bin","bert_chinese.bin"]:
+            T.check(sp, name, D, max_ids, unk, offsets=with_offsets)
+    for name in ([] if with_offsets else ["bert_base_tok.bin","bert_chinese.bin"]):
         T.check_wp(wp, name, D, 1024); T.check_wp(wp, name, D[:150], rng.choice([1,2,9]))
     nd+=len(D); print("round",rnd,"docs",nd,"%.0fs"%(time.time()-t0), flush=True)
 print("OK")
