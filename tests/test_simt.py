@@ -128,7 +128,7 @@ def test_kernel_source_offsets(sim, name, unk):
     """TextToIdsWithOffsets_sp: the byte offsets carried through -- sp_unigram_offsets_kernel (one-window fast path, the
     general path behind it for documents of more than a window), sp_bpe_offsets_kernel (the sliding window: offsets slide
     with the symbols; cuts at U+2581 and inside a run without one), the general path for the models neither serves."""
-    docs = corpus_docs(7, 140)
+    docs = corpus_docs(7, 70)
     lines = read_lines("test.txt")[:400]
     docs += [b" ".join(lines[i:i + 30]) for i in range(0, 120, 30)] + [b"ab" * 700, b" a" * 300, b"=" * 700 + b" x",
              b"supercalifragilisticexpialidocious antidisestablishmentarianism " * 12, b"\xef\xbb\xbf" + b"word " * 300]
