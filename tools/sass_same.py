@@ -28,6 +28,7 @@ def kernel_sass(lib, name):
         if res:
             labels = {}
             res = [re.sub(r"\.L_x_\d+", lambda m: labels.setdefault(m.group(0), f".L{len(labels)}"), l) for l in res]
+            res = [re.sub(r"\$__internal_\d+_", "$__internal_N_", l) for l in res]      # the compiler's numbering of its helpers
             return [re.sub(r"\s+", " ", l).strip() for l in res]
     raise SystemExit(f"{name}: not found in {lib}")
 
